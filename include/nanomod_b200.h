@@ -1,0 +1,122 @@
+/* nanomod_b200.h -- C ABI of the B200-native NanoMod detection stage.
+ *
+ * One call = the reference's `mfilter_coverage(moptions); mtest2(moptions)` pair
+ * (bin/scripts/myDetect.py:639-641; the functions at :301-314 and :416-457) up to, but not
+ * including, ranking and text formatting, which stay on the host side of this boundary.
+ * The reference has no FFI of its own: it calls scipy in-process.  The entry points below are
+ * what a ctypes binding for that seam binds; INTEGRATION.md shows the stub.
+ *
+ * Plain C types only.  All buffers are caller-owned; the library owns only its scratch
+ * memory and (for the *_host entry) its staging buffers, both inside the handle.
+ */
+#ifndef NANOMOD_B200_H
+#define NANOMOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_VERSION 100 /* 0.1.0 */
+
+/* status codes (0 = ok).  nm_last_error(h) gives the text of the most recent failure. */
+enum {
+  NM_OK = 0,
+  NM_ERR_BAD_ARG = 1,    /* null pointer, negative size, misaligned vals pointer ...          */
+  NM_ERR_BAD_PARAM = 2,  /* option outside the reference's accepted range (NanoMod.py:66,74) */
+  NM_ERR_CUDA = 3,       /* a CUDA runtime call failed                                       */
+  NM_ERR_OOM = 4,        /* device or pinned-host allocation failed                          */
+  NM_ERR_TOO_DEEP = 5,   /* a position's coverage exceeds the deep tier's shared-memory cap  */
+  NM_ERR_NO_DEVICE = 6   /* no CUDA device / not an sm_100 device                            */
+};
+
+/* combination methods: bit mask.  testMethod 'ks' == NM_COMBINE_NONE (myDetect.py:443),
+ * 'fisher' (:392-393), 'stouffer' (:395-401).  Both bits may be set (BASELINE cfg 3). */
+enum { NM_COMBINE_NONE = 0, NM_COMBINE_FISHER = 1, NM_COMBINE_STOUFFER = 2 };
+
+#define NM_MAX_NB 32          /* largest neighborPvalues the combine kernel accepts */
+#define NM_LANE_TIER_MAX 128  /* coverage per group handled by the lane-per-position tier */
+#define NM_DEEP_TIER_MAX_POOLED 49152 /* pow2(n0)+pow2(n1) cap of the block-per-position tier */
+
+/* Options that reach the device (subset of `moptions`, read at myDetect.py:301-414).
+ * Names follow NanoMod.py:354-359. */
+typedef struct nm_params {
+  int32_t min_coverage;  /* MinCoverage      (default 5, must be >= 3: NanoMod.py:66)          */
+  int32_t nb;            /* neighborPvalues  (default 2, >= 0: NanoMod.py:74)                  */
+  double weights_dif;    /* WeightsDif       (default 2.0; values < 1 become 1.0: :77-78)      */
+  int32_t combine;       /* NM_COMBINE_* mask (testMethod)                                     */
+  int32_t want_u;        /* also compute mannwhitneyu (myDetect.py:331)                        */
+  int32_t want_t;        /* also compute Welch ttest_ind (myDetect.py:335)                     */
+  int32_t reserved;
+} nm_params;
+
+/* CSR pileup over n_pos candidate positions (the reference's
+ * moptions[ds]['norm_mean'][(chrom,strand)][pos] -> list, myDetect.py:569-572), positions in
+ * the reference's iteration order: sorted (chrom,strand), ascending pos (:421,429).
+ * valsG[offG[i] .. offG[i+1]) are the event means of group G (0 = wrkBase1, 1 = wrkBase2) at
+ * candidate i.  A position missing from a group simply has an empty slice.
+ * Requirements for the *_device entry: vals pointers 16-byte aligned and readable up to the
+ * next multiple of 4 floats past offG[n_pos] (nm_padded_len). */
+typedef struct nm_pileup {
+  const float* vals0;
+  const int64_t* off0; /* [n_pos + 1] */
+  const float* vals1;
+  const int64_t* off1; /* [n_pos + 1] */
+  const int32_t* pos;  /* [n_pos] 0-based reference coordinate                     */
+  const int32_t* seg;  /* [n_pos] id of the (chrom,strand) the position belongs to */
+  int64_t n_pos;
+} nm_pileup;
+
+/* Per-row outputs (SoA), each with capacity n_pos.  Row r is the r-th candidate that passes
+ * the coverage filter in BOTH groups (myDetect.py:301-314 + :428,431), i.e. row order ==
+ * order of moptions['sign_test'].  Pointers marked optional may be NULL. */
+typedef struct nm_table {
+  int32_t* row_pos_index; /* candidate index of the row                                      */
+  int32_t* n0;            /* len(group 0)                                                    */
+  int32_t* n1;            /* len(group 1)                                                    */
+  int32_t* ks_dnum;       /* max_x |c0(x)*n1 - c1(x)*n0| : exact integer KS numerator        */
+  double* ks_d;           /* optional: D = ks_dnum / (n0*n1)                                 */
+  double* ks_p;           /* kstwobign.sf((en+0.12+0.11/en)*D), clamped to >= DBL_MIN        */
+  int64_t* two_u;         /* want_u: 2*min(u1,u2), exact integer                             */
+  double* u_stat;         /* optional: U                                                     */
+  double* u_p;            /* want_u: one-sided normal-approximation p (scipy 1.2.1 default)  */
+  double* t_stat;         /* want_t: Welch t (group0 - group1)                               */
+  double* t_p;            /* want_t: two-sided p                                             */
+  double* fisher_stat;    /* NM_COMBINE_FISHER: -2 sum ln p over the window                  */
+  double* fisher_p;
+  double* stouffer_stat;  /* NM_COMBINE_STOUFFER: weighted Z                                 */
+  double* stouffer_p;
+  uint8_t* flags;         /* optional: bit0 = all pooled values identical (U p is NaN)       */
+} nm_table;
+
+typedef struct nm_handle nm_handle;
+
+int nm_version(void);
+/* Number of floats a vals buffer must have allocated to hold nvals values. */
+int64_t nm_padded_len(int64_t nvals);
+
+/* One handle per GPU and per thread of use; calls on one handle must be serialised. */
+int nm_create(int device, nm_handle** out);
+void nm_destroy(nm_handle* h);
+const char* nm_last_error(const nm_handle* h);
+
+/* Device-resident entry: every pointer in `pileup` and `table` is a device pointer on the
+ * handle's GPU.  Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream);
+ * the call synchronises that stream once internally (to size its grids) and once more before
+ * returning, so outputs are complete on return.  *n_rows receives the number of rows. */
+int nm_detect_device(nm_handle* h, const nm_pileup* pileup, const nm_params* params,
+                     const nm_table* table, int64_t* n_rows, void* cuda_stream);
+
+/* Host entry: every pointer is host memory (pinned memory makes the copies asynchronous).
+ * Copies the pileup to the GPU, runs nm_detect_device, copies the n_rows result rows back. */
+int nm_detect_host(nm_handle* h, const nm_pileup* pileup, const nm_params* params,
+                   const nm_table* table, int64_t* n_rows);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t nm_launch_count(const nm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOMOD_B200_H */

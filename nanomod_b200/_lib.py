@@ -1,0 +1,139 @@
+"""ctypes binding of include/nanomod_b200.h (the C ABI in nanomod_b200/_C/libnanomod_b200.so).
+
+There is no fallback: if the shared library has not been built (``python -m nanomod_b200.build``
+or ``__graft_entry__.build()``) or no sm_100 GPU is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libnanomod_b200.so")
+
+NM_OK = 0
+NM_COMBINE_NONE, NM_COMBINE_FISHER, NM_COMBINE_STOUFFER = 0, 1, 2
+NM_MAX_NB = 32
+NM_LANE_TIER_MAX = 128
+
+ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: "NM_ERR_OOM",
+               5: "NM_ERR_TOO_DEEP", 6: "NM_ERR_NO_DEVICE"}
+
+# every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count"]
+
+
+class NmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (%d): %s" % (ERROR_NAMES.get(code, "NM_ERR_?"), code, msg))
+        self.code = code
+
+
+class nm_params(C.Structure):
+    _fields_ = [("min_coverage", C.c_int32), ("nb", C.c_int32), ("weights_dif", C.c_double),
+                ("combine", C.c_int32), ("want_u", C.c_int32), ("want_t", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class nm_pileup(C.Structure):
+    _fields_ = [("vals0", C.c_void_p), ("off0", C.c_void_p), ("vals1", C.c_void_p),
+                ("off1", C.c_void_p), ("pos", C.c_void_p), ("seg", C.c_void_p),
+                ("n_pos", C.c_int64)]
+
+
+TABLE_FIELDS = ["row_pos_index", "n0", "n1", "ks_dnum", "ks_d", "ks_p", "two_u", "u_stat", "u_p",
+                "t_stat", "t_p", "fisher_stat", "fisher_p", "stouffer_stat", "stouffer_p", "flags"]
+TABLE_DTYPES = {"row_pos_index": "int32", "n0": "int32", "n1": "int32", "ks_dnum": "int32",
+                "ks_d": "float64", "ks_p": "float64", "two_u": "int64", "u_stat": "float64",
+                "u_p": "float64", "t_stat": "float64", "t_p": "float64", "fisher_stat": "float64",
+                "fisher_p": "float64", "stouffer_stat": "float64", "stouffer_p": "float64",
+                "flags": "uint8"}
+
+
+class nm_table(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in TABLE_FIELDS]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "nanomod_b200: %s is missing -- build it with `python -m nanomod_b200.build` "
+            "(needs nvcc).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.nm_version.restype = C.c_int
+    lib.nm_padded_len.restype = C.c_int64
+    lib.nm_padded_len.argtypes = [C.c_int64]
+    lib.nm_create.restype = C.c_int
+    lib.nm_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.nm_destroy.restype = None
+    lib.nm_destroy.argtypes = [C.c_void_p]
+    lib.nm_last_error.restype = C.c_char_p
+    lib.nm_last_error.argtypes = [C.c_void_p]
+    lib.nm_launch_count.restype = C.c_int64
+    lib.nm_launch_count.argtypes = [C.c_void_p]
+    lib.nm_detect_device.restype = C.c_int
+    lib.nm_detect_device.argtypes = [C.c_void_p, C.POINTER(nm_pileup), C.POINTER(nm_params),
+                                     C.POINTER(nm_table), C.POINTER(C.c_int64), C.c_void_p]
+    lib.nm_detect_host.restype = C.c_int
+    lib.nm_detect_host.argtypes = [C.c_void_p, C.POINTER(nm_pileup), C.POINTER(nm_params),
+                                   C.POINTER(nm_table), C.POINTER(C.c_int64)]
+    _lib = lib
+    return lib
+
+
+def padded_len(nvals: int) -> int:
+    """Floats a vals buffer must have allocated for nvals values (nm_padded_len)."""
+    return (int(nvals) + 3) // 4 * 4 + 4
+
+
+class Handle:
+    """Owns one nm_handle (one GPU).  Not thread-safe; use one per thread / rank."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        rc = self._lib.nm_create(int(device), C.byref(self._h))
+        if rc != NM_OK:
+            raise NmError(rc, self._lib.nm_last_error(None).decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.nm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != NM_OK:
+            raise NmError(rc, self._lib.nm_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.nm_launch_count(self._h))
+
+    def detect_host(self, pileup: nm_pileup, params: nm_params, table: nm_table) -> int:
+        n_rows = C.c_int64(0)
+        self._check(self._lib.nm_detect_host(self._h, C.byref(pileup), C.byref(params),
+                                             C.byref(table), C.byref(n_rows)))
+        return int(n_rows.value)
+
+    def detect_device(self, pileup: nm_pileup, params: nm_params, table: nm_table,
+                      stream: int = 0) -> int:
+        n_rows = C.c_int64(0)
+        self._check(self._lib.nm_detect_device(self._h, C.byref(pileup), C.byref(params),
+                                               C.byref(table), C.byref(n_rows),
+                                               C.c_void_p(int(stream))))
+        return int(n_rows.value)

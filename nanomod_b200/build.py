@@ -1,0 +1,68 @@
+"""Build nanomod_b200/_C/libnanomod_b200.so in-tree with nvcc for sm_100a.
+
+Used by ``__graft_entry__.build()`` and by developers (``python -m nanomod_b200.build``).
+The two translation units compile in parallel; an object is rebuilt only when one of its
+sources is newer.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_C")
+LIB = os.path.join(OUT_DIR, "libnanomod_b200.so")
+UNITS = ["nm_api.cu", "nm_lane_kernel.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _deps():
+    inc = os.path.join(HERE, "..", "include", "nanomod_b200.h")
+    return [inc] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                    if f.endswith((".cuh", ".inc", ".h"))]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _compile(unit, force):
+    src = os.path.join(CSRC, unit)
+    obj = os.path.join(OUT_DIR, unit.replace(".cu", ".o"))
+    if not force and not _stale(obj, [src] + _deps()):
+        return obj, ""
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, r.stdout, r.stderr))
+    return obj, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        results = list(ex.map(lambda u: _compile(u, force), UNITS))
+    objs = [o for o, _ in results]
+    log = "\n".join(l for _, l in results if l)
+    if log:
+        with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+            f.write(log)
+        if verbose:
+            print(log)
+    if force or _stale(LIB, objs):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

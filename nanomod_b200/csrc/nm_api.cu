@@ -1,0 +1,663 @@
+// nm_api.cu -- plan / deep / combine kernels and the C ABI of include/nanomod_b200.h.
+//
+// Stage map (reference: bin/scripts/myDetect.py):
+//   nm_plan_*          mfilter_coverage (:301-314) + the "present in both groups" rule of
+//                      mtest2 (:428,431): ordered compaction of candidate positions into rows.
+//   nm_lane_kernel     (nm_lane_kernel.cu) getKStest (:327-343), rows with <= 128 reads/group.
+//   nm_deep_kernel     the same statistics for deeper rows: one CTA per position, TMA bulk
+//                      load of the contiguous pileup slice, shared-memory bitonic sort, rank
+//                      counts by binary search.
+//   nm_combine_kernel  combin_pvalues / get_combin_pvalue / pos_check (:366-414).
+// There is no CPU path: every entry point fails with NM_ERR_NO_DEVICE / NM_ERR_CUDA when the
+// GPU is not usable.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nm_device.cuh"
+
+// ------------------------------------------------------------------------------------------
+// plan: coverage filter + ordered compaction (myDetect.py:301-314, :428-431)
+// ------------------------------------------------------------------------------------------
+#define NM_PLAN_THREADS 256
+#define NM_PLAN_PER_THREAD 4
+#define NM_PLAN_PER_BLOCK (NM_PLAN_THREADS * NM_PLAN_PER_THREAD)
+
+// exclusive scan of one int per thread over a 256-thread block; returns block total in *total
+__device__ __forceinline__ int nm_block_excl_scan(int v, int* total) {
+  __shared__ int warp_tot[NM_PLAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NM_PLAN_THREADS / 32; ++w) {
+    const int t = warp_tot[w];
+    if (w < wid) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(NM_PLAN_THREADS)
+nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1, int64_t n_pos,
+              int mincov, int* __restrict__ block_count, nm_summary* __restrict__ sum) {
+  const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
+  int cnt = 0, max_lane = 0, n_deep = 0, max_deep = 0;
+#pragma unroll
+  for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
+    const int64_t p = p0 + k;
+    if (p < n_pos) {
+      const int64_t n0 = off0[p + 1] - off0[p];
+      const int64_t n1 = off1[p + 1] - off1[p];
+      if (n0 >= mincov && n1 >= mincov) {
+        ++cnt;
+        const int64_t m = n0 > n1 ? n0 : n1;
+        if (m <= NM_LANE_TIER_MAX) {
+          max_lane = max_lane > (int)m ? max_lane : (int)m;
+        } else {
+          ++n_deep;
+          const int64_t cap = 1 << 24;
+          const int p2 = nm_pow2ceil((int)(n0 < cap ? n0 : cap)) + nm_pow2ceil((int)(n1 < cap ? n1 : cap));
+          max_deep = max_deep > p2 ? max_deep : p2;
+        }
+      }
+    }
+  }
+  int total;
+  (void)nm_block_excl_scan(cnt, &total);
+  max_lane = __reduce_max_sync(0xffffffffu, max_lane);
+  max_deep = __reduce_max_sync(0xffffffffu, max_deep);
+  n_deep = __reduce_add_sync(0xffffffffu, n_deep);
+  if ((threadIdx.x & 31) == 0) {
+    if (max_lane) atomicMax(&sum->max_lane_n, max_lane);
+    if (n_deep) {
+      atomicAdd(&sum->n_deep, n_deep);
+      atomicMax(&sum->max_deep_p2, max_deep);
+    }
+  }
+  if (threadIdx.x == 0) block_count[blockIdx.x] = total;
+}
+
+// single-block exclusive scan of the per-block counts (in place) + total row count
+__global__ void __launch_bounds__(NM_PLAN_THREADS)
+nm_plan_scan(int* __restrict__ block_count, int nblk, nm_summary* __restrict__ sum) {
+  __shared__ unsigned long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += NM_PLAN_THREADS) {
+    const int idx = base + threadIdx.x;
+    const int v = idx < nblk ? block_count[idx] : 0;
+    int total;
+    const int ex = nm_block_excl_scan(v, &total);
+    const unsigned long long carry = carry_s;
+    if (idx < nblk) block_count[idx] = (int)(carry + (unsigned long long)ex);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + (unsigned long long)total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sum->n_rows = carry_s;
+}
+
+__global__ void __launch_bounds__(NM_PLAN_THREADS)
+nm_plan_scatter(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1, int64_t n_pos,
+                int mincov, const int* __restrict__ block_offset, int32_t* __restrict__ row_pos_index,
+                int32_t* __restrict__ row_n0, int32_t* __restrict__ row_n1,
+                int32_t* __restrict__ deep_rows, nm_summary* __restrict__ sum) {
+  const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
+  int n0v[NM_PLAN_PER_THREAD], n1v[NM_PLAN_PER_THREAD];
+  bool keep[NM_PLAN_PER_THREAD];
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
+    const int64_t p = p0 + k;
+    keep[k] = false;
+    n0v[k] = n1v[k] = 0;
+    if (p < n_pos) {
+      const int64_t n0 = off0[p + 1] - off0[p];
+      const int64_t n1 = off1[p + 1] - off1[p];
+      keep[k] = (n0 >= mincov && n1 >= mincov);
+      n0v[k] = (int)(n0 < 0x7fffffff ? n0 : 0x7fffffff);
+      n1v[k] = (int)(n1 < 0x7fffffff ? n1 : 0x7fffffff);
+      cnt += keep[k] ? 1 : 0;
+    }
+  }
+  int total;
+  int r = block_offset[blockIdx.x] + nm_block_excl_scan(cnt, &total);
+#pragma unroll
+  for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
+    if (keep[k]) {
+      row_pos_index[r] = (int32_t)(p0 + k);
+      row_n0[r] = n0v[k];
+      row_n1[r] = n1v[k];
+      if (n0v[k] > NM_LANE_TIER_MAX || n1v[k] > NM_LANE_TIER_MAX) {
+        const int slot = atomicAdd(&sum->deep_cursor, 1);
+        deep_rows[slot] = r;
+      }
+      ++r;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// deep tier: one CTA per position
+// ------------------------------------------------------------------------------------------
+#define NM_DEEP_THREADS 256
+
+__device__ __forceinline__ void nm_block_bitonic(float* s, int P, int tid) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += NM_DEEP_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const float x = s[i], y = s[p];
+        const bool up = (i & k) == 0;
+        const float lo = fminf(x, y), hi = fmaxf(x, y);
+        s[i] = up ? lo : hi;
+        s[p] = up ? hi : lo;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NM_DEEP_THREADS) nm_deep_kernel(const nm_kargs a, const int want_u,
+                                                                  const int want_t) {
+  extern __shared__ __align__(128) unsigned char nm_smem[];
+  __shared__ double red_d[NM_DEEP_THREADS / 32];
+  __shared__ long long red_l[3][NM_DEEP_THREADS / 32];
+  __shared__ double bcast[2];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nm_smem);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  const int64_t r = a.deep_rows[blockIdx.x];
+  const int32_t src = a.row_pos_index[r];
+  const int n0 = a.row_n0[r], n1 = a.row_n1[r];
+  const long long s0 = a.off0[src], s1 = a.off1[src];
+  const int P0 = nm_pow2ceil(n0), P1 = nm_pow2ceil(n1);
+  const long long al0 = s0 & ~3LL, al1 = s1 & ~3LL;
+  const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
+  float* rawA = reinterpret_cast<float*>(nm_smem + 16);
+  float* rawB = rawA + P0 + 4;
+  float* sa = rawA + sh0;
+  float* sb = rawB + sh1;
+
+  // TMA bulk load of the two contiguous pileup slices
+  if (tid == 0) {
+    nm_mbar_init(bar, 1);
+    const uint32_t b0 = (uint32_t)((sh0 + n0 + 3) & ~3) * 4u;
+    const uint32_t b1 = (uint32_t)((sh1 + n1 + 3) & ~3) * 4u;
+    nm_mbar_expect_tx(bar, b0 + b1);
+    nm_bulk_g2s(rawA, a.vals0 + al0, b0, bar);
+    nm_bulk_g2s(rawB, a.vals1 + al1, b1, bar);
+  }
+  __syncthreads();
+  nm_mbar_wait(bar, 0);
+  __syncthreads();  // nobody pads before everyone has seen the copy complete
+  for (int k = n0 + tid; k < P0; k += NM_DEEP_THREADS) sa[k] = NM_INF;
+  for (int k = n1 + tid; k < P1; k += NM_DEEP_THREADS) sb[k] = NM_INF;
+
+  double mean[2] = {0.0, 0.0}, var[2] = {0.0, 0.0};
+  if (want_t) {
+    for (int g = 0; g < 2; ++g) {
+      const float* s = g ? sb : sa;
+      const int n = g ? n1 : n0;
+      double part = 0.0;
+      for (int k = tid; k < n; k += NM_DEEP_THREADS) part += (double)s[k];
+      part = nm_warp_sum_d(part);
+      if (lane == 0) red_d[wid] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
+        bcast[0] = t / (double)n;
+      }
+      __syncthreads();
+      const double m = bcast[0];
+      part = 0.0;
+      for (int k = tid; k < n; k += NM_DEEP_THREADS) {
+        const double d = (double)s[k] - m;
+        part += d * d;
+      }
+      part = nm_warp_sum_d(part);
+      __syncthreads();
+      if (lane == 0) red_d[wid] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
+        bcast[1] = t / (double)(n - 1);
+      }
+      __syncthreads();
+      mean[g] = m;
+      var[g] = bcast[1];
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  nm_block_bitonic(sa, P0, tid);
+  nm_block_bitonic(sb, P1, tid);
+
+  nm_deep_acc acc;
+  nm_deep_acc_init(&acc);
+  for (int e = tid; e < n0 + n1; e += NM_DEEP_THREADS) {
+    nm_deep_acc one;
+    nm_deep_acc_init(&one);
+    nm_deep_element(sa, n0, sb, n1, e, want_u != 0, &one);
+    nm_deep_acc_merge(&acc, one);
+  }
+  acc.dnum = nm_warp_max_ll(acc.dnum);
+  acc.r2 = nm_warp_sum_ll(acc.r2);
+  acc.tie = nm_warp_sum_ll(acc.tie);
+  if (lane == 0) {
+    red_l[0][wid] = acc.dnum;
+    red_l[1][wid] = acc.r2;
+    red_l[2][wid] = acc.tie;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    nm_deep_acc tot;
+    nm_deep_acc_init(&tot);
+    for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) {
+      nm_deep_acc one;
+      one.dnum = red_l[0][w];
+      one.r2 = red_l[1][w];
+      one.tie = red_l[2][w];
+      nm_deep_acc_merge(&tot, one);
+    }
+    nm_row_out o;
+    o.two_u = 0;
+    o.u_stat = o.u_p = o.t_stat = o.t_p = 0.0;
+    nm_deep_finish(tot, n0, n1, want_u != 0, want_t != 0, mean[0], var[0], mean[1], var[1], &o);
+    nm_store_row(a, r, o, want_u != 0, want_t != 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// combine: sliding-window Fisher / weighted Stouffer over the KS p-values (myDetect.py:366-414)
+// ------------------------------------------------------------------------------------------
+#define NM_COMB_THREADS 256
+
+struct nm_comb_args {
+  const double* ks_p;
+  const int32_t* ks_dnum;
+  const int32_t* row_pos_index;
+  const int32_t* row_n0;
+  const int32_t* row_n1;
+  const int32_t* pos;
+  const int32_t* seg;
+  int64_t n_rows;
+  int nb;
+  int want_fisher, want_stouffer;
+  double wnorm;
+  double w[NM_MAX_NB + 1];
+  double* f_stat;
+  double* f_p;
+  double* s_stat;
+  double* s_p;
+};
+
+struct nm_comb_win {
+  const double* z;
+  const double* lnp;
+  const int* pos;
+  const int* seg;
+  int c;  // index of the centre row inside the shared tile
+  __device__ __forceinline__ void operator()(int k, double* zo, double* lo) const {
+    const int j = c + k;
+    // a halo slot outside [0, n_rows) carries seg = -1 and never matches
+    const bool okk = (k == 0) || (seg[j] == seg[c] && pos[j] - pos[c] == k);
+    *zo = okk ? z[j] : -INFINITY;
+    *lo = okk ? lnp[j] : 0.0;
+  }
+};
+
+__global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_comb_args a) {
+  __shared__ double z_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
+  __shared__ double l_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
+  __shared__ int pos_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
+  __shared__ int seg_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
+  const int nb = a.nb;
+  const int64_t tile0 = (int64_t)blockIdx.x * NM_COMB_THREADS;
+  for (int t = threadIdx.x; t < NM_COMB_THREADS + 2 * nb; t += NM_COMB_THREADS) {
+    const int64_t r = tile0 - nb + t;
+    double z = -INFINITY, l = 0.0;
+    int ps = 0, sg = -1;
+    if (r >= 0 && r < a.n_rows) {
+      const double p = a.ks_p[r];
+      const int32_t src = a.row_pos_index[r];
+      ps = a.pos[src];
+      sg = a.seg[src];
+      if (a.want_stouffer) z = nm_norm_isf(p);
+      if (a.want_fisher) l = log(p);
+    }
+    z_s[t] = z;
+    l_s[t] = l;
+    pos_s[t] = ps;
+    seg_s[t] = sg;
+  }
+  __syncthreads();
+  const int64_t r = tile0 + threadIdx.x;
+  if (r >= a.n_rows) return;
+  if (nb == 0) {
+    // get_combin_pvalue returns the KS tuple itself when neighborPvalues == 0 (:413)
+    const double d = (double)a.ks_dnum[r] / ((double)a.row_n0[r] * (double)a.row_n1[r]);
+    const double p = a.ks_p[r];
+    if (a.want_fisher) { a.f_stat[r] = d; a.f_p[r] = p; }
+    if (a.want_stouffer) { a.s_stat[r] = d; a.s_p[r] = p; }
+    return;
+  }
+  const nm_comb_win W{z_s, l_s, pos_s, seg_s, (int)threadIdx.x + nb};
+  double fs = 0.0, fp = 0.0, ss = 0.0, sp = 0.0;
+  nm_combine_row(nb, a.w, a.wnorm, W, a.want_fisher != 0, a.want_stouffer != 0, &fs, &fp, &ss, &sp);
+  if (a.want_fisher) { a.f_stat[r] = fs; a.f_p[r] = fp; }
+  if (a.want_stouffer) { a.s_stat[r] = ss; a.s_p[r] = sp; }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: handle, scratch, C ABI
+// ------------------------------------------------------------------------------------------
+struct nm_buf {
+  void* p;
+  size_t cap;
+};
+
+struct nm_handle {
+  int device;
+  int sm_count;
+  cudaStream_t own_stream;
+  nm_summary* d_sum;
+  nm_summary* h_sum;  // pinned
+  nm_buf d_block_count, d_deep_rows;
+  // staging for nm_detect_host
+  nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
+  nm_buf d_out[16];
+  int64_t launches;
+  char err[512];
+};
+
+static char g_err[512] = "";
+
+static int nm_fail(nm_handle* h, int code, const char* fmt, ...) {
+  char* dst = h ? h->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define NM_CUDA(h, call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return nm_fail(h, e_ == cudaErrorMemoryAllocation ? NM_ERR_OOM : NM_ERR_CUDA,       \
+                     "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,    \
+                     __LINE__);                                                           \
+  } while (0)
+
+static int nm_reserve(nm_handle* h, nm_buf* b, size_t bytes) {
+  if (bytes <= b->cap) return NM_OK;
+  if (b->p) {
+    NM_CUDA(h, cudaFree(b->p));
+    b->p = nullptr;
+    b->cap = 0;
+  }
+  const size_t want = bytes + bytes / 8 + 256;
+  NM_CUDA(h, cudaMalloc(&b->p, want));
+  b->cap = want;
+  return NM_OK;
+}
+
+extern "C" int nm_version(void) { return NM_VERSION; }
+
+extern "C" int64_t nm_padded_len(int64_t nvals) { return (nvals + 3) / 4 * 4 + 4; }
+
+extern "C" const char* nm_last_error(const nm_handle* h) { return h ? h->err : g_err; }
+
+extern "C" int64_t nm_launch_count(const nm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nm_create(int device, nm_handle** out) {
+  if (!out) return nm_fail(nullptr, NM_ERR_BAD_ARG, "nm_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return nm_fail(nullptr, NM_ERR_NO_DEVICE, "nm_create: no CUDA device (%s)",
+                   e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev)
+    return nm_fail(nullptr, NM_ERR_BAD_ARG, "nm_create: device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return nm_fail(nullptr, NM_ERR_CUDA, "nm_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return nm_fail(nullptr, NM_ERR_NO_DEVICE,
+                   "nm_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                   device, prop.major, prop.minor);
+  nm_handle* h = (nm_handle*)calloc(1, sizeof(nm_handle));
+  if (!h) return nm_fail(nullptr, NM_ERR_OOM, "nm_create: out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  int rc = NM_OK;
+  do {
+    if (cudaSetDevice(device) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
+    if (cudaMalloc(&h->d_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
+    if (cudaMallocHost(&h->h_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
+  } while (0);
+  if (rc != NM_OK) {
+    nm_fail(nullptr, rc, "nm_create: CUDA set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    nm_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return NM_OK;
+}
+
+extern "C" void nm_destroy(nm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_vals0, &h->d_vals1,
+                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg};
+  for (nm_buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (nm_buf& b : h->d_out)
+    if (b.p) cudaFree(b.p);
+  if (h->d_sum) cudaFree(h->d_sum);
+  if (h->h_sum) cudaFreeHost(h->h_sum);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  free(h);
+}
+
+static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
+  if (!p) return nm_fail(h, NM_ERR_BAD_ARG, "params is NULL");
+  *eff = *p;
+  if (p->min_coverage < 3)  // NanoMod.py:66
+    return nm_fail(h, NM_ERR_BAD_PARAM, "The coverage (%d) is too small", p->min_coverage);
+  if (p->nb < 0)  // NanoMod.py:74
+    return nm_fail(h, NM_ERR_BAD_PARAM, "The neighborPvalues (%d) cannot be smaller than 0", p->nb);
+  if (p->nb > NM_MAX_NB)
+    return nm_fail(h, NM_ERR_BAD_PARAM, "neighborPvalues (%d) exceeds NM_MAX_NB (%d)", p->nb, NM_MAX_NB);
+  if (p->combine & ~(NM_COMBINE_FISHER | NM_COMBINE_STOUFFER))
+    return nm_fail(h, NM_ERR_BAD_PARAM, "unknown combine mask %d", p->combine);
+  if (!(p->weights_dif >= 1.0)) eff->weights_dif = 1.0;  // NanoMod.py:77-78
+  return NM_OK;
+}
+
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int lane_smem,
+                           int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+  if (n_rows > n_deep) {
+    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, lane_smem, st);
+    if (e != cudaSuccess)
+      return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+  }
+  if (n_deep > 0) {
+    NM_CUDA(h, cudaFuncSetAttribute(nm_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_smem));
+    nm_deep_kernel<<<(unsigned)n_deep, NM_DEEP_THREADS, deep_smem, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+    NM_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  return NM_OK;
+}
+
+extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_params* params,
+                                const nm_table* tb, int64_t* n_rows_out, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!pl || !tb || !n_rows_out) return nm_fail(h, NM_ERR_BAD_ARG, "pileup/table/n_rows is NULL");
+  nm_params prm;
+  int rc = nm_check_params(h, params, &prm);
+  if (rc != NM_OK) return rc;
+  const bool want_u = prm.want_u != 0, want_t = prm.want_t != 0;
+  const bool want_f = (prm.combine & NM_COMBINE_FISHER) != 0, want_s = (prm.combine & NM_COMBINE_STOUFFER) != 0;
+  if (pl->n_pos < 0 || pl->n_pos > 0x7fffffffLL - NM_PLAN_PER_BLOCK)
+    return nm_fail(h, NM_ERR_BAD_ARG, "n_pos (%lld) out of range", (long long)pl->n_pos);
+  *n_rows_out = 0;
+  if (pl->n_pos == 0) return NM_OK;
+  if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
+    return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
+  if ((((uintptr_t)pl->vals0) | ((uintptr_t)pl->vals1)) & 15)
+    return nm_fail(h, NM_ERR_BAD_ARG, "vals0/vals1 must be 16-byte aligned");
+  if (!tb->row_pos_index || !tb->n0 || !tb->n1 || !tb->ks_dnum || !tb->ks_p)
+    return nm_fail(h, NM_ERR_BAD_ARG, "table lacks a mandatory output (row_pos_index,n0,n1,ks_dnum,ks_p)");
+  if (want_u && (!tb->two_u || !tb->u_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_u needs two_u and u_p");
+  if (want_t && (!tb->t_stat || !tb->t_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_t needs t_stat and t_p");
+  if (want_f && (!tb->fisher_stat || !tb->fisher_p)) return nm_fail(h, NM_ERR_BAD_ARG, "fisher outputs missing");
+  if (want_s && (!tb->stouffer_stat || !tb->stouffer_p)) return nm_fail(h, NM_ERR_BAD_ARG, "stouffer outputs missing");
+
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t n_pos = pl->n_pos;
+  const int nblk = (int)((n_pos + NM_PLAN_PER_BLOCK - 1) / NM_PLAN_PER_BLOCK);
+  if ((rc = nm_reserve(h, &h->d_block_count, sizeof(int) * (size_t)nblk)) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_deep_rows, sizeof(int32_t) * (size_t)n_pos)) != NM_OK) return rc;
+
+  // ---- plan: filter + ordered compaction
+  NM_CUDA(h, cudaMemsetAsync(h->d_sum, 0, sizeof(nm_summary), st));
+  nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
+                                                  (int*)h->d_block_count.p, h->d_sum);
+  nm_plan_scan<<<1, NM_PLAN_THREADS, 0, st>>>((int*)h->d_block_count.p, nblk, h->d_sum);
+  nm_plan_scatter<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
+                                                    (const int*)h->d_block_count.p, tb->row_pos_index,
+                                                    tb->n0, tb->n1, (int32_t*)h->d_deep_rows.p, h->d_sum);
+  NM_CUDA(h, cudaGetLastError());
+  h->launches += 3;
+  NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  const nm_summary sum = *h->h_sum;
+  const int64_t n_rows = (int64_t)sum.n_rows;
+  *n_rows_out = n_rows;
+  if (n_rows == 0) return NM_OK;
+  if (sum.n_deep > 0 && sum.max_deep_p2 > NM_DEEP_TIER_MAX_POOLED)
+    return nm_fail(h, NM_ERR_TOO_DEEP,
+                   "a position has pow2(n0)+pow2(n1) = %d > %d values; deeper pileups are not supported",
+                   sum.max_deep_p2, NM_DEEP_TIER_MAX_POOLED);
+
+  // ---- per-position tests
+  nm_kargs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.vals0 = pl->vals0; ka.vals1 = pl->vals1; ka.off0 = pl->off0; ka.off1 = pl->off1;
+  ka.row_pos_index = tb->row_pos_index; ka.row_n0 = tb->n0; ka.row_n1 = tb->n1;
+  ka.n_rows = n_rows;
+  const int ncls = (sum.max_lane_n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 1);
+  ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
+  ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
+  ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
+  ka.deep_rows = (const int32_t*)h->d_deep_rows.p; ka.n_deep = sum.n_deep;
+  const int lane_smem = 16 + 2 * ka.region_floats * (int)sizeof(float);
+  const int deep_smem = 16 + (sum.max_deep_p2 + 8) * (int)sizeof(float);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, lane_smem, deep_smem, n_rows, sum.n_deep, st);
+  if (rc != NM_OK) return rc;
+
+  // ---- neighbour combination
+  if (want_f || want_s) {
+    nm_comb_args ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.ks_p = tb->ks_p; ca.ks_dnum = tb->ks_dnum; ca.row_pos_index = tb->row_pos_index;
+    ca.row_n0 = tb->n0; ca.row_n1 = tb->n1; ca.pos = pl->pos; ca.seg = pl->seg;
+    ca.n_rows = n_rows; ca.nb = prm.nb; ca.want_fisher = want_f; ca.want_stouffer = want_s;
+    ca.wnorm = nm_build_weights(prm.nb, prm.weights_dif, ca.w);
+    ca.f_stat = tb->fisher_stat; ca.f_p = tb->fisher_p; ca.s_stat = tb->stouffer_stat; ca.s_p = tb->stouffer_p;
+    const unsigned grid = (unsigned)((n_rows + NM_COMB_THREADS - 1) / NM_COMB_THREADS);
+    nm_combine_kernel<<<grid, NM_COMB_THREADS, 0, st>>>(ca);
+    NM_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  return NM_OK;
+}
+
+extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params* params,
+                              const nm_table* tb, int64_t* n_rows_out) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!pl || !tb || !n_rows_out) return nm_fail(h, NM_ERR_BAD_ARG, "pileup/table/n_rows is NULL");
+  nm_params prm;
+  int rc = nm_check_params(h, params, &prm);
+  if (rc != NM_OK) return rc;
+  *n_rows_out = 0;
+  if (pl->n_pos < 0) return nm_fail(h, NM_ERR_BAD_ARG, "n_pos is negative");
+  if (pl->n_pos == 0) return NM_OK;
+  if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
+    return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  const int64_t n = pl->n_pos;
+  const int64_t nv0 = pl->off0[n], nv1 = pl->off1[n];
+  if (nv0 < 0 || nv1 < 0 || pl->off0[0] != 0 || pl->off1[0] != 0)
+    return nm_fail(h, NM_ERR_BAD_ARG, "offsets must start at 0 and be non-decreasing");
+  if ((rc = nm_reserve(h, &h->d_vals0, sizeof(float) * (size_t)nm_padded_len(nv0))) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_vals1, sizeof(float) * (size_t)nm_padded_len(nv1))) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_off0, sizeof(int64_t) * (size_t)(n + 1))) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_off1, sizeof(int64_t) * (size_t)(n + 1))) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_pos, sizeof(int32_t) * (size_t)n)) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_seg, sizeof(int32_t) * (size_t)n)) != NM_OK) return rc;
+  NM_CUDA(h, cudaMemcpyAsync(h->d_vals0.p, pl->vals0, sizeof(float) * (size_t)nv0, cudaMemcpyHostToDevice, st));
+  NM_CUDA(h, cudaMemcpyAsync(h->d_vals1.p, pl->vals1, sizeof(float) * (size_t)nv1, cudaMemcpyHostToDevice, st));
+  NM_CUDA(h, cudaMemcpyAsync(h->d_off0.p, pl->off0, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+  NM_CUDA(h, cudaMemcpyAsync(h->d_off1.p, pl->off1, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+  NM_CUDA(h, cudaMemcpyAsync(h->d_pos.p, pl->pos, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  NM_CUDA(h, cudaMemcpyAsync(h->d_seg.p, pl->seg, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+
+  // device-side table mirrors exactly the outputs the caller asked for
+  void* const host_ptrs[16] = {tb->row_pos_index, tb->n0, tb->n1, tb->ks_dnum, tb->ks_d, tb->ks_p,
+                               tb->two_u, tb->u_stat, tb->u_p, tb->t_stat, tb->t_p, tb->fisher_stat,
+                               tb->fisher_p, tb->stouffer_stat, tb->stouffer_p, tb->flags};
+  const size_t elem[16] = {4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 1};
+  void* dev_ptrs[16];
+  for (int k = 0; k < 16; ++k) {
+    dev_ptrs[k] = nullptr;
+    if (host_ptrs[k]) {
+      if ((rc = nm_reserve(h, &h->d_out[k], elem[k] * (size_t)n)) != NM_OK) return rc;
+      dev_ptrs[k] = h->d_out[k].p;
+    }
+  }
+  nm_pileup dpl = {(const float*)h->d_vals0.p, (const int64_t*)h->d_off0.p, (const float*)h->d_vals1.p,
+                   (const int64_t*)h->d_off1.p, (const int32_t*)h->d_pos.p, (const int32_t*)h->d_seg.p, n};
+  nm_table dtb = {(int32_t*)dev_ptrs[0], (int32_t*)dev_ptrs[1], (int32_t*)dev_ptrs[2], (int32_t*)dev_ptrs[3],
+                  (double*)dev_ptrs[4], (double*)dev_ptrs[5], (int64_t*)dev_ptrs[6], (double*)dev_ptrs[7],
+                  (double*)dev_ptrs[8], (double*)dev_ptrs[9], (double*)dev_ptrs[10], (double*)dev_ptrs[11],
+                  (double*)dev_ptrs[12], (double*)dev_ptrs[13], (double*)dev_ptrs[14], (uint8_t*)dev_ptrs[15]};
+  int64_t n_rows = 0;
+  rc = nm_detect_device(h, &dpl, &prm, &dtb, &n_rows, (void*)st);
+  if (rc != NM_OK) return rc;
+  const bool live[16] = {true, true, true, true, true, true,
+                         prm.want_u != 0, prm.want_u != 0, prm.want_u != 0, prm.want_t != 0, prm.want_t != 0,
+                         (prm.combine & NM_COMBINE_FISHER) != 0, (prm.combine & NM_COMBINE_FISHER) != 0,
+                         (prm.combine & NM_COMBINE_STOUFFER) != 0, (prm.combine & NM_COMBINE_STOUFFER) != 0, true};
+  for (int k = 0; k < 16; ++k)
+    if (host_ptrs[k] && live[k] && n_rows > 0)
+      NM_CUDA(h, cudaMemcpyAsync(host_ptrs[k], dev_ptrs[k], elem[k] * (size_t)n_rows, cudaMemcpyDeviceToHost, st));
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  *n_rows_out = n_rows;
+  return NM_OK;
+}

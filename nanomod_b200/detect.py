@@ -1,0 +1,341 @@
+"""Host side of the detection stage: options, the per-position result table, ranking, the
+called-site rule and the text writer -- everything of ``mtest2`` / ``save_test``
+(bin/scripts/myDetect.py:416-545) that is not arithmetic.  The arithmetic runs in the CUDA
+library behind ``nanomod_b200._lib`` (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .pileup import Pileup
+
+
+class OptionError(ValueError):
+    """Invalid option; the message is the reference's own text (NanoMod.py:40-97, 148-153)."""
+
+
+@dataclass
+class DetectOptions:
+    """Options of ``NanoMod.py detect`` that the stage reads (names and defaults verbatim:
+    NanoMod.py:348-366, 377-392).  ``window`` is the command-line value (21), stored by the
+    reference as (W-1)/2 (:51) -- see ``half_window``."""
+    wrkBase1: Optional[str] = None
+    wrkBase2: Optional[str] = None
+    outLevel: int = 2
+    window: int = 21
+    FileID: str = "mod"
+    outFolder: str = "mRes/"
+    MinCoverage: int = 5
+    topN: int = 30
+    neighborPvalues: int = 2
+    WeightsDif: float = 2.0
+    testMethod: str = "stouffer"
+    rankUse: str = "pv"
+    SaveTest: int = 1
+    RegionRankbyST: int = 0
+    percentile: float = 0.1
+    WindOvlp: int = 0
+    NA: str = ""
+    Pos: str = ""
+    mstd: bool = False
+    plotType: str = "Density"
+    min_lr: int = 500
+    min_lr_nb: int = 0
+    downsampling_quantile: float = 0.25
+    downsampling: int = 100
+    coverages: str = "0-0"
+    # not reference options: which of the reference's three per-position tests to compute.
+    # The reference always computes all three (myDetect.py:331-341).
+    want_u: bool = True
+    want_t: bool = True
+    # compute both combinations in one pass (BASELINE config 3); ranking still follows testMethod
+    both_combinations: bool = False
+
+    @property
+    def half_window(self) -> int:
+        return (self.window - 1) // 2  # NanoMod.py:51 (Python 2 integer division)
+
+    def validate(self) -> None:
+        """mCommonParam's checks (NanoMod.py:40-97); raises OptionError with the same text."""
+        err = ""
+        if self.half_window < 1:
+            err += "\n\tWindow size (%d) is too small" % self.window
+        if self.MinCoverage < 3:
+            err += "\n\tThe coverage (%d) is too small" % self.MinCoverage
+        if self.topN < 1:
+            err += "\n\tThe topN (%d) is too smaller" % self.topN
+        if self.neighborPvalues < 0:
+            err += "\n\tThe neighborPvalues (%d) cannot be smaller than 0" % self.neighborPvalues
+        if self.testMethod not in ("fisher", "stouffer", "ks"):
+            err += "\n\ttestMethod must be one of fisher, stouffer, ks"
+        if self.rankUse not in ("st", "pv"):
+            err += "\n\trankUse must be one of st, pv"
+        if self.WeightsDif < 1:
+            self.WeightsDif = 1.0  # NanoMod.py:77-78
+        if self.percentile < 0:
+            self.percentile = 0.0
+        if self.percentile >= 1:
+            self.percentile = 0.99
+        cov = [int(x) for x in str(self.coverages).split("-")]
+        if any(c > 0 for c in cov):
+            err += "\n\tdown-sampling (--coverages %s) is not supported by the GPU path yet" % self.coverages
+        if self.RegionRankbyST != 0:
+            err += "\n\tRegionRankbyST=1 is not supported by the GPU path yet"
+        if err:
+            raise OptionError("Please provide correct parameters" + err)
+
+    def combine_mask(self) -> int:
+        if self.both_combinations:
+            return _lib.NM_COMBINE_FISHER | _lib.NM_COMBINE_STOUFFER
+        return {"ks": _lib.NM_COMBINE_NONE, "fisher": _lib.NM_COMBINE_FISHER,
+                "stouffer": _lib.NM_COMBINE_STOUFFER}[self.testMethod]
+
+    def to_params(self) -> _lib.nm_params:
+        return _lib.nm_params(int(self.MinCoverage), int(self.neighborPvalues), float(self.WeightsDif),
+                              int(self.combine_mask()), int(bool(self.want_u)), int(bool(self.want_t)), 0)
+
+    @classmethod
+    def from_moptions(cls, moptions: Dict) -> "DetectOptions":
+        o = cls()
+        for k in ("outLevel", "FileID", "outFolder", "MinCoverage", "topN", "neighborPvalues",
+                  "WeightsDif", "testMethod", "rankUse", "SaveTest", "RegionRankbyST", "percentile",
+                  "WindOvlp", "NA", "mstd"):
+            if k in moptions:
+                setattr(o, k, moptions[k])
+        if "window" in moptions:  # moptions stores the half window
+            o.window = 2 * int(moptions["window"]) + 1
+        if "coverages" in moptions:
+            o.coverages = "-".join(str(int(c)) for c in moptions["coverages"])
+        return o
+
+
+@dataclass
+class SignTestTable:
+    """The per-position result table == ``moptions['sign_test']`` in SoA form (row order
+    identical).  Columns not computed are None."""
+    options: DetectOptions
+    seg_names: List[Tuple[str, str]]
+    seg: np.ndarray
+    pos: np.ndarray
+    base: np.ndarray
+    n0: np.ndarray
+    n1: np.ndarray
+    ks_dnum: np.ndarray
+    ks_d: np.ndarray
+    ks_p: np.ndarray
+    two_u: Optional[np.ndarray] = None
+    u_stat: Optional[np.ndarray] = None
+    u_p: Optional[np.ndarray] = None
+    t_stat: Optional[np.ndarray] = None
+    t_p: Optional[np.ndarray] = None
+    fisher_stat: Optional[np.ndarray] = None
+    fisher_p: Optional[np.ndarray] = None
+    stouffer_stat: Optional[np.ndarray] = None
+    stouffer_p: Optional[np.ndarray] = None
+    flags: Optional[np.ndarray] = None
+    row_pos_index: Optional[np.ndarray] = None
+
+    def __len__(self) -> int:
+        return int(self.pos.shape[0])
+
+    # ---- the combined column selected by testMethod (4th tuple of a sign_test row) ----------
+    def comb(self) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+        m = self.options.testMethod
+        if m == "fisher":
+            return self.fisher_stat, self.fisher_p
+        if m == "stouffer":
+            return self.stouffer_stat, self.stouffer_p
+        return None
+
+    def to_sign_test(self) -> List:
+        """``moptions['sign_test']`` exactly as mtest2 builds it (myDetect.py:436, :377)."""
+        comb = self.comb()
+        zeros = np.zeros(len(self))
+        u_s = self.u_stat if self.u_stat is not None else zeros
+        u_p = self.u_p if self.u_p is not None else zeros
+        t_s = self.t_stat if self.t_stat is not None else zeros
+        t_p = self.t_p if self.t_p is not None else zeros
+        out = []
+        for r in range(len(self)):
+            sk = self.seg_names[self.seg[r]]
+            tests = [(float(u_s[r]), float(u_p[r])), (float(t_s[r]), float(t_p[r])),
+                     (float(self.ks_d[r]), float(self.ks_p[r]))]
+            if comb is not None:
+                tests.append((float(comb[0][r]), float(comb[1][r])))
+            out.append(((sk[0], sk[1], int(self.pos[r]), chr(self.base[r]), int(self.n0[r]),
+                         int(self.n1[r])), tests))
+        return out
+
+    # ---- save_test (myDetect.py:522-538) ---------------------------------------------------
+    def format_lines(self) -> List[str]:
+        comb = self.comb()
+        with_comb = self.options.neighborPvalues > 0 and comb is not None
+        zeros = np.zeros(len(self))
+        u_s = self.u_stat if self.u_stat is not None else zeros
+        u_p = self.u_p if self.u_p is not None else zeros
+        t_s = self.t_stat if self.t_stat is not None else zeros
+        t_p = self.t_p if self.t_p is not None else zeros
+        lines = []
+        for r in range(len(self)):
+            sk = self.seg_names[self.seg[r]]
+            s = "%s %s %d %s %d %d %.3f %.3E %.3f %.3E %.3f %.3E" % (
+                sk[0], sk[1], self.pos[r] + 1, chr(self.base[r]), self.n0[r], self.n1[r],
+                u_s[r], u_p[r], t_s[r], t_p[r], self.ks_d[r], self.ks_p[r])
+            if with_comb:
+                s += " %.3f %.3E\n" % (comb[0][r], comb[1][r])
+            else:
+                s += "\n"
+            lines.append(s)
+        return lines
+
+    def save_test(self, path: Optional[str] = None) -> Optional[str]:
+        """Write ``<outFolder>/<FileID>_sign_test.txt`` when SaveTest != 0."""
+        if self.options.SaveTest == 0:
+            return None
+        if path is None:
+            os.makedirs(self.options.outFolder, exist_ok=True)
+            path = self.options.outFolder + "/" + self.options.FileID + "_sign_test.txt"
+        with open(path, "w") as f:
+            f.writelines(self.format_lines())
+        return path
+
+    # ---- ranking (myDetect.py:447-462, RegionRankbyST == 0) --------------------------------
+    def ranked(self) -> np.ndarray:
+        """Row indices in the order of ``moptions['sorted_sign_test']``: stable sort by
+        (combined, KS, U) on the p-value ('pv') or the statistic ('st', then reversed)."""
+        use_p = self.options.rankUse == "pv"
+        comb = self.comb()
+        ks = self.ks_p if use_p else self.ks_d
+        if self.u_p is not None:
+            u = self.u_p if use_p else self.u_stat
+        else:
+            u = np.zeros(len(self))
+        keys = [u, ks]
+        if comb is not None:
+            keys.append(comb[1] if use_p else comb[0])
+        order = np.lexsort(tuple(keys))  # last key is primary; lexsort is stable
+        if not use_p:
+            order = order[::-1]
+        return order
+
+    # ---- called sites (mboxplot :279-297 + plot1 :153-164) ---------------------------------
+    def called_sites(self) -> List[Tuple[str, str, int]]:
+        nb = self.options.neighborPvalues
+        closesize = nb * 2
+        nearby = self.options.half_window
+        n = len(self)
+        out: List[Tuple[str, str, int]] = []
+        acc_seg: List[int] = []
+        acc_pos: List[int] = []
+        for r in self.ranked():
+            r = int(r)
+            sg, ps = int(self.seg[r]), int(self.pos[r])
+            if any(s == sg and abs(p - ps) < closesize for s, p in zip(acc_seg, acc_pos)):
+                continue
+            lo, hi = r - nearby, r + nearby
+            okk = lo >= 0 and hi <= n - 1
+            if okk:
+                w = slice(lo, hi + 1)
+                okk = bool(np.all(self.seg[w] == sg) and
+                           np.all(self.pos[w].astype(np.int64) - ps == np.arange(-nearby, nearby + 1)))
+            if okk:
+                sk = self.seg_names[sg]
+                out.append((sk[0], sk[1], ps))
+                acc_seg.append(sg)
+                acc_pos.append(ps)
+            if len(out) == self.options.topN:
+                break
+        return out
+
+
+_TABLE_OPTIONAL = {"two_u": "want_u", "u_stat": "want_u", "u_p": "want_u", "t_stat": "want_t",
+                   "t_p": "want_t"}
+
+
+def _wanted_columns(opt: DetectOptions) -> List[str]:
+    cols = ["row_pos_index", "n0", "n1", "ks_dnum", "ks_d", "ks_p", "flags"]
+    if opt.want_u:
+        cols += ["two_u", "u_stat", "u_p"]
+    if opt.want_t:
+        cols += ["t_stat", "t_p"]
+    mask = opt.combine_mask()
+    if mask & _lib.NM_COMBINE_FISHER:
+        cols += ["fisher_stat", "fisher_p"]
+    if mask & _lib.NM_COMBINE_STOUFFER:
+        cols += ["stouffer_stat", "stouffer_p"]
+    return cols
+
+
+class Detector:
+    """One GPU's detection engine.  ``detect`` is the host-buffer call (numpy in, numpy out,
+    H2D/D2H inside); ``detect_device`` works on torch CUDA tensors that are already resident."""
+
+    def __init__(self, device: int = 0):
+        self.handle = _lib.Handle(device)
+        self.device = int(device)
+
+    @property
+    def launch_count(self) -> int:
+        return self.handle.launch_count
+
+    def detect(self, pileup: Pileup, options: Optional[DetectOptions] = None,
+               out: Optional[Dict[str, np.ndarray]] = None) -> SignTestTable:
+        opt = options or DetectOptions()
+        opt.validate()
+        n = pileup.n_pos
+        cols = _wanted_columns(opt)
+        if out is None:
+            out = {c: np.empty(n, dtype=_lib.TABLE_DTYPES[c]) for c in cols}
+        tb = _lib.nm_table(**{c: out[c].ctypes.data for c in cols})
+        pl = _lib.nm_pileup(pileup.vals0.ctypes.data, pileup.off0.ctypes.data, pileup.vals1.ctypes.data,
+                            pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n)
+        n_rows = self.handle.detect_host(pl, opt.to_params(), tb)
+        res = {c: out[c][:n_rows] for c in cols}
+        idx = res["row_pos_index"]
+        return SignTestTable(options=opt, seg_names=pileup.seg_names, seg=pileup.seg[idx],
+                             pos=pileup.pos[idx], base=pileup.base[idx],
+                             **{c: res[c] for c in cols})
+
+    def detect_device(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
+                      stream: Optional[int] = None) -> int:
+        """Device-resident call.  ``out`` maps column name -> torch CUDA tensor with capacity
+        n_pos (see ``alloc_device_table``).  Returns n_rows; results are complete on return."""
+        import torch
+        cols = _wanted_columns(options)
+        tb = _lib.nm_table(**{c: out[c].data_ptr() for c in cols})
+        pl = _lib.nm_pileup(dev.vals0.data_ptr(), dev.off0.data_ptr(), dev.vals1.data_ptr(),
+                            dev.off1.data_ptr(), dev.pos.data_ptr(), dev.seg.data_ptr(), dev.n_pos)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev.vals0.device).cuda_stream
+        return self.handle.detect_device(pl, options.to_params(), tb, stream)
+
+
+@dataclass
+class DevicePileup:
+    """CSR pileup resident in HBM (torch CUDA tensors; vals padded per nm_padded_len)."""
+    vals0: "object"
+    off0: "object"
+    vals1: "object"
+    off1: "object"
+    pos: "object"
+    seg: "object"
+    n_pos: int
+
+    @classmethod
+    def from_host(cls, p: Pileup, device) -> "DevicePileup":
+        import torch
+        t = lambda a: torch.from_numpy(a).to(device)
+        return cls(t(p.vals0), t(p.off0), t(p.vals1), t(p.off1), t(p.pos), t(p.seg), p.n_pos)
+
+
+def alloc_device_table(options: DetectOptions, n_pos: int, device) -> Dict[str, "object"]:
+    import torch
+    tdt = {"int32": torch.int32, "int64": torch.int64, "float64": torch.float64, "uint8": torch.uint8}
+    return {c: torch.empty(n_pos, dtype=tdt[_lib.TABLE_DTYPES[c]], device=device)
+            for c in _wanted_columns(options)}

@@ -1,0 +1,118 @@
+// TEST HARNESS ONLY -- compiles the product's host/device headers (nm_math.cuh, nm_lane.cuh,
+// nm_deep.cuh) with g++ so that the per-lane logic and the fp64 tails can be checked against
+// the oracle on a machine without a GPU.  Nothing in nanomod_b200/ links or loads this file;
+// the product path is CUDA-only.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../nanomod_b200/csrc/nm_lane.cuh"
+#include "../../nanomod_b200/csrc/nm_deep.cuh"
+
+namespace {
+struct ArrAcc {
+  const float* p;
+  float operator()(int i) const { return p[i]; }
+};
+
+template <int N>
+void lane_position(const float* a, int n0, const float* b, int n1, bool want_u, bool want_t,
+                   nm_row_out* out) {
+  nm_lane_acc acc;
+  memset(&acc, 0, sizeof(acc));
+  std::vector<float> sa(N + 1), sb(N + 1);
+  {
+    float x[N];
+    for (int k = 0; k < N; ++k) x[k] = k < n0 ? a[k] : INFINITY;
+    if (want_t) nm_moments(a, n0, &acc.mean0, &acc.var0);
+    nm_sortnet<N>::run(x);
+    for (int k = 0; k < N; ++k) sa[k] = x[k];
+    sa[N] = INFINITY;
+  }
+  {
+    float x[N];
+    for (int k = 0; k < N; ++k) x[k] = k < n1 ? b[k] : INFINITY;
+    if (want_t) nm_moments(b, n1, &acc.mean1, &acc.var1);
+    nm_sortnet<N>::run(x);
+    for (int k = 0; k < N; ++k) sb[k] = x[k];
+    sb[N] = INFINITY;
+  }
+  ArrAcc A{sa.data()}, B{sb.data()};
+  // tmax deliberately larger than n0+n1: lanes of a warp share the longest trip count
+  if (want_u)
+    nm_merge_walk<true>(n0, n1, n0 + n1 + 5, A, B, &acc);
+  else
+    nm_merge_walk<false>(n0, n1, n0 + n1 + 5, A, B, &acc);
+  nm_lane_finish(acc, n0, n1, want_u, want_t, out);
+}
+}  // namespace
+
+extern "C" {
+
+int emul_lane_position(const float* a, int n0, const float* b, int n1, int want_u, int want_t,
+                       nm_row_out* out) {
+  const int nmax = n0 > n1 ? n0 : n1;
+  if (nmax > NM_LANE_MAX_N || n0 < 2 || n1 < 2) return 1;
+  const int nsel = (nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+  memset(out, 0, sizeof(*out));
+#define CALL(NN) lane_position<NN>(a, n0, b, n1, want_u != 0, want_t != 0, out)
+  NM_DISPATCH_N(nsel, CALL)
+#undef CALL
+  return 0;
+}
+
+// Deep tier: sorted copies + per-element rank counts, reduced exactly as the block kernel does.
+int emul_deep_position(const float* a, int n0, const float* b, int n1, int want_u, int want_t,
+                       nm_row_out* out) {
+  std::vector<float> sa(a, a + n0), sb(b, b + n1);
+  std::sort(sa.begin(), sa.end());
+  std::sort(sb.begin(), sb.end());
+  nm_deep_acc acc;
+  nm_deep_acc_init(&acc);
+  for (int e = 0; e < n0 + n1; ++e) {
+    nm_deep_acc one;
+    nm_deep_acc_init(&one);
+    nm_deep_element(sa.data(), n0, sb.data(), n1, e, want_u != 0, &one);
+    nm_deep_acc_merge(&acc, one);
+  }
+  double m0 = 0, v0 = 0, m1 = 0, v1 = 0;
+  if (want_t) {
+    nm_moments(a, n0, &m0, &v0);
+    nm_moments(b, n1, &m1, &v1);
+  }
+  memset(out, 0, sizeof(*out));
+  nm_deep_finish(acc, n0, n1, want_u != 0, want_t != 0, m0, v0, m1, v1, out);
+  return 0;
+}
+
+void emul_combine(const double* ks_p, const int32_t* pos, const int32_t* seg, int64_t n, int nb,
+                  double weights_dif, int want_fisher, int want_stouffer, double* f_stat,
+                  double* f_p, double* s_stat, double* s_p) {
+  std::vector<double> w(nb + 1);
+  const double wnorm = nm_build_weights(nb, weights_dif, w.data());
+  for (int64_t i = 0; i < n; ++i) {
+    auto W = [&](int k, double* z, double* lnp) {
+      const int64_t j = i + k;
+      bool ok = j >= 0 && j < n;
+      if (ok && k != 0) ok = seg[j] == seg[i] && (int64_t)pos[j] - (int64_t)pos[i] == (int64_t)k;
+      const double p = ok ? ks_p[j] : 1.0;
+      *z = nm_norm_isf(p);
+      *lnp = log(p);
+    };
+    double fs = 0, fp = 0, ss = 0, sp = 0;
+    nm_combine_row(nb, w.data(), wnorm, W, want_fisher != 0, want_stouffer != 0, &fs, &fp, &ss, &sp);
+    if (want_fisher) { f_stat[i] = fs; f_p[i] = fp; }
+    if (want_stouffer) { s_stat[i] = ss; s_p[i] = sp; }
+  }
+}
+
+double emul_kolmogorov_sf(double x) { return nm_kolmogorov_sf(x); }
+double emul_student_t_two_sided(double t, double df) { return nm_student_t_two_sided(t, df); }
+double emul_chi2_sf_even(double x2, int k) { return nm_chi2_sf_even(x2, k); }
+double emul_norm_sf(double z) { return nm_norm_sf(z); }
+double emul_norm_isf(double p) { return nm_norm_isf(p); }
+int emul_sizeof_row_out(void) { return (int)sizeof(nm_row_out); }
+}

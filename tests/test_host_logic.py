@@ -1,0 +1,187 @@
+"""Host-side logic that needs no GPU: pileup packing, option validation (reference messages),
+table text, ranking and the called-site rule against the oracle, and the C-ABI library's
+symbols + its refusal to run without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nanomod_b200 as nm
+from nanomod_b200 import _lib
+from nanomod_b200.detect import SignTestTable
+from oracle import nanomod_oracle as o
+from oracle import nanomod_oracle_vec as ov
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def oracle_table(p, opt):
+    """A SignTestTable filled from the vectorised oracle (what the GPU would return)."""
+    res = ov.detect(p.vals0, p.off0, p.vals1, p.off1, p.pos, p.seg, opt.MinCoverage, opt.neighborPvalues,
+                    opt.WeightsDif, ("stouffer", "fisher"))
+    idx = res["row_pos_index"]
+    return SignTestTable(options=opt, seg_names=p.seg_names, seg=p.seg[idx], pos=p.pos[idx], base=p.base[idx],
+                         n0=res["n0"], n1=res["n1"], ks_dnum=res["dnum"], ks_d=res["D"], ks_p=res["pks"],
+                         two_u=res["twoU"], u_stat=res["U"], u_p=res["pu"], t_stat=res["t"], t_p=res["pt"],
+                         fisher_stat=res.get("fisher_stat"), fisher_p=res.get("fisher_p"),
+                         stouffer_stat=res.get("stouffer_stat"), stouffer_p=res.get("stouffer_p"))
+
+
+def oracle_moptions(p, opt):
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(MinCoverage=opt.MinCoverage, neighborPvalues=opt.neighborPvalues,
+                            WeightsDif=opt.WeightsDif, testMethod=opt.testMethod, rankUse=opt.rankUse,
+                            topN=opt.topN, window=opt.half_window)
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    o.mfilter_coverage(mo)
+    o.mtest2(mo, strict=False)
+    return mo
+
+
+def table_from_sign_test(p, opt, mo):
+    """SignTestTable carrying the scalar oracle's exact numbers (so ranking ties break alike)."""
+    st_ = mo["sign_test"]
+    seg_id = {sk: i for i, sk in enumerate(p.seg_names)}
+    col = lambda f: np.array([f(m) for m in st_])
+    kw = {}
+    if opt.testMethod != "ks":
+        kw = {opt.testMethod + "_stat": col(lambda m: m[1][3][0]), opt.testMethod + "_p": col(lambda m: m[1][3][1])}
+    return SignTestTable(options=opt, seg_names=p.seg_names,
+                         seg=col(lambda m: seg_id[(m[0][0], m[0][1])]).astype(np.int32),
+                         pos=col(lambda m: m[0][2]).astype(np.int32),
+                         base=col(lambda m: ord(m[0][3])).astype(np.uint8),
+                         n0=col(lambda m: m[0][4]), n1=col(lambda m: m[0][5]),
+                         ks_dnum=np.zeros(len(st_), np.int32), ks_d=col(lambda m: m[1][2][0]),
+                         ks_p=col(lambda m: m[1][2][1]), u_stat=col(lambda m: m[1][0][0]),
+                         u_p=col(lambda m: m[1][0][1]), t_stat=col(lambda m: m[1][1][0]),
+                         t_p=col(lambda m: m[1][1][1]), **kw)
+
+
+def test_pileup_roundtrip_and_order():
+    p = nm.synthetic_pileup(400, 9, 11, drop_frac1=0.1, two_strands=True, round_decimals=3)
+    p.validate()
+    d0, d1 = p.to_dicts()
+    q = nm.Pileup.from_dicts(d0, d1)
+    c0, c1 = p.counts()
+    both = (c0 > 0) & (c1 > 0)
+    assert q.n_pos == int(both.sum())
+    assert np.array_equal(q.pos, p.pos[both]) and np.array_equal(q.seg, p.seg[both])
+    assert q.seg_names == [("syn", "+"), ("syn", "-")]
+    assert np.array_equal(q.vals0[:q.off0[-1]], np.concatenate([p.group(0, i) for i in np.nonzero(both)[0]]))
+    assert q.vals0.shape[0] >= _lib.padded_len(q.off0[-1]) and q.vals0.ctypes.data % 16 == 0
+    s = p.slice_rows(100, 250)
+    assert s.n_pos == 150 and np.array_equal(s.group(1, 0), p.group(1, 100))
+
+
+def test_pileup_npz_roundtrip(tmp_path):
+    p = nm.synthetic_pileup(50, 6, 7, two_strands=True)
+    f = str(tmp_path / "p.npz")
+    p.save_npz(f)
+    q = nm.Pileup.load_npz(f)
+    assert np.array_equal(q.vals1[:q.off1[-1]], p.vals1[:p.off1[-1]]) and q.seg_names == p.seg_names
+
+
+def test_option_defaults_match_reference_cli():
+    d = nm.DetectOptions()
+    assert (d.window, d.FileID, d.outFolder, d.MinCoverage, d.topN, d.neighborPvalues, d.WeightsDif) == \
+        (21, "mod", "mRes/", 5, 30, 2, 2.0)
+    assert (d.testMethod, d.rankUse, d.SaveTest, d.RegionRankbyST, d.percentile, d.WindOvlp, d.NA) == \
+        ("stouffer", "pv", 1, 0, 0.1, 0, "")
+    assert (d.min_lr, d.min_lr_nb, d.downsampling_quantile, d.downsampling, d.coverages, d.outLevel) == \
+        (500, 0, 0.25, 100, "0-0", 2)
+    assert d.half_window == 10
+
+
+def test_option_validation_messages():
+    with pytest.raises(nm.OptionError, match=r"The coverage \(2\) is too small"):
+        nm.DetectOptions(MinCoverage=2).validate()
+    with pytest.raises(nm.OptionError, match=r"The neighborPvalues \(-1\) cannot be smaller than 0"):
+        nm.DetectOptions(neighborPvalues=-1).validate()
+    with pytest.raises(nm.OptionError, match=r"Window size \(2\) is too small"):
+        nm.DetectOptions(window=2).validate()
+    with pytest.raises(nm.OptionError, match="topN"):
+        nm.DetectOptions(topN=0).validate()
+    d = nm.DetectOptions(WeightsDif=0.5)
+    d.validate()
+    assert d.WeightsDif == 1.0  # NanoMod.py:77-78
+    with pytest.raises(nm.OptionError, match="down-sampling"):
+        nm.DetectOptions(coverages="50-50").validate()
+
+
+@pytest.mark.parametrize("method,rank", [("stouffer", "pv"), ("fisher", "pv"), ("ks", "pv"), ("stouffer", "st")])
+def test_table_text_ranking_called_sites_match_oracle(method, rank):
+    p = nm.synthetic_pileup(3000, 25, 25, drop_frac1=0.004, two_strands=True)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod=method, rankUse=rank, topN=8)
+    mo = oracle_moptions(p, opt)
+    t = table_from_sign_test(p, opt, mo)
+    assert t.format_lines() == o.save_test_lines(mo)
+    assert oracle_table(p, opt).format_lines() == o.save_test_lines(mo)  # vectorised oracle, 4 digits
+    want_order = [(m[0][0], m[0][1], m[0][2]) for m in mo["sorted_sign_test"]]
+    got_order = [(t.seg_names[t.seg[r]][0], t.seg_names[t.seg[r]][1], int(t.pos[r])) for r in t.ranked()]
+    assert got_order == want_order
+    assert t.called_sites() == o.called_sites(mo)
+    assert len(t.called_sites()) == 8
+    st_ = t.to_sign_test()
+    assert st_[5][0] == mo["sign_test"][5][0] and len(st_[5][1]) == len(mo["sign_test"][5][1])
+
+
+def test_called_sites_find_planted_positions():
+    p = nm.synthetic_pileup(10000, 50, 50)
+    opt = nm.DetectOptions(neighborPvalues=3, topN=6)
+    sites = oracle_table(p, opt).called_sites()
+    assert len(sites) == 6
+    assert all(abs((s[2] % 1000) - 500) <= 2 for s in sites)
+
+
+def test_save_test_file(tmp_path):
+    p = nm.synthetic_pileup(40, 6, 6)
+    opt = nm.DetectOptions(outFolder=str(tmp_path), FileID="abc")
+    t = oracle_table(p, opt)
+    path = t.save_test()
+    assert path.endswith("abc_sign_test.txt")
+    lines = open(path).read().splitlines()
+    assert len(lines) == 40
+    assert re.match(r"^syn \+ 1 A 6 6 \d+\.\d{3} \d\.\d{3}E[-+]\d+ -?\d+\.\d{3} ", lines[0])
+    assert lines[0].endswith("-inf 1.000E+00")  # first nb rows: missing neighbours -> Z = -inf, p = 1
+    opt.SaveTest = 0
+    assert t.save_test() is None
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nanomod_b200.h")).read()
+    declared = set(re.findall(r"\b(nm_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert os.path.exists(_lib.LIB_PATH), "run `python -m nanomod_b200.build` (or __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.nm_version.restype = ctypes.c_int
+    assert lib.nm_version() == 100
+    assert _lib.load().nm_padded_len(5) == _lib.padded_len(5) == 12
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.nm_params) == 32
+    assert ctypes.sizeof(_lib.nm_pileup) == 56
+    assert ctypes.sizeof(_lib.nm_table) == 16 * 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nm.NmError) as e:
+        nm.Detector(0)
+    assert e.value.code == 6  # NM_ERR_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nanomod_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
