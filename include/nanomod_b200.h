@@ -116,6 +116,10 @@ int nm_detect_host(nm_handle* h, const nm_pileup* pileup, const nm_params* param
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nm_launch_count(const nm_handle* h);
 
+/* Device time (ms, CUDA events on the call's stream) of the most recent nm_detect_* call:
+ * ms4[0] plan kernels, [1] lane-tier kernel, [2] deep-tier kernel, [3] combine kernel. */
+int nm_last_timings(const nm_handle* h, double* ms4);
+
 #ifdef __cplusplus
 }
 #endif

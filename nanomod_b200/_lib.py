@@ -21,7 +21,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count"]
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings"]
 
 
 class NmError(RuntimeError):
@@ -79,6 +79,8 @@ def load():
     lib.nm_last_error.argtypes = [C.c_void_p]
     lib.nm_launch_count.restype = C.c_int64
     lib.nm_launch_count.argtypes = [C.c_void_p]
+    lib.nm_last_timings.restype = C.c_int
+    lib.nm_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.nm_detect_device.restype = C.c_int
     lib.nm_detect_device.argtypes = [C.c_void_p, C.POINTER(nm_pileup), C.POINTER(nm_params),
                                      C.POINTER(nm_table), C.POINTER(C.c_int64), C.c_void_p]
@@ -123,6 +125,12 @@ class Handle:
     @property
     def launch_count(self) -> int:
         return int(self._lib.nm_launch_count(self._h))
+
+    def last_timings(self):
+        """Device ms of the last call: {'plan','lane','deep','combine'} (CUDA events)."""
+        ms = (C.c_double * 4)()
+        self._check(self._lib.nm_last_timings(self._h, ms))
+        return {"plan": ms[0], "lane": ms[1], "deep": ms[2], "combine": ms[3]}
 
     def detect_host(self, pileup: nm_pileup, params: nm_params, table: nm_table) -> int:
         n_rows = C.c_int64(0)

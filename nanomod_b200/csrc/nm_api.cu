@@ -382,6 +382,8 @@ struct nm_handle {
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
   nm_buf d_out[16];
   int64_t launches;
+  cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
+  double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
 };
 
@@ -426,6 +428,12 @@ extern "C" const char* nm_last_error(const nm_handle* h) { return h ? h->err : g
 
 extern "C" int64_t nm_launch_count(const nm_handle* h) { return h ? h->launches : 0; }
 
+extern "C" int nm_last_timings(const nm_handle* h, double* ms4) {
+  if (!h || !ms4) return NM_ERR_BAD_ARG;
+  for (int k = 0; k < 4; ++k) ms4[k] = h->last_ms[k];
+  return NM_OK;
+}
+
 extern "C" int nm_create(int device, nm_handle** out) {
   if (!out) return nm_fail(nullptr, NM_ERR_BAD_ARG, "nm_create: out is NULL");
   *out = nullptr;
@@ -453,6 +461,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
     if (cudaMalloc(&h->d_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
     if (cudaMallocHost(&h->h_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
+    for (int k = 0; k < 5 && rc == NM_OK; ++k)
+      if (cudaEventCreate(&h->ev[k]) != cudaSuccess) rc = NM_ERR_CUDA;
   } while (0);
   if (rc != NM_OK) {
     nm_fail(nullptr, rc, "nm_create: CUDA set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -475,6 +485,8 @@ extern "C" void nm_destroy(nm_handle* h) {
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->h_sum) cudaFreeHost(h->h_sum);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int k = 0; k < 5; ++k)
+    if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   free(h);
 }
 
@@ -495,18 +507,21 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
 
 static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int lane_smem,
                            int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+  NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
     const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, lane_smem, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
   }
+  NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
     NM_CUDA(h, cudaFuncSetAttribute(nm_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_smem));
     nm_deep_kernel<<<(unsigned)n_deep, NM_DEEP_THREADS, deep_smem, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
     NM_CUDA(h, cudaGetLastError());
     h->launches++;
   }
+  NM_CUDA(h, cudaEventRecord(h->ev[3], st));
   return NM_OK;
 }
 
@@ -542,6 +557,8 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   if ((rc = nm_reserve(h, &h->d_deep_rows, sizeof(int32_t) * (size_t)n_pos)) != NM_OK) return rc;
 
   // ---- plan: filter + ordered compaction
+  for (int k = 0; k < 4; ++k) h->last_ms[k] = 0.0;
+  NM_CUDA(h, cudaEventRecord(h->ev[0], st));
   NM_CUDA(h, cudaMemsetAsync(h->d_sum, 0, sizeof(nm_summary), st));
   nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
                                                   (int*)h->d_block_count.p, h->d_sum);
@@ -551,8 +568,13 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
                                                     tb->n0, tb->n1, (int32_t*)h->d_deep_rows.p, h->d_sum);
   NM_CUDA(h, cudaGetLastError());
   h->launches += 3;
+  NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->last_ms[0] = ms;
+  }
   const nm_summary sum = *h->h_sum;
   const int64_t n_rows = (int64_t)sum.n_rows;
   *n_rows_out = n_rows;
@@ -593,7 +615,16 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     NM_CUDA(h, cudaGetLastError());
     h->launches++;
   }
+  NM_CUDA(h, cudaEventRecord(h->ev[4], st));
   NM_CUDA(h, cudaStreamSynchronize(st));
+  {
+    float ms = 0.f;
+    // ev[1] is re-recorded after the plan readback, so [0] covers only the plan kernels' span
+    // up to the first record; tiers and combine are bracketed exactly
+    if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->last_ms[1] = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->last_ms[2] = ms;
+    if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->last_ms[3] = ms;
+  }
   return NM_OK;
 }
 

@@ -1,0 +1,368 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+the same float32 inputs.
+
+Parity bar (BASELINE.json north_star / SURVEY.md 8d):
+  exact      row set and order, n0, n1, the integer KS numerator Dnum, 2U
+  rel 1e-6   every p-value and statistic (KS, U, t, Fisher X^2, Stouffer Z); -inf == -inf;
+             values clamped to DBL_MIN / DBL_MAX equal bit for bit
+  identical  called-site list
+"""
+import numpy as np
+import pytest
+
+import nanomod_b200 as nm
+from nanomod_b200 import myDetect
+from nanomod_b200.sharded import ShardedDetector, plan_shards
+from oracle import nanomod_oracle as o
+from oracle import nanomod_oracle_vec as ov
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # stated tolerance of the north star for p-values and z-scores
+
+
+@pytest.fixture(scope="module")
+def det():
+    return nm.Detector(0)
+
+
+def close(got, want, rtol=RTOL, atol=0.0):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    with np.errstate(invalid="ignore"):
+        ok = same | (np.abs(got - want) <= rtol * np.abs(want) + atol)
+    return bool(np.all(ok)), int(np.argmin(ok)) if not np.all(ok) else -1
+
+
+def assert_table_matches(t, res, opt, check_ut=True):
+    assert len(t) == len(res["dnum"])
+    assert np.array_equal(t.row_pos_index, res["row_pos_index"])
+    assert np.array_equal(t.n0, res["n0"]) and np.array_equal(t.n1, res["n1"])
+    assert np.array_equal(t.ks_dnum, res["dnum"]), "KS numerator must be bit-exact"
+    for name, got, want, atol in (("ks_d", t.ks_d, res["D"], 0), ("ks_p", t.ks_p, res["pks"], 0)):
+        ok, i = close(got, want, atol=atol)
+        assert ok, (name, i, got[i], want[i])
+    if check_ut and opt.want_u:
+        assert np.array_equal(t.two_u, res["twoU"]), "2U must be bit-exact"
+        assert np.array_equal(t.flags & 1, res["uflag"])
+        for name, got, want in (("u_stat", t.u_stat, res["U"]), ("u_p", t.u_p, res["pu"])):
+            ok, i = close(got, want)
+            assert ok, (name, i, got[i], want[i])
+    if check_ut and opt.want_t:
+        ok, i = close(t.t_stat, res["t"], atol=1e-12)  # t crosses 0: absolute floor for |t| < 1e-6
+        assert ok, ("t", i, t.t_stat[i], res["t"][i])
+        ok, i = close(t.t_p, res["pt"])
+        assert ok, ("t_p", i, t.t_p[i], res["pt"][i])
+    for m in ("stouffer", "fisher"):
+        if getattr(t, m + "_p") is not None and (m + "_p") in res:
+            gs, gp = getattr(t, m + "_stat"), getattr(t, m + "_p")
+            assert np.array_equal(np.isneginf(gs), np.isneginf(res[m + "_stat"]))
+            ok, i = close(gs, res[m + "_stat"], atol=1e-9)
+            assert ok, (m + "_stat", i, gs[i], res[m + "_stat"][i])
+            ok, i = close(gp, res[m + "_p"])
+            assert ok, (m + "_p", i, gp[i], res[m + "_p"][i])
+
+
+def vec(p, opt, methods=("stouffer", "fisher")):
+    return ov.detect(p.vals0, p.off0, p.vals1, p.off1, p.pos, p.seg, opt.MinCoverage, opt.neighborPvalues,
+                     opt.WeightsDif, methods)
+
+
+def scalar_moptions(p, opt):
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(MinCoverage=opt.MinCoverage, neighborPvalues=opt.neighborPvalues,
+                            WeightsDif=opt.WeightsDif, testMethod=opt.testMethod, rankUse=opt.rankUse,
+                            topN=opt.topN, window=opt.half_window)
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    o.mfilter_coverage(mo)
+    o.mtest2(mo, strict=False)
+    return mo
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 1: 10 kb, 2x50, KS + weighted Stouffer +-3 -- against the SCALAR oracle
+# ---------------------------------------------------------------------------------------------
+def test_cfg1_scalar_oracle_full(det):
+    p = nm.synthetic_pileup(10000, 50, 50)
+    opt = nm.DetectOptions(neighborPvalues=3, WeightsDif=2.0, testMethod="stouffer", topN=30)
+    t = det.detect(p, opt)
+    mo = scalar_moptions(p, opt)
+    st_ = mo["sign_test"]
+    assert len(t) == len(st_) == 10000
+    for r in (0, 1, 2, 3, 499, 500, 501, 5000, 9996, 9997, 9998, 9999):
+        key, tests = st_[r]
+        assert (key[2], key[4], key[5]) == (t.pos[r], t.n0[r], t.n1[r])
+    col = lambda f: np.array([f(m) for m in st_])
+    for name, got, want in (("U", t.u_stat, col(lambda m: m[1][0][0])), ("pU", t.u_p, col(lambda m: m[1][0][1])),
+                            ("pt", t.t_p, col(lambda m: m[1][1][1])), ("D", t.ks_d, col(lambda m: m[1][2][0])),
+                            ("pks", t.ks_p, col(lambda m: m[1][2][1])), ("Z", t.stouffer_stat, col(lambda m: m[1][3][0])),
+                            ("pZ", t.stouffer_p, col(lambda m: m[1][3][1]))):
+        ok, i = close(got, want, atol=1e-9 if name == "Z" else 0)
+        assert ok, (name, i, got[i], want[i])
+    ok, i = close(t.t_stat, col(lambda m: m[1][1][0]), atol=1e-12)
+    assert ok
+    assert np.array_equal(t.two_u, np.round(2 * col(lambda m: m[1][0][0])).astype(np.int64))
+    # called sites and the table text
+    assert t.called_sites() == o.called_sites(mo)
+    want_lines = o.save_test_lines(mo)
+    got_lines = t.format_lines()
+    same = sum(a == b for a, b in zip(got_lines, want_lines))
+    assert same >= 0.999 * len(want_lines), same  # a %.3E digit may flip on a 1e-13 difference
+    assert int(np.sum(np.isneginf(t.stouffer_stat))) == 6  # first/last 3 rows: Z = -inf, p = 1
+
+
+@pytest.mark.parametrize("variant", ["ties3", "ties1", "gaps", "two_strands_gaps", "poisson", "mincov3", "integers"])
+def test_cfg1_variants(det, variant):
+    kw = {"ties3": dict(round_decimals=3), "ties1": dict(round_decimals=1), "gaps": dict(drop_frac1=0.01),
+          "two_strands_gaps": dict(drop_frac1=0.02, two_strands=True, round_decimals=2),
+          "poisson": dict(poisson=True, clip=(2, 128), round_decimals=3),
+          "mincov3": dict(poisson=True, clip=(1, 12)), "integers": dict(round_decimals=0)}[variant]
+    n = 50 if variant not in ("mincov3",) else 6
+    p = nm.synthetic_pileup(10000, n, n, seed=nm.SYN_SEED + 1, **kw)
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True, MinCoverage=3 if variant == "mincov3" else 5)
+    t = det.detect(p, opt)
+    assert_table_matches(t, vec(p, opt), opt)
+
+
+@pytest.mark.parametrize("nb,wd,method", [(0, 2.0, "stouffer"), (1, 1.0, "stouffer"), (2, 2.0, "fisher"),
+                                          (5, 1.5, "stouffer"), (32, 2.0, "fisher"), (2, 0.3, "stouffer")])
+def test_combination_parameters(det, nb, wd, method):
+    p = nm.synthetic_pileup(4000, 20, 24, drop_frac1=0.01, two_strands=True)
+    opt = nm.DetectOptions(neighborPvalues=nb, WeightsDif=wd, testMethod=method, want_u=False, want_t=False)
+    t = det.detect(p, opt)
+    opt_eff = nm.DetectOptions(neighborPvalues=nb, WeightsDif=max(wd, 1.0), testMethod=method)
+    res = vec(p, opt_eff, (method,))
+    assert_table_matches(t, res, opt, check_ut=False)
+    assert t.u_p is None and t.t_p is None
+
+
+def test_ks_only_and_column_subsets(det):
+    p = nm.synthetic_pileup(3000, 30, 30, round_decimals=2)
+    res = vec(p, nm.DetectOptions(), ())
+    for want_u, want_t in ((False, False), (True, False), (False, True)):
+        opt = nm.DetectOptions(testMethod="ks", want_u=want_u, want_t=want_t)
+        t = det.detect(p, opt)
+        assert t.stouffer_p is None and t.fisher_p is None
+        assert_table_matches(t, res, opt)
+
+
+def test_every_coverage_1_to_140(det):
+    """Coverage sweep through every network size and across the lane/deep tier boundary."""
+    rng = np.random.default_rng(9)
+    c0 = np.concatenate([np.arange(1, 141), rng.integers(3, 141, 400)]).astype(np.int64)
+    c1 = np.concatenate([np.arange(1, 141)[::-1], rng.integers(3, 141, 400)]).astype(np.int64)
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0.4, 1, off1[-1]), 2).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(len(c0), dtype=np.int32))
+    opt = nm.DetectOptions(MinCoverage=3, neighborPvalues=2, both_combinations=True)
+    assert_table_matches(det.detect(p, opt), vec(p, opt), opt)
+
+
+def test_deep_rows_mixed_with_lane_rows(det):
+    """Deep pileups (block-per-position tier) interleaved with ordinary rows; a +4 sigma deep
+    site drives the KS p-value below DBL_MIN so that the clamp (myDetect.py:317-320) is hit."""
+    rng = np.random.default_rng(21)
+    L = 600
+    c0 = np.full(L, 40, np.int64)
+    c1 = np.full(L, 40, np.int64)
+    deep = {10: (2000, 2000), 11: (2000, 1500), 12: (129, 5), 13: (5, 129), 300: (4000, 3000), 301: (257, 255), 599: (1024, 1024)}
+    for i, (a, b) in deep.items():
+        c0[i], c1[i] = a, b
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 3).astype(np.float32)
+    shift = np.zeros(L)
+    shift[10] = 4.0
+    shift[300] = 0.1
+    v1 = np.round(rng.normal(0, 1, off1[-1]) + np.repeat(shift, c1), 3).astype(np.float32)
+    v1[off1[11]:off1[12]] += 50.0  # disjoint deep groups
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True)
+    t = det.detect(p, opt)
+    res = vec(p, opt)
+    assert_table_matches(t, res, opt)
+    assert t.ks_p[11] == o.FLOAT_MIN and t.ks_dnum[11] == 2000 * 1500
+    # the scalar oracle agrees on the deep rows too
+    for i in deep:
+        ref = o.per_position(p.group(0, i).astype(np.float64), p.group(1, i).astype(np.float64))
+        assert t.ks_dnum[i] == ref["dnum"] and t.two_u[i] == ref["twoU"]
+        assert abs(t.ks_p[i] - ref["pks"]) <= RTOL * ref["pks"]
+
+
+def test_cfg5_deep_plasmid_slice(det):
+    """BASELINE config 5 shape (2x2000x), 300 positions of it, with planted +4 sigma sites."""
+    L, n = 300, 2000
+    rng = np.random.default_rng(5)
+    off = (np.arange(L + 1) * n).astype(np.int64)
+    v0 = rng.normal(0, 1, L * n).astype(np.float32)
+    shift = np.zeros(L)
+    shift[[50, 150, 250]] = 4.0
+    v1 = (rng.normal(0, 1, L * n) + np.repeat(shift, n)).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off, v1, off, np.arange(L, dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer")
+    t = det.detect(p, opt)
+    assert_table_matches(t, vec(p, opt, ("stouffer",)), opt)
+    assert np.all(t.ks_p[[50, 150, 250]] == o.FLOAT_MIN)
+    assert abs(t.stouffer_stat[150] - 37.5193793471445 * 100 / np.linalg.norm(o.stouffer_weights(3, 2.0))) < 1.0
+
+
+def test_degenerate_positions(det):
+    rows = [([1.0] * 6, [1.0] * 7), ([1.0] * 5, [2.0] * 5), ([2.0] * 5, [1.0] * 5),
+            ([0.0, -0.0, 0.0, 1.0, 2.0], [-0.0, 0.0, 1.0, 2.0, 3.0]), ([1.0, 2.0, 3.0], [1.0, 2.0, 3.0])]
+    c0 = np.array([len(a) for a, _ in rows])
+    c1 = np.array([len(b) for _, b in rows])
+    p = nm.Pileup.from_arrays(np.concatenate([a for a, _ in rows]), np.concatenate([[0], np.cumsum(c0)]),
+                              np.concatenate([b for _, b in rows]), np.concatenate([[0], np.cumsum(c1)]),
+                              np.arange(len(rows), dtype=np.int32))
+    t = det.detect(p, nm.DetectOptions(MinCoverage=3, testMethod="ks"))
+    assert t.flags[0] & 1 and np.isnan(t.u_p[0]) and t.ks_dnum[0] == 0 and t.ks_p[0] == 1.0 and t.two_u[0] == 42
+    assert np.isnan(t.t_stat[0]) and np.isnan(t.t_p[0])
+    assert t.t_stat[1] == -np.inf and t.t_p[1] == o.FLOAT_MIN and t.ks_dnum[1] == 25 and t.two_u[1] == 0
+    assert t.t_stat[2] == o.FLOAT_MAX
+    ref = o.per_position(np.array(rows[3][0]), np.array(rows[3][1]))
+    assert t.ks_dnum[3] == ref["dnum"] and t.two_u[3] == ref["twoU"]
+    assert t.ks_dnum[4] == 0 and t.two_u[4] == 9
+
+
+def test_empty_and_all_filtered(det):
+    p = nm.synthetic_pileup(100, 4, 4)
+    t = det.detect(p, nm.DetectOptions(MinCoverage=5))
+    assert len(t) == 0 and t.called_sites() == []
+    empty = nm.Pileup.from_arrays(np.zeros(0, np.float32), np.zeros(1, np.int64), np.zeros(0, np.float32),
+                                  np.zeros(1, np.int64), np.zeros(0, np.int32))
+    assert len(det.detect(empty, nm.DetectOptions())) == 0
+
+
+def test_error_codes(det):
+    p = nm.synthetic_pileup(64, 8, 8)
+    from nanomod_b200 import _lib
+    pl = _lib.nm_pileup(p.vals0.ctypes.data, p.off0.ctypes.data, p.vals1.ctypes.data, p.off1.ctypes.data,
+                        p.pos.ctypes.data, p.seg.ctypes.data, p.n_pos)
+    out = {c: np.empty(64, dtype=_lib.TABLE_DTYPES[c]) for c in ("row_pos_index", "n0", "n1", "ks_dnum", "ks_p")}
+    tb = _lib.nm_table(**{c: a.ctypes.data for c, a in out.items()})
+    for prm, code in ((_lib.nm_params(2, 2, 2.0, 0, 0, 0, 0), 2), (_lib.nm_params(5, -1, 2.0, 0, 0, 0, 0), 2),
+                      (_lib.nm_params(5, 33, 2.0, 2, 0, 0, 0), 2), (_lib.nm_params(5, 2, 2.0, 8, 0, 0, 0), 2),
+                      (_lib.nm_params(5, 2, 2.0, 2, 0, 0, 0), 1),   # stouffer outputs missing
+                      (_lib.nm_params(5, 2, 2.0, 0, 1, 0, 0), 1)):  # U outputs missing
+        with pytest.raises(nm.NmError) as e:
+            det.handle.detect_host(pl, prm, tb)
+        assert e.value.code == code, (prm.min_coverage, prm.nb, e.value)
+    assert det.handle.detect_host(pl, _lib.nm_params(5, 2, 2.0, 0, 0, 0, 0), tb) == 64
+    # too deep for the shared-memory tier
+    n = 40000
+    big = nm.Pileup.from_arrays(np.zeros(n, np.float32), np.array([0, n]), np.ones(n, np.float32), np.array([0, n]),
+                                np.zeros(1, np.int32))
+    with pytest.raises(nm.NmError) as e:
+        det.detect(big, nm.DetectOptions(testMethod="ks"))
+    assert e.value.code == 5
+
+
+def test_reference_seam_mirror(det):
+    """myDetect.mfilter_coverage / mtest2 / getKStest on the reference's own data model."""
+    p = nm.synthetic_pileup(1500, 14, 16, drop_frac1=0.02, two_strands=True, round_decimals=3)
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(neighborPvalues=2, testMethod="stouffer", SaveTest=0, topN=5)
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    mo["_detector"] = det
+    ref = scalar_moptions(p, nm.DetectOptions(neighborPvalues=2, topN=5))
+    myDetect.mfilter_coverage(mo)
+    myDetect.mtest2(mo)
+    assert len(mo["sign_test"]) == len(ref["sign_test"])
+    for got, want in zip(mo["sign_test"], ref["sign_test"]):
+        assert got[0] == want[0]
+        for (gs, gp), (ws, wp) in zip(got[1], want[1]):
+            assert gs == ws or abs(gs - ws) <= RTOL * abs(ws) + 1e-12
+            assert gp == wp or abs(gp - wp) <= RTOL * abs(wp)
+    assert [m[0] for m in mo["sorted_sign_test"][:20]] == [m[0] for m in ref["sorted_sign_test"][:20]]
+    assert myDetect.called_sites(mo) == o.called_sites(ref)
+    a, b = [.1, .2, .2, .3, .3, .3], [.2, .3, .3, .4, .4, .5, .6]  # K2 of SURVEY 8c
+    (u, pu), (tt, pt), (d, pks) = myDetect.getKStest(mo, a, b, "+")
+    want = o.getKStest(o.default_moptions(), np.float32(a).astype(np.float64), np.float32(b).astype(np.float64), "+")
+    for g, w in zip((u, pu, tt, pt, d, pks), [x for pair in want for x in pair]):
+        assert abs(g - w) <= RTOL * abs(w)
+    assert abs(pks - 0.15504417912365295) < 1e-6 and u == 7.0
+
+
+def test_device_resident_entry_and_unaligned_offsets(det):
+    """nm_detect_device on torch tensors; rows whose slices start at odd element offsets."""
+    import torch
+    p = nm.synthetic_pileup(5000, 50, 50, poisson=True, clip=(5, 128), seed=77)
+    opt = nm.DetectOptions(neighborPvalues=3, want_u=True, want_t=True)
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    out = nm.alloc_device_table(opt, p.n_pos, "cuda:0")
+    n_rows = det.detect_device(dev, opt, out)
+    res = vec(p, opt, ("stouffer",))
+    assert n_rows == len(res["dnum"])
+    assert np.array_equal(out["ks_dnum"][:n_rows].cpu().numpy(), res["dnum"])
+    assert np.array_equal(out["two_u"][:n_rows].cpu().numpy(), res["twoU"])
+    ok, i = close(out["stouffer_p"][:n_rows].cpu().numpy(), res["stouffer_p"])
+    assert ok
+    tm = det.handle.last_timings()
+    assert tm["lane"] > 0 and tm["combine"] > 0 and det.launch_count >= 5
+
+
+def test_sharded_equals_single(det):
+    """Halo-recompute sharding (2, 3 and 8 shards on one GPU) is identical to the single run."""
+    p = nm.synthetic_pileup(6000, 20, 20, drop_frac1=0.01, two_strands=True, poisson=True, clip=(3, 60))
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True)
+    full = det.detect(p, opt)
+    sd = ShardedDetector(det)
+    for world in (2, 3, 8):
+        parts = [sd.detect_range(p, lo, hi, opt) for lo, hi in plan_shards(p.off0, p.off1, world)]
+        for name in ("row_pos_index", "ks_dnum", "ks_p", "two_u", "u_p", "t_stat", "t_p", "stouffer_stat",
+                     "stouffer_p", "fisher_stat", "fisher_p"):
+            cat = np.concatenate([getattr(t, name) for t in parts])
+            assert cat.tobytes() == getattr(full, name).tobytes(), (world, name)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 2 at full size (4.6 Mb, 2x100x): size-independent properties + sampled oracle
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_full_size_properties(det):
+    import torch
+    from bench import make_device_workload
+    L, n = 4_600_000, 100
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False)
+    dev, host_shift = make_device_workload(L, n, n, torch.device("cuda:0"))
+    out = nm.alloc_device_table(opt, L, "cuda:0")
+    assert det.detect_device(dev, opt, out) == L
+    dnum = out["ks_dnum"].clone()
+    pks = out["ks_p"].clone()
+    z = out["stouffer_stat"].clone()
+    # (1) sampled rows against the vectorised oracle (every planted site +-10 and a 0.5 % sample)
+    rng = np.random.default_rng(1)
+    planted = np.nonzero(host_shift > 0)[0]
+    near = np.unique(np.clip(planted[:, None] + np.arange(-10, 11)[None, :], 0, L - 1))[::7]
+    rows = np.unique(np.concatenate([rng.choice(L, 23000, replace=False), near, [0, 1, L - 2, L - 1]]))
+    r_t = torch.from_numpy(rows).cuda()
+    A = dev.vals0[: L * n].view(L, n)[r_t].double().cpu().numpy()
+    B = dev.vals1[: L * n].view(L, n)[r_t].double().cpu().numpy()
+    blk = ov.tests_block(A, np.full(len(rows), n), B, np.full(len(rows), n))
+    assert np.array_equal(dnum[r_t].cpu().numpy(), blk["dnum"])
+    ok, i = close(pks[r_t].cpu().numpy(), blk["pks"])
+    assert ok
+    # (2) combination of the GPU's own p-values over a window of rows == oracle combine
+    lo = 123_000
+    seg = np.zeros(4000, np.int32)
+    c = ov.combine(pks[lo:lo + 4000].cpu().numpy(), np.arange(lo, lo + 4000, dtype=np.int32), seg, 3, 2.0, "stouffer")
+    ok, i = close(z[lo + 3:lo + 3997].cpu().numpy(), c["stat"][3:-3], atol=1e-9)
+    assert ok
+    assert int(torch.isinf(z).sum().item()) == 6  # only the first/last nb rows of the single run
+    # (3) symmetry: swapping the groups leaves Dnum and the p-value unchanged
+    swapped = nm.DevicePileup(dev.vals1, dev.off1, dev.vals0, dev.off0, dev.pos, dev.seg, L)
+    out2 = nm.alloc_device_table(opt, L, "cuda:0")
+    det.detect_device(swapped, opt, out2)
+    assert torch.equal(out2["ks_dnum"], dnum) and torch.equal(out2["ks_p"], pks)
+    # (4) order statistics only: an exact strictly increasing map (x -> 2x) leaves Dnum unchanged
+    mono = nm.DevicePileup(dev.vals0 * 2.0, dev.off0, dev.vals1 * 2.0, dev.off1, dev.pos, dev.seg, L)
+    det.detect_device(mono, opt, out2)
+    assert torch.equal(out2["ks_dnum"], dnum)
+    # (5) idempotence / determinism
+    det.detect_device(dev, opt, out2)
+    assert torch.equal(out2["ks_dnum"], dnum) and torch.equal(out2["stouffer_stat"].nan_to_num(neginf=-1e300), z.nan_to_num(neginf=-1e300))
+    # (6) the planted sites are what gets called
+    t_pos = torch.argsort(out["stouffer_p"])[:200].cpu().numpy()
+    assert np.mean(host_shift[t_pos] > 0) > 0.95
