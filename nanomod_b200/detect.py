@@ -297,9 +297,12 @@ class Detector:
                             pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n)
         n_rows = self.handle.detect_host(pl, opt.to_params(), tb)
         res = {c: out[c][:n_rows] for c in cols}
-        idx = res["row_pos_index"]
-        return SignTestTable(options=opt, seg_names=pileup.seg_names, seg=pileup.seg[idx],
-                             pos=pileup.pos[idx], base=pileup.base[idx],
+        if n_rows == n:  # nothing filtered: rows are the candidates themselves
+            seg, pos, base = pileup.seg, pileup.pos, pileup.base
+        else:
+            idx = res["row_pos_index"]
+            seg, pos, base = pileup.seg[idx], pileup.pos[idx], pileup.base[idx]
+        return SignTestTable(options=opt, seg_names=pileup.seg_names, seg=seg, pos=pos, base=base,
                              **{c: res[c] for c in cols})
 
     def detect_device(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
