@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libnanomod_b200.so")
+# NANOMOD_B200_LIB selects an experimental build variant of the same library (see build.py)
+LIB_PATH = os.environ.get("NANOMOD_B200_LIB") or os.path.join(_HERE, "_C", "libnanomod_b200.so")
 
 NM_OK = 0
 NM_COMBINE_NONE, NM_COMBINE_FISHER, NM_COMBINE_STOUFFER = 0, 1, 2

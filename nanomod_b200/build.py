@@ -33,36 +33,42 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def _compile(unit, force):
+def _compile(unit, force, defs=(), suffix=""):
     src = os.path.join(CSRC, unit)
-    obj = os.path.join(OUT_DIR, unit.replace(".cu", ".o"))
+    obj = os.path.join(OUT_DIR, unit.replace(".cu", suffix + ".o"))
     if not force and not _stale(obj, [src] + _deps()):
         return obj, ""
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defs] + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, r.stdout, r.stderr))
     return obj, r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defs=(), suffix: str = "") -> str:
+    """Build the library.  ``defs``/``suffix`` make an experimental variant (e.g.
+    defs=("NM_INT_KEYS",), suffix="_int" -> libnanomod_b200_int.so) that can be selected at run
+    time with the NANOMOD_B200_LIB environment variable; the default build has neither."""
     os.makedirs(OUT_DIR, exist_ok=True)
+    lib = LIB.replace(".so", suffix + ".so")
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
-        results = list(ex.map(lambda u: _compile(u, force), UNITS))
+        results = list(ex.map(lambda u: _compile(u, force, defs, suffix), UNITS))
     objs = [o for o, _ in results]
     log = "\n".join(l for _, l in results if l)
     if log:
-        with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+        with open(os.path.join(OUT_DIR, "ptxas%s.log" % suffix), "w") as f:
             f.write(log)
         if verbose:
             print(log)
-    if force or _stale(LIB, objs):
-        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    if force or _stale(lib, objs):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    _defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    _suf = "".join(a[len("--suffix="):] for a in sys.argv[1:] if a.startswith("--suffix="))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defs=_defs, suffix=_suf))

@@ -505,11 +505,10 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   return NM_OK;
 }
 
-static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int lane_smem,
-                           int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
-    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, lane_smem, st);
+    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -591,14 +590,15 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.row_pos_index = tb->row_pos_index; ka.row_n0 = tb->n0; ka.row_n1 = tb->n1;
   ka.n_rows = n_rows;
   const int ncls = (sum.max_lane_n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
-  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 1);
+  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 2);
+  ka.one = 1;
+  ka.mone = -1;
   ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
   ka.deep_rows = (const int32_t*)h->d_deep_rows.p; ka.n_deep = sum.n_deep;
-  const int lane_smem = 16 + 2 * ka.region_floats * (int)sizeof(float);
   const int deep_smem = 16 + (sum.max_deep_p2 + 8) * (int)sizeof(float);
-  rc = nm_launch_tiers(h, ka, want_u, want_t, lane_smem, deep_smem, n_rows, sum.n_deep, st);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;
 
   // ---- neighbour combination

@@ -100,6 +100,7 @@ struct nm_kargs {
   const int32_t* row_n1;
   int64_t n_rows;
   int region_floats;  // floats per group region in shared memory (lane tier)
+  int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int32_t* ks_dnum;
   double* ks_d;
   double* ks_p;
@@ -133,4 +134,4 @@ __device__ __forceinline__ void nm_store_row(const nm_kargs& a, int64_t r, const
 
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int smem_bytes, cudaStream_t st);
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, cudaStream_t st);

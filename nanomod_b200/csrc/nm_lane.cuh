@@ -9,6 +9,8 @@
 // against the oracle on the CPU; the product runs it only inside nm_lane_kernel.
 #pragma once
 
+#include <string.h>
+
 #include "nm_math.cuh"
 
 #define NM_LANE_MAX_N 128  // largest per-group coverage handled by the lane tier
@@ -17,6 +19,44 @@
 template <int N>
 struct nm_sortnet;
 
+// Sort keys.  Default: the float32 values themselves (FMNMX compare-exchange).  With
+// -DNM_INT_KEYS the values are mapped to order-preserving int32 keys so that two thirds of the
+// compare-exchanges can run as {min, a+b-min} with the additions issued as IMADs on the FMA
+// pipe, which is otherwise idle (the ALU pipe is the bottleneck of the sort: tools/ubench.cu).
+// x + 0.0f folds -0.0 into +0.0 first, so that -0.0 and 0.0 stay tied as they are for scipy.
+#ifdef NM_INT_KEYS
+typedef int nm_key;
+NM_HD nm_key nm_make_key(float x) {
+  const float y = x + 0.0f;
+#if defined(__CUDA_ARCH__)
+  const int k = __float_as_int(y);
+#else
+  int k;
+  memcpy(&k, &y, sizeof(k));
+#endif
+  return k ^ ((k >> 31) & 0x7fffffff);
+}
+#define NM_KEY_PINF 0x7f800000
+#define NM_KEY_NINF ((int)0x807fffff)
+NM_HD int nm_min(int a, int b) { return a < b ? a : b; }
+NM_HD int nm_max(int a, int b) { return a > b ? a : b; }
+#define NM_CEB(i, j)                          \
+  {                                           \
+    const T lo_ = nm_min(x[i], x[j]);         \
+    const T t_ = x[i] * one + x[j];           \
+    x[j] = lo_ * mone + t_;                   \
+    x[i] = lo_;                               \
+  }
+#else
+typedef float nm_key;
+NM_HD nm_key nm_make_key(float x) { return x; }
+#define NM_KEY_PINF INFINITY
+#define NM_KEY_NINF (-INFINITY)
+#define NM_CEB(i, j) NM_CE(i, j)
+#endif
+NM_HD float nm_min(float a, float b) { return fminf(a, b); }
+NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
+
 #define NM_CE(i, j)                    \
   {                                    \
     const T lo_ = nm_min(x[i], x[j]);  \
@@ -24,10 +64,9 @@ struct nm_sortnet;
     x[i] = lo_;                        \
     x[j] = hi_;                        \
   }
-NM_HD float nm_min(float a, float b) { return fminf(a, b); }
-NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
 #include "nm_sortnet.inc"
 #undef NM_CE
+#undef NM_CEB
 
 // Per-position integer/moment results before the fp64 tails.
 struct nm_lane_acc {
@@ -53,42 +92,92 @@ NM_HD void nm_moments(const float* x, int n, double* mean_out, double* var_out) 
   *var_out = ss / (double)(n - 1);
 }
 
-// One merge-walk over the two sorted groups.  A(i)/B(j) return sorted element i/j, and +inf
-// for i >= n0 / j >= n1 (network padding + one sentinel slot).  The ECDF difference is
-// evaluated only where the next pooled value is strictly larger, i.e. after a whole tie
-// group has been consumed from BOTH samples -- this is searchsorted(side='right') of the
-// reference.  tmax >= n0+n1 is the (warp-uniform) trip count.
-template <bool WANT_U, class AccA, class AccB>
-NM_HD void nm_merge_walk(int n0, int n1, int tmax, const AccA& A, const AccB& B, nm_lane_acc* acc) {
-  int i = 0, j = 0;
-  float va = A(0), vb = B(0);
-  float v = fminf(va, vb);
-  int dmax = 0;
-  int g = 0, ig = 0, r2 = 0, tie = 0;
-  const int T = n0 + n1;
-  for (int s = 0; s < tmax; ++s) {
-    const bool act = s < T;
-    const bool le = va <= vb;
-    i += (act && le) ? 1 : 0;
-    j += (act && !le) ? 1 : 0;
-    va = A(i);
-    vb = B(j);
-    const float vn = fminf(va, vb);
-    const bool endg = act && (vn > v);
-    v = vn;
-    int d = i * n1 - j * n0;
-    d = d < 0 ? -d : d;
-    if (endg) {
-      dmax = d > dmax ? d : dmax;
+// Merge walk over the two sorted groups, split into two independent dependency chains that
+// meet in the middle (instruction-level parallelism: each chain is a serial pointer chase).
+//
+// Column layout (stride S floats between consecutive elements; S = 32 on the device, where a
+// lane's sorted group is stored transposed so that data-dependent indexing never bank-conflicts):
+//   col[0] = -inf | col[(k+1)*S] = k-th smallest key, k < n | +inf from row n+1 .. N+1.
+// Forward chain: takes the pooled elements 0 .. T/2-1 in ascending order (ties: group 0 first).
+// Backward chain: takes T-1 .. T/2 in descending order (ties: group 1 first) -- the mirror rule,
+// so both chains describe the same pooled order and stop at the same split (i*, j*).
+// The ECDF difference c0*n1 - c1*n0 is evaluated only at tie-group boundaries, i.e. where the
+// next pooled value differs -- searchsorted(side='right') of scipy-1.2.1 ks_2samp.  For the rank
+// statistics each chain closes the tie groups that lie entirely on its side; the group that
+// straddles the split (if any) is closed once, after the loop.  iters >= ceil((n0+n1)/2) is the
+// warp-uniform trip count.
+template <bool WANT_U, int S>
+NM_HD void nm_merge_walk(const nm_key* colA, const nm_key* colB, int n0, int n1, int iters,
+                         nm_lane_acc* acc) {
+  const int T = n0 + n1, T1 = T >> 1, T2 = T - T1;
+  const nm_key* fa = colA + S;
+  const nm_key* fb = colB + S;
+  nm_key va = *fa, vb = *fb, v = nm_min(va, vb);
+  const nm_key* ba = colA + n0 * S;
+  const nm_key* bb = colB + n1 * S;
+  nm_key ea = *ba, eb = *bb, w = nm_max(ea, eb);
+  int df = 0, db = 0, dmax = 0;
+  int fi = 0, g = 0, ig = 0;    // forward: group-0 count, open group start (count, group-0 count)
+  int bi = n0, h = T, ih = n0;  // backward: group-0 count below, open group end (count, group-0 count)
+  int r2 = 0, tie = 0;
+  for (int s = 0; s < iters; ++s) {
+    {
+      const bool act = s < T1;
+      const bool le = va <= vb;
+      const bool ta = act && le, tb = act && !le;
+      fa += ta ? S : 0;
+      fb += tb ? S : 0;
+      df += ta ? n1 : 0;
+      df -= tb ? n0 : 0;
+      va = *fa;
+      vb = *fb;
+      const nm_key vn = nm_min(va, vb);
+      const bool q = act && (vn > v);
+      v = vn;
+      const int ad = df < 0 ? -df : df;
+      dmax = (q && ad > dmax) ? ad : dmax;
       if (WANT_U) {
-        const int tc = i + j;
-        const int t = tc - g;
-        r2 += (i - ig) * (g + tc + 1);
+        fi += ta ? 1 : 0;
+        const int tc = s + 1;
+        const int t = q ? tc - g : 0;
+        const int ca = q ? fi - ig : 0;
+        r2 += ca * (g + tc + 1);
         tie += t * (t * t - 1);
-        g = tc;
-        ig = i;
+        g = q ? tc : g;
+        ig = q ? fi : ig;
       }
     }
+    {
+      const bool act = s < T2;
+      const bool ge = eb >= ea;
+      const bool tb = act && ge, ta = act && !ge;
+      bb -= tb ? S : 0;
+      ba -= ta ? S : 0;
+      db += tb ? n0 : 0;
+      db -= ta ? n1 : 0;
+      ea = *ba;
+      eb = *bb;
+      const nm_key wn = nm_max(ea, eb);
+      const bool q = act && (wn < w);
+      w = wn;
+      const int ad = db < 0 ? -db : db;
+      dmax = (q && ad > dmax) ? ad : dmax;
+      if (WANT_U) {
+        bi -= ta ? 1 : 0;
+        const int tc = T - (s + 1);
+        const int t = q ? h - tc : 0;
+        const int ca = q ? ih - bi : 0;
+        r2 += ca * (tc + h + 1);
+        tie += t * (t * t - 1);
+        h = q ? tc : h;
+        ih = q ? bi : ih;
+      }
+    }
+  }
+  if (WANT_U) {  // the tie group straddling the split: [g, h); empty (t = 0) when both closed
+    const int t = h - g;
+    r2 += (ih - ig) * (g + h + 1);
+    tie += t * (t * t - 1);
   }
   acc->dnum = dmax;
   acc->r2 = r2;

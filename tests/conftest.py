@@ -21,18 +21,20 @@ class RowOut(ctypes.Structure):
                 ("t_stat", ctypes.c_double), ("t_p", ctypes.c_double), ("flags", ctypes.c_int)]
 
 
-@pytest.fixture(scope="session")
-def emul():
+@pytest.fixture(scope="session", params=["float_keys", "int_keys"])
+def emul(request):
     """g++ build of tests/host_emul/emul.cpp: the product's host/device headers compiled for the
-    CPU so their logic can be checked without a GPU.  Test harness only."""
+    CPU so their logic can be checked without a GPU.  Test harness only.  Built twice: with the
+    default float32 sort keys and with -DNM_INT_KEYS (order-preserving int32 keys)."""
     src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
     out_dir = os.path.join(ROOT, "tests", "host_emul", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libemul.so")
+    lib = os.path.join(out_dir, "libemul_%s.so" % request.param)
     deps = [src] + [os.path.join(ROOT, "nanomod_b200", "csrc", f)
                     for f in ("nm_math.cuh", "nm_lane.cuh", "nm_deep.cuh", "nm_sortnet.inc")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", lib])
+        defs = ["-DNM_INT_KEYS"] if request.param == "int_keys" else []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + defs + ["-x", "c++", src, "-o", lib])
     L = ctypes.CDLL(lib)
     assert L.emul_sizeof_row_out() == ctypes.sizeof(RowOut)
     dbl = ctypes.c_double

@@ -13,39 +13,38 @@
 #include "../../nanomod_b200/csrc/nm_deep.cuh"
 
 namespace {
-struct ArrAcc {
-  const float* p;
-  float operator()(int i) const { return p[i]; }
-};
+volatile int g_one = 1, g_mone = -1;  // runtime constants, as on the device
 
 template <int N>
 void lane_position(const float* a, int n0, const float* b, int n1, bool want_u, bool want_t,
                    nm_row_out* out) {
   nm_lane_acc acc;
   memset(&acc, 0, sizeof(acc));
-  std::vector<float> sa(N + 1), sb(N + 1);
+  std::vector<nm_key> sa(N + 2), sb(N + 2);
   {
-    float x[N];
-    for (int k = 0; k < N; ++k) x[k] = k < n0 ? a[k] : INFINITY;
+    nm_key x[N];
+    for (int k = 0; k < N; ++k) x[k] = k < n0 ? nm_make_key(a[k]) : (nm_key)NM_KEY_PINF;
     if (want_t) nm_moments(a, n0, &acc.mean0, &acc.var0);
-    nm_sortnet<N>::run(x);
-    for (int k = 0; k < N; ++k) sa[k] = x[k];
-    sa[N] = INFINITY;
+    nm_sortnet<N>::run(x, g_one, g_mone);
+    sa[0] = NM_KEY_NINF;
+    for (int k = 0; k < N; ++k) sa[k + 1] = x[k];
+    sa[N + 1] = NM_KEY_PINF;
   }
   {
-    float x[N];
-    for (int k = 0; k < N; ++k) x[k] = k < n1 ? b[k] : INFINITY;
+    nm_key x[N];
+    for (int k = 0; k < N; ++k) x[k] = k < n1 ? nm_make_key(b[k]) : (nm_key)NM_KEY_PINF;
     if (want_t) nm_moments(b, n1, &acc.mean1, &acc.var1);
-    nm_sortnet<N>::run(x);
-    for (int k = 0; k < N; ++k) sb[k] = x[k];
-    sb[N] = INFINITY;
+    nm_sortnet<N>::run(x, g_one, g_mone);
+    sb[0] = NM_KEY_NINF;
+    for (int k = 0; k < N; ++k) sb[k + 1] = x[k];
+    sb[N + 1] = NM_KEY_PINF;
   }
-  ArrAcc A{sa.data()}, B{sb.data()};
-  // tmax deliberately larger than n0+n1: lanes of a warp share the longest trip count
+  // iters deliberately larger than needed: lanes of a warp share the longest trip count
+  const int iters = (n0 + n1 + 1) / 2 + 3;
   if (want_u)
-    nm_merge_walk<true>(n0, n1, n0 + n1 + 5, A, B, &acc);
+    nm_merge_walk<true, 1>(sa.data(), sb.data(), n0, n1, iters, &acc);
   else
-    nm_merge_walk<false>(n0, n1, n0 + n1 + 5, A, B, &acc);
+    nm_merge_walk<false, 1>(sa.data(), sb.data(), n0, n1, iters, &acc);
   nm_lane_finish(acc, n0, n1, want_u, want_t, out);
 }
 }  // namespace
