@@ -508,7 +508,7 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
 static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
-    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, st);
+    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, h->sm_count, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -593,6 +593,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 2);
   ka.one = 1;
   ka.mone = -1;
+  ka.tile_cursor = &h->d_sum->tile_cursor;
   ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;

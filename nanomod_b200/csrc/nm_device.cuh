@@ -46,6 +46,11 @@ __device__ __forceinline__ void nm_bulk_g2s(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// L2 prefetch of a contiguous global range (no shared memory involved)
+__device__ __forceinline__ void nm_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ long long nm_warp_min_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -79,7 +84,8 @@ struct nm_summary {
   int n_deep;       // rows with max(n0,n1) > NM_LANE_TIER_MAX
   int max_deep_p2;  // max over deep rows of pow2ceil(n0)+pow2ceil(n1)
   int deep_cursor;
-  int pad[2];
+  int tile_cursor;  // lane-tier work queue (tiles beyond the first wave)
+  int pad;
 };
 
 
@@ -101,6 +107,7 @@ struct nm_kargs {
   int64_t n_rows;
   int region_floats;  // floats per group region in shared memory (lane tier)
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
+  int* tile_cursor;   // device counter, zero at launch
   int32_t* ks_dnum;
   double* ks_d;
   double* ks_p;
@@ -134,4 +141,4 @@ __device__ __forceinline__ void nm_store_row(const nm_kargs& a, int64_t r, const
 
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, cudaStream_t st);
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st);

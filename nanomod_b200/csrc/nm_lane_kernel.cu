@@ -164,6 +164,68 @@ __device__ __forceinline__ int nm_lane_gather(float* region, const float* __rest
   return base;
 }
 
+// Per-lane description of one row of a tile (tile = 32 consecutive rows, one per lane).
+struct nm_tile_meta {
+  int64_t r;        // row index
+  long long s0, s1; // start of the row's slices in vals0 / vals1
+  int n0, n1;       // coverage (0 when the lane has no lane-tier row)
+  bool ok;
+};
+
+__device__ __forceinline__ nm_tile_meta nm_tile_fetch(const nm_kargs& a, int64_t tile, int lane) {
+  nm_tile_meta m;
+  m.r = tile * 32 + lane;
+  m.n0 = m.n1 = 0;
+  m.s0 = m.s1 = 0;
+  m.ok = false;
+  if (tile >= 0 && m.r < a.n_rows) {
+    const int nn0 = a.row_n0[m.r], nn1 = a.row_n1[m.r];
+    if (nn0 <= NM_LANE_TIER_MAX && nn1 <= NM_LANE_TIER_MAX) {
+      const int32_t src = a.row_pos_index[m.r];
+      m.ok = true;
+      m.n0 = nn0;
+      m.n1 = nn1;
+      m.s0 = a.off0[src];
+      m.s1 = a.off1[src];
+    }
+  }
+  return m;
+}
+
+// Warp-level plan for staging a tile: where its two value slices start, whether each is one
+// contiguous run of the CSR array (-> one TMA bulk copy) and each lane's offset in the region.
+struct nm_tile_stage {
+  long long al0, al1;      // 16-byte aligned starts of the bulk copies
+  unsigned bytes0, bytes1; // bulk copy sizes (0: not contiguous, use the gather)
+  int base0, base1;        // this lane's row offset inside region A / B (contiguous case)
+  int nmax, tmax;
+  bool any;
+};
+
+__device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
+  nm_tile_stage st;
+  const long long big = 0x7fffffffffffffffLL;
+  st.any = __any_sync(0xffffffffu, m.ok);
+  const long long first0 = nm_warp_min_ll(m.ok ? m.s0 : big), first1 = nm_warp_min_ll(m.ok ? m.s1 : big);
+  const long long end0 = nm_warp_max_ll(m.ok ? m.s0 + m.n0 : -1), end1 = nm_warp_max_ll(m.ok ? m.s1 + m.n1 : -1);
+  const int tot0 = __reduce_add_sync(0xffffffffu, m.n0), tot1 = __reduce_add_sync(0xffffffffu, m.n1);
+  st.nmax = __reduce_max_sync(0xffffffffu, m.n0 > m.n1 ? m.n0 : m.n1);
+  st.tmax = __reduce_max_sync(0xffffffffu, m.n0 + m.n1);
+  st.al0 = first0 & ~3LL;
+  st.al1 = first1 & ~3LL;
+  const bool contig0 = st.any && (end0 - first0) == (long long)tot0;
+  const bool contig1 = st.any && (end1 - first1) == (long long)tot1;
+  st.bytes0 = contig0 ? (unsigned)(((first0 - st.al0) + tot0 + 3) & ~3LL) * 4u : 0u;
+  st.bytes1 = contig1 ? (unsigned)(((first1 - st.al1) + tot1 + 3) & ~3LL) * 4u : 0u;
+  st.base0 = m.ok ? (int)(m.s0 - st.al0) : 0;
+  st.base1 = m.ok ? (int)(m.s1 - st.al1) : 0;
+  return st;
+}
+
+// Persistent lane-tier kernel: every warp loops over tiles taken from a global cursor.  While
+// a tile is being sorted, the next tile's metadata is already in registers and its value
+// slices are being pulled into L2; its TMA copies are issued the moment the merge walk has
+// released the two regions, so that they overlap the fp64 tails of the current tile.
 __global__ void __launch_bounds__(32 * NM_LANE_WARPS, 8 / NM_LANE_WARPS)
 nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
@@ -173,76 +235,100 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(my);
   float* regA = reinterpret_cast<float*>(my + 16);
   float* regB = regA + a.region_floats;
+  const int64_t n_tiles = (a.n_rows + 31) >> 5;
+  const int64_t n_warps = (int64_t)gridDim.x * NM_LANE_WARPS;
 
-  const int64_t r = ((int64_t)blockIdx.x * NM_LANE_WARPS + wib) * 32 + lane;
-  int n0 = 0, n1 = 0;
-  long long s0 = 0, s1 = 0;
-  bool ok = false;
-  if (r < a.n_rows) {
-    const int nn0 = a.row_n0[r], nn1 = a.row_n1[r];
-    if (nn0 <= NM_LANE_TIER_MAX && nn1 <= NM_LANE_TIER_MAX) {
-      const int32_t src = a.row_pos_index[r];
-      ok = true;
-      n0 = nn0;
-      n1 = nn1;
-      s0 = a.off0[src];
-      s1 = a.off1[src];
-    }
-  }
-  if (!__any_sync(0xffffffffu, ok)) return;
-
-  const long long big = 0x7fffffffffffffffLL;
-  const long long first0 = nm_warp_min_ll(ok ? s0 : big), first1 = nm_warp_min_ll(ok ? s1 : big);
-  const long long end0 = nm_warp_max_ll(ok ? s0 + n0 : -1), end1 = nm_warp_max_ll(ok ? s1 + n1 : -1);
-  const int tot0 = __reduce_add_sync(0xffffffffu, n0), tot1 = __reduce_add_sync(0xffffffffu, n1);
-  const bool contig0 = (end0 - first0) == (long long)tot0;
-  const bool contig1 = (end1 - first1) == (long long)tot1;
-  const int nmax = __reduce_max_sync(0xffffffffu, n0 > n1 ? n0 : n1);
-  const int tmax = __reduce_max_sync(0xffffffffu, n0 + n1);
-  const int nsel = (nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
-
-  // stage the tile: one TMA bulk copy per contiguous group slice, else a cooperative gather
-  const long long al0 = first0 & ~3LL, al1 = first1 & ~3LL;
-  int base0 = ok ? (int)(s0 - al0) : 0, base1 = ok ? (int)(s1 - al1) : 0;
-  if (contig0 || contig1) {
-    if (lane == 0) {
-      nm_mbar_init(bar, 1);
-      const uint32_t b0 = contig0 ? (uint32_t)(((first0 - al0) + tot0 + 3) & ~3LL) * 4u : 0u;
-      const uint32_t b1 = contig1 ? (uint32_t)(((first1 - al1) + tot1 + 3) & ~3LL) * 4u : 0u;
-      nm_mbar_expect_tx(bar, b0 + b1);
-      if (contig0) nm_bulk_g2s(regA, a.vals0 + al0, b0, bar);
-      if (contig1) nm_bulk_g2s(regB, a.vals1 + al1, b1, bar);
-    }
-    __syncwarp();
-  }
-  if (!contig0) base0 = nm_lane_gather(regA, a.vals0, s0, n0, lane);
-  if (!contig1) base1 = nm_lane_gather(regB, a.vals1, s1, n1, lane);
-  if (contig0 || contig1) nm_mbar_wait(bar, 0);
+  int64_t tile = (int64_t)blockIdx.x * NM_LANE_WARPS + wib;
+  if (tile >= n_tiles) return;
+  if (lane == 0) nm_mbar_init(bar, 1);
   __syncwarp();
+  unsigned parity = 0;
 
-  nm_lane_acc acc;
-  acc.dnum = acc.r2 = acc.tie = 0;
-  acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
+  nm_tile_meta cur = nm_tile_fetch(a, tile, lane);
+  nm_tile_stage cst = nm_tile_plan(cur);
+  bool staged = false;  // TMA for `cur` already issued?
+
+  while (true) {
+    // ---- claim the next tile and start fetching its metadata (consumed after the walk)
+    int64_t next = -1;
+    {
+      long long t = 0;
+      if (lane == 0) t = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+      t = __shfl_sync(0xffffffffu, t, 0);
+      next = t < n_tiles ? t : -1;
+    }
+    const nm_tile_meta nxt = nm_tile_fetch(a, next, lane);
+
+    if (cst.any) {
+      // ---- stage the current tile (unless its copies were issued at the end of the last one)
+      if (!staged && (cst.bytes0 | cst.bytes1) && lane == 0) {
+        nm_mbar_expect_tx(bar, cst.bytes0 + cst.bytes1);
+        if (cst.bytes0) nm_bulk_g2s(regA, a.vals0 + cst.al0, cst.bytes0, bar);
+        if (cst.bytes1) nm_bulk_g2s(regB, a.vals1 + cst.al1, cst.bytes1, bar);
+      }
+      int base0 = cst.base0, base1 = cst.base1;
+      if (!cst.bytes0) base0 = nm_lane_gather(regA, a.vals0, cur.s0, cur.n0, lane);
+      if (!cst.bytes1) base1 = nm_lane_gather(regB, a.vals1, cur.s1, cur.n1, lane);
+      // plan the next tile now (its metadata loads have had the whole staging latency to land)
+      // and pull its value slices into L2 while this tile is being sorted
+      const nm_tile_stage nst = nm_tile_plan(nxt);
+      if (lane == 0) {
+        if (nst.bytes0) nm_prefetch_l2(a.vals0 + nst.al0, nst.bytes0);
+        if (nst.bytes1) nm_prefetch_l2(a.vals1 + nst.al1, nst.bytes1);
+      }
+      if (cst.bytes0 | cst.bytes1) {
+        nm_mbar_wait(bar, parity);
+        parity ^= 1u;
+      }
+      __syncwarp();
+
+      const int n0 = cur.n0, n1 = cur.n1;
+      const int nsel = (cst.nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+      nm_lane_acc acc;
+      acc.dnum = acc.r2 = acc.tie = 0;
+      acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
 #define NM_CALL(NN) \
   nm_lane_tile<NN>(regA, regB, base0, base1, n0, n1, lane, want_t != 0, a.one, a.mone, &acc)
-  NM_DISPATCH_N(nsel, NM_CALL)
+      NM_DISPATCH_N(nsel, NM_CALL)
 #undef NM_CALL
 
-  const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
-  const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
-  const int iters = (tmax + 1) >> 1;
-  const bool uniform = __all_sync(0xffffffffu, ok && (n0 + n1 == tmax));
-  if (want_u)
-    nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
-  else if (uniform)
-    acc.dnum = nm_walk_ks_uniform(colA, colB, n0, n1);
-  else
-    nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
+      const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
+      const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
+      const int iters = (cst.tmax + 1) >> 1;
+      const bool uniform = __all_sync(0xffffffffu, cur.ok && (n0 + n1 == cst.tmax));
+      if (want_u)
+        nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
+      else if (uniform)
+        acc.dnum = nm_walk_ks_uniform(colA, colB, n0, n1);
+      else
+        nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
 
-  if (ok) {
-    nm_row_out o;
-    nm_lane_finish(acc, n0, n1, want_u != 0, want_t != 0, &o);
-    nm_store_row(a, r, o, want_u != 0, want_t != 0);
+      // ---- the regions are free again: issue the next tile's copies before the fp64 tails
+      __syncwarp();
+      staged = false;
+      if (nst.any && (nst.bytes0 | nst.bytes1)) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          nm_mbar_expect_tx(bar, nst.bytes0 + nst.bytes1);
+          if (nst.bytes0) nm_bulk_g2s(regA, a.vals0 + nst.al0, nst.bytes0, bar);
+          if (nst.bytes1) nm_bulk_g2s(regB, a.vals1 + nst.al1, nst.bytes1, bar);
+        }
+        staged = true;
+      }
+
+      if (cur.ok) {
+        nm_row_out o;
+        nm_lane_finish(acc, n0, n1, want_u != 0, want_t != 0, &o);
+        nm_store_row(a, cur.r, o, want_u != 0, want_t != 0);
+      }
+      cur = nxt;
+      cst = nst;
+    } else {
+      cur = nxt;
+      cst = nm_tile_plan(nxt);
+      staged = false;
+    }
+    if (next < 0) break;
   }
 }
 
@@ -250,13 +336,19 @@ int nm_lane_smem_bytes(int region_floats) {
   return NM_LANE_WARPS * (16 + 2 * region_floats * (int)sizeof(float));
 }
 
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, cudaStream_t st) {
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
   const int smem_bytes = nm_lane_smem_bytes(ka.region_floats);
   cudaError_t e = cudaFuncSetAttribute(nm_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        smem_bytes);
   if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_lane_kernel, 32 * NM_LANE_WARPS, smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) per_sm = 1;
   const int64_t tiles = (ka.n_rows + 31) / 32;
-  const unsigned grid = (unsigned)((tiles + NM_LANE_WARPS - 1) / NM_LANE_WARPS);
-  nm_lane_kernel<<<grid, 32 * NM_LANE_WARPS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+  int64_t grid = (tiles + NM_LANE_WARPS - 1) / NM_LANE_WARPS;
+  const int64_t resident = (int64_t)per_sm * sm_count;
+  if (grid > resident) grid = resident;
+  nm_lane_kernel<<<(unsigned)grid, 32 * NM_LANE_WARPS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
   return (int)cudaGetLastError();
 }

@@ -2,7 +2,7 @@
 # Second GPU session: compare lane-kernel build variants (parity + bench), profile two of them.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-for v in "" _w4 _int _int_w4; do
+for v in "" _w4 _int _int_w4 _int_w8; do
   export NANOMOD_B200_LIB=$PWD/nanomod_b200/_C/libnanomod_b200$v.so
   echo "== variant '$v'"
   timeout 900 python -m pytest tests -m gpu -q --maxfail=5 -p no:cacheprovider > gpurun_out/pytest_gpu$v.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu$v.log
