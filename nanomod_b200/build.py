@@ -18,6 +18,9 @@ LIB = os.path.join(OUT_DIR, "libnanomod_b200.so")
 UNITS = ["nm_api.cu", "nm_lane_kernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# Default configuration of the lane tier (profiles/round1_variants.md): order-preserving int32
+# sort keys with the mixed ALU/FMA compare-exchange, four independent warps (tiles) per CTA.
+DEFAULT_DEFS = ("NM_INT_KEYS", "NM_LANE_WARPS=4")
 
 
 def _deps():
@@ -38,7 +41,7 @@ def _compile(unit, force, defs=(), suffix=""):
     obj = os.path.join(OUT_DIR, unit.replace(".cu", suffix + ".o"))
     if not force and not _stale(obj, [src] + _deps()):
         return obj, ""
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defs] + ["-c", src, "-o", obj]
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in (defs or DEFAULT_DEFS)] + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, r.stdout, r.stderr))
