@@ -19,8 +19,8 @@ UNITS = ["nm_api.cu", "nm_lane_kernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # Default configuration of the lane tier (profiles/round1_variants.md): order-preserving int32
-# sort keys with the mixed ALU/FMA compare-exchange, four independent warps (tiles) per CTA.
-DEFAULT_DEFS = ("NM_INT_KEYS", "NM_LANE_WARPS=4")
+# sort keys with the mixed ALU/FMA compare-exchange (CTA shape is chosen at launch).
+DEFAULT_DEFS = ("NM_INT_KEYS",)
 
 
 def _deps():

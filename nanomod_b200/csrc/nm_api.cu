@@ -505,10 +505,10 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   return NM_OK;
 }
 
-static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
-    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, h->sm_count, st);
+    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, max_lane_n, h->sm_count, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -599,7 +599,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
   ka.deep_rows = (const int32_t*)h->d_deep_rows.p; ka.n_deep = sum.n_deep;
   const int deep_smem = 16 + (sum.max_deep_p2 + 8) * (int)sizeof(float);
-  rc = nm_launch_tiers(h, ka, want_u, want_t, deep_smem, n_rows, sum.n_deep, st);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, sum.max_lane_n, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;
 
   // ---- neighbour combination

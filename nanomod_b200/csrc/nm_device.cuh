@@ -141,4 +141,5 @@ __device__ __forceinline__ void nm_store_row(const nm_kargs& a, int64_t r, const
 
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st);
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count,
+                   cudaStream_t st);

@@ -65,8 +65,46 @@ NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
     x[j] = hi_;                        \
   }
 #include "nm_sortnet.inc"
+
+// Looped, small-footprint sorts for the large size classes (tools/gen_sortloop.py).
+template <int N>
+struct nm_sortloop;
+#define NM_NO_UNROLL _Pragma("unroll 1")
+// rotate the register array left by Q: x[k] <- x[k+Q] (register moves; indices stay static)
+#define NM_ROTATE(x, N, Q)                                       \
+  {                                                              \
+    T t_[Q];                                                     \
+    _Pragma("unroll") for (int k_ = 0; k_ < (Q); ++k_) t_[k_] = x[k_];                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < (N) - (Q); ++k_) x[k_] = x[k_ + (Q)];        \
+    _Pragma("unroll") for (int k_ = 0; k_ < (Q); ++k_) x[(N) - (Q) + k_] = t_[k_];       \
+  }
+#include "nm_sortloop.inc"
+#undef NM_ROTATE
 #undef NM_CE
 #undef NM_CEB
+
+// The sorter of a size class: flat network for N < 72 (code <= ~20 KB), looped sort above.
+// run() leaves the k-th smallest key in x[order(k)].
+// Looped sorts are OFF by default: in isolation they win (tools/ubench3.cu), inside the lane
+// kernel the register moves push the FMA pipe to the limit and the kernel got slower
+// (profiles/round1_variants.md).  -DNM_LOOPED_MIN_N=72 turns them on for N >= 72.
+#ifndef NM_LOOPED_MIN_N
+#define NM_LOOPED_MIN_N 1000
+#endif
+template <int N, bool LOOPED = (N >= NM_LOOPED_MIN_N)>
+struct nm_sorter;
+template <int N>
+struct nm_sorter<N, false> {
+  template <class T>
+  NM_HD static void run(T (&x)[N], int one, int mone) { nm_sortnet<N>::run(x, one, mone); }
+  NM_HD static constexpr int order(int k) { return k; }
+};
+template <int N>
+struct nm_sorter<N, true> {
+  template <class T>
+  NM_HD static void run(T (&x)[N], int one, int mone) { nm_sortloop<N>::run(x, one, mone); }
+  NM_HD static int order(int k) { return nm_sortloop<N>::order(k); }
+};
 
 // Per-position integer/moment results before the fp64 tails.
 struct nm_lane_acc {

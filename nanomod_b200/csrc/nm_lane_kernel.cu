@@ -12,22 +12,83 @@
 //   3. one merge walk per lane gives the KS numerator (+ rank sums), then the fp64 tails.
 #include "nm_device.cuh"
 
-#ifndef NM_LANE_WARPS
-#define NM_LANE_WARPS 1  // warps (= independent 32-row tiles) per CTA
-#endif
+#define NM_LANE_MAX_WARPS 4  // warps (= independent 32-row tiles) per CTA, chosen at launch
+
+// Visit the row's values through 128-bit shared-memory loads from the 16-byte aligned address
+// below the row (N/4 + 1 loads): window slot e holds row element e - shift and is valid iff
+// 0 <= e - shift < n.  BODY sees (e, j_ = e & 3, valid, v).
+#define NM_FOR_ROW(NQ, raw4, shift, n, BODY)                                     \
+  _Pragma("unroll") for (int q_ = 0; q_ < (NQ); ++q_) {                          \
+    const float4 v4_ = (raw4)[q_];                                               \
+    const float vv_[4] = {v4_.x, v4_.y, v4_.z, v4_.w};                           \
+    _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) {                           \
+      const int e = 4 * q_ + j_;                                                 \
+      const bool valid = (unsigned)(e - (shift)) < (unsigned)(n);                \
+      const float v = vv_[j_];                                                   \
+      BODY                                                                       \
+    }                                                                            \
+    /* keep ptxas from hoisting every load above the first use (register pressure) */ \
+    if ((q_ & 3) == 3) asm volatile("" ::: "memory");                            \
+  }
+
+// sum of four accumulators that were filled by window slot (e & 3), combined in the order of the
+// ROW index class ((e - shift) & 3): the result does not depend on the row's alignment
+__device__ __forceinline__ double nm_sum4_by_row_class(const double (&s)[4], int shift) {
+  const double c0 = shift == 0 ? s[0] : shift == 1 ? s[1] : shift == 2 ? s[2] : s[3];
+  const double c1 = shift == 0 ? s[1] : shift == 1 ? s[2] : shift == 2 ? s[3] : s[0];
+  const double c2 = shift == 0 ? s[2] : shift == 1 ? s[3] : shift == 2 ? s[0] : s[1];
+  const double c3 = shift == 0 ? s[3] : shift == 1 ? s[0] : shift == 2 ? s[1] : s[2];
+  return __dadd_rn(__dadd_rn(c0, c1), __dadd_rn(c2, c3));
+}
+
+// Welch moments of one row: two-pass, fp64, four accumulators by row index mod 4, read through
+// the same aligned 128-bit window as the sort.  A ROLLED loop with explicitly rounded
+// operations: the instruction sequence applied to a row depends only on the row itself (not on
+// its alignment, its tile or the tile's network size), so results are bit-identical however
+// the genome is sharded -- and the loop body stays in the instruction cache.
+__device__ __forceinline__ void nm_lane_moments(const float* region, int base, int n, double* mean,
+                                                double* var) {
+  const int shift = base & 3;
+  const float4* raw4 = reinterpret_cast<const float4*>(region + (base - shift));
+  const int nq = __reduce_max_sync(0xffffffffu, (shift + n + 3) >> 2);
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const float4 v4 = raw4[q];
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
+      s[j] = __dadd_rn(s[j], valid ? (double)vv[j] : 0.0);
+    }
+  }
+  const double m = __ddiv_rn(nm_sum4_by_row_class(s, shift), (double)n);
+  double ss[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const float4 v4 = raw4[q];
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
+      const double d = valid ? __dsub_rn((double)vv[j], m) : 0.0;
+      ss[j] = __fma_rn(d, d, ss[j]);
+    }
+  }
+  *mean = m;
+  *var = __ddiv_rn(nm_sum4_by_row_class(ss, shift), (double)(n - 1));
+}
 
 // Load one group's row into registers (pad +inf), sort, write back transposed with a -inf row
 // in front and a +inf sentinel row behind (layout expected by nm_merge_walk).
 template <int N>
 __device__ __forceinline__ void nm_lane_sort_group(float* region, int base, int n, int lane,
-                                                   bool want_t, int one, int mone, double* mean,
-                                                   double* var) {
+                                                   int one, int mone) {
   nm_key x[N];
-  const float* raw = region + base;
-  if (want_t) nm_moments(raw, n, mean, var);
-  const bool vec = __all_sync(0xffffffffu, ((base & 3) == 0) && (n == N));
-  if (vec) {
-    const float4* raw4 = reinterpret_cast<const float4*>(raw);
+  const int shift = base & 3;
+  const float4* raw4 = reinterpret_cast<const float4*>(region + (base - shift));
+  const bool full = __all_sync(0xffffffffu, (shift == 0) && (n == N));
+  if (__builtin_expect(full, 1)) {
 #pragma unroll
     for (int q = 0; q < N / 4; ++q) {
       const float4 v = raw4[q];
@@ -37,38 +98,39 @@ __device__ __forceinline__ void nm_lane_sort_group(float* region, int base, int 
       x[4 * q + 3] = nm_make_key(v.w);
     }
   } else {
+    NM_FOR_ROW(N / 4, raw4, shift, n, { x[e] = valid ? nm_make_key(v) : (nm_key)NM_KEY_PINF; })
+    // the last (up to 3) elements of a long shifted row lie in window slots N..N+2; slots
+    // 0..shift-1 are free exactly then (N + j valid  =>  j < shift), so they wrap around
+    const float4 w4 = raw4[N / 4];
+    const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const float v = raw[k];
-      x[k] = (k < n) ? nm_make_key(v) : (nm_key)NM_KEY_PINF;
+    for (int j = 0; j < 3; ++j) {
+      const bool wrap = (unsigned)(N + j - shift) < (unsigned)n;
+      x[j] = wrap ? nm_make_key(ww[j]) : x[j];
     }
   }
-  nm_sortnet<N>::run(x, one, mone);
+  nm_sorter<N>::run(x, one, mone);
   __syncwarp();  // every lane has consumed its raw row; the region may now be overwritten
   nm_key* col = reinterpret_cast<nm_key*>(region) + lane;
   col[0] = NM_KEY_NINF;
 #pragma unroll
-  for (int k = 0; k < N; ++k) col[(k + 1) << 5] = x[k];
+  for (int k = 0; k < N; ++k) col[(k + 1) << 5] = x[nm_sorter<N>::order(k)];
   col[(N + 1) << 5] = NM_KEY_PINF;
 }
 
 template <int N>
 __device__ __forceinline__ void nm_lane_tile(float* regA, float* regB, int base0, int base1,
-                                             int n0, int n1, int lane, bool want_t, int one,
-                                             int mone, nm_lane_acc* acc) {
+                                             int n0, int n1, int lane, int one, int mone) {
 #pragma unroll 1
-  for (int g = 0; g < 2; ++g) {
-    double m = 0.0, v = 0.0;
-    nm_lane_sort_group<N>(g ? regB : regA, g ? base1 : base0, g ? n1 : n0, lane, want_t, one, mone, &m, &v);
-    if (g) { acc->mean1 = m; acc->var1 = v; } else { acc->mean0 = m; acc->var0 = v; }
-  }
+  for (int g = 0; g < 2; ++g)
+    nm_lane_sort_group<N>(g ? regB : regA, g ? base1 : base0, g ? n1 : n0, lane, one, mone);
   __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
-// Device fast path of nm_merge_walk (KS numerator only) for tiles whose 32 lanes all hold the
-// same pooled count T: no activity predicates, pointer-chasing with predicated adds and loads,
-// and the ECDF numerator carried on the FMA pipe.  Same algorithm, same tie rule, same
+// Device fast path of nm_merge_walk (KS numerator only): no activity predicates,
+// pointer-chasing with predicated adds and loads, and the ECDF numerator carried on the FMA
+// pipe.  Same algorithm, same tie rule, same
 // evaluation points as nm_merge_walk (nm_lane.cuh), which the CPU tests cover; this spelling
 // exists because the ALU pipe is the kernel's bottleneck and the generic code costs ~18
 // instructions per pooled element against 11 here.
@@ -120,9 +182,13 @@ __device__ __forceinline__ void nm_lane_tile(float* regA, float* regB, int base0
       : "+r"(ba), "+r"(bb), "+" NM_KREG(ea), "+" NM_KREG(eb), "+" NM_KREG(w), "+r"(dmax) \
       : "r"(T), "r"(c))
 
-__device__ __forceinline__ int nm_walk_ks_uniform(const nm_key* colA, const nm_key* colB, int n0,
-                                                  int n1) {
-  const int T = n0 + n1, T1 = T >> 1;
+// Both chains run `iters` (warp-uniform, >= ceil(T/2) for every lane) steps, so on lanes whose
+// T is smaller than the warp maximum they overlap in the middle; every evaluated point is still
+// a genuine tie-group boundary, so the maximum is unchanged.  Requires iters <= T on every lane
+// (a chain must not run off the end of the columns).
+__device__ __forceinline__ int nm_walk_ks_fast(const nm_key* colA, const nm_key* colB, int n0,
+                                               int n1, int iters) {
+  const int T = n0 + n1;
   const unsigned A0 = nm_smem_u32(colA), B0 = nm_smem_u32(colB);
   unsigned fa = A0 + 128u, fb = B0 + 128u;
   unsigned ba = A0 + 128u * (unsigned)n0, bb = B0 + 128u * (unsigned)n1;
@@ -135,13 +201,12 @@ __device__ __forceinline__ int nm_walk_ks_uniform(const nm_key* colA, const nm_k
   int cb = -(int)(A0 * (unsigned)T) - k0 * (T - 1);
   int dmax = 0;
 #pragma unroll 4
-  for (int s = 0; s < T1; ++s) {
+  for (int s = 0; s < iters; ++s) {
     NM_FWD_STEP(fa, fb, va, vb, v, cf, dmax);
     NM_BWD_STEP(ba, bb, ea, eb, w, cb, dmax);
     cf -= k0;
     cb += k0;
   }
-  if (T & 1) NM_BWD_STEP(ba, bb, ea, eb, w, cb, dmax);  // the backward chain takes ceil(T/2)
   return dmax >> 7;
 }
 
@@ -209,7 +274,6 @@ __device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
   const long long first0 = nm_warp_min_ll(m.ok ? m.s0 : big), first1 = nm_warp_min_ll(m.ok ? m.s1 : big);
   const long long end0 = nm_warp_max_ll(m.ok ? m.s0 + m.n0 : -1), end1 = nm_warp_max_ll(m.ok ? m.s1 + m.n1 : -1);
   const int tot0 = __reduce_add_sync(0xffffffffu, m.n0), tot1 = __reduce_add_sync(0xffffffffu, m.n1);
-  st.nmax = __reduce_max_sync(0xffffffffu, m.n0 > m.n1 ? m.n0 : m.n1);
   st.tmax = __reduce_max_sync(0xffffffffu, m.n0 + m.n1);
   st.al0 = first0 & ~3LL;
   st.al1 = first1 & ~3LL;
@@ -219,6 +283,7 @@ __device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
   st.bytes1 = contig1 ? (unsigned)(((first1 - st.al1) + tot1 + 3) & ~3LL) * 4u : 0u;
   st.base0 = m.ok ? (int)(m.s0 - st.al0) : 0;
   st.base1 = m.ok ? (int)(m.s1 - st.al1) : 0;
+  st.nmax = __reduce_max_sync(0xffffffffu, m.n0 > m.n1 ? m.n0 : m.n1);
   return st;
 }
 
@@ -226,7 +291,8 @@ __device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
 // a tile is being sorted, the next tile's metadata is already in registers and its value
 // slices are being pulled into L2; its TMA copies are issued the moment the merge walk has
 // released the two regions, so that they overlap the fp64 tails of the current tile.
-__global__ void __launch_bounds__(32 * NM_LANE_WARPS, 8 / NM_LANE_WARPS)
+template <int NMAX>
+__global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, NMAX <= 64 ? 3 : 2)
 nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -236,9 +302,10 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   float* regA = reinterpret_cast<float*>(my + 16);
   float* regB = regA + a.region_floats;
   const int64_t n_tiles = (a.n_rows + 31) >> 5;
-  const int64_t n_warps = (int64_t)gridDim.x * NM_LANE_WARPS;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
 
-  int64_t tile = (int64_t)blockIdx.x * NM_LANE_WARPS + wib;
+  int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
   if (tile >= n_tiles) return;
   if (lane == 0) nm_mbar_init(bar, 1);
   __syncwarp();
@@ -287,19 +354,24 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       nm_lane_acc acc;
       acc.dnum = acc.r2 = acc.tie = 0;
       acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
-#define NM_CALL(NN) \
-  nm_lane_tile<NN>(regA, regB, base0, base1, n0, n1, lane, want_t != 0, a.one, a.mone, &acc)
+      if (want_t) {  // Welch moments from the raw rows, before the sort overwrites them
+        nm_lane_moments(regA, base0, n0, &acc.mean0, &acc.var0);
+        nm_lane_moments(regB, base1, n1, &acc.mean1, &acc.var1);
+      }
+#define NM_CALL(NN)                                                                          \
+  if (NN <= NMAX)                                                                            \
+    nm_lane_tile<(NN <= NMAX ? NN : NMAX)>(regA, regB, base0, base1, n0, n1, lane, a.one, a.mone)
       NM_DISPATCH_N(nsel, NM_CALL)
 #undef NM_CALL
 
       const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
       const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
       const int iters = (cst.tmax + 1) >> 1;
-      const bool uniform = __all_sync(0xffffffffu, cur.ok && (n0 + n1 == cst.tmax));
+      const bool fast = __all_sync(0xffffffffu, n0 + n1 >= iters);
       if (want_u)
         nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
-      else if (uniform)
-        acc.dnum = nm_walk_ks_uniform(colA, colB, n0, n1);
+      else if (fast)
+        acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters);
       else
         nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
 
@@ -332,23 +404,38 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   }
 }
 
-int nm_lane_smem_bytes(int region_floats) {
-  return NM_LANE_WARPS * (16 + 2 * region_floats * (int)sizeof(float));
+static int nm_lane_warp_smem(int region_floats) { return 16 + 2 * region_floats * (int)sizeof(float); }
+
+template <int NMAX>
+static int nm_launch_lane_t(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
+  const int per_warp = nm_lane_warp_smem(ka.region_floats);
+  cudaError_t e = cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       NM_LANE_MAX_WARPS * per_warp);
+  if (e != cudaSuccess) return (int)e;
+  // CTA shape: as many resident warps per SM as shared memory and registers allow
+  int best_w = 1, best_blocks = 0, best_warps = 0;
+  for (int w = NM_LANE_MAX_WARPS; w >= 1; --w) {
+    int blocks = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_kernel<NMAX>, 32 * w, (size_t)w * per_warp);
+    if (e != cudaSuccess) return (int)e;
+    if (blocks * w > best_warps) {
+      best_warps = blocks * w;
+      best_w = w;
+      best_blocks = blocks;
+    }
+  }
+  if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
+  const int64_t tiles = (ka.n_rows + 31) / 32;
+  int64_t grid = (tiles + best_w - 1) / best_w;
+  const int64_t resident = (int64_t)best_blocks * sm_count;
+  if (grid > resident) grid = resident;
+  nm_lane_kernel<NMAX><<<(unsigned)grid, 32 * best_w, (size_t)best_w * per_warp, st>>>(ka, want_u ? 1 : 0,
+                                                                                       want_t ? 1 : 0);
+  return (int)cudaGetLastError();
 }
 
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
-  const int smem_bytes = nm_lane_smem_bytes(ka.region_floats);
-  cudaError_t e = cudaFuncSetAttribute(nm_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem_bytes);
-  if (e != cudaSuccess) return (int)e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_lane_kernel, 32 * NM_LANE_WARPS, smem_bytes);
-  if (e != cudaSuccess) return (int)e;
-  if (per_sm < 1) per_sm = 1;
-  const int64_t tiles = (ka.n_rows + 31) / 32;
-  int64_t grid = (tiles + NM_LANE_WARPS - 1) / NM_LANE_WARPS;
-  const int64_t resident = (int64_t)per_sm * sm_count;
-  if (grid > resident) grid = resident;
-  nm_lane_kernel<<<(unsigned)grid, 32 * NM_LANE_WARPS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
-  return (int)cudaGetLastError();
+// max_n = longest lane-tier row of this call
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st) {
+  if (max_n <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, st);
+  return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
 }

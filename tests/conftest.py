@@ -31,7 +31,7 @@ def emul(request):
     os.makedirs(out_dir, exist_ok=True)
     lib = os.path.join(out_dir, "libemul_%s.so" % request.param)
     deps = [src] + [os.path.join(ROOT, "nanomod_b200", "csrc", f)
-                    for f in ("nm_math.cuh", "nm_lane.cuh", "nm_deep.cuh", "nm_sortnet.inc")]
+                    for f in ("nm_math.cuh", "nm_lane.cuh", "nm_deep.cuh", "nm_sortnet.inc", "nm_sortloop.inc")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         defs = ["-DNM_INT_KEYS"] if request.param == "int_keys" else []
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + defs + ["-x", "c++", src, "-o", lib])

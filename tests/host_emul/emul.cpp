@@ -25,18 +25,18 @@ void lane_position(const float* a, int n0, const float* b, int n1, bool want_u, 
     nm_key x[N];
     for (int k = 0; k < N; ++k) x[k] = k < n0 ? nm_make_key(a[k]) : (nm_key)NM_KEY_PINF;
     if (want_t) nm_moments(a, n0, &acc.mean0, &acc.var0);
-    nm_sortnet<N>::run(x, g_one, g_mone);
+    nm_sorter<N>::run(x, g_one, g_mone);
     sa[0] = NM_KEY_NINF;
-    for (int k = 0; k < N; ++k) sa[k + 1] = x[k];
+    for (int k = 0; k < N; ++k) sa[k + 1] = x[nm_sorter<N>::order(k)];
     sa[N + 1] = NM_KEY_PINF;
   }
   {
     nm_key x[N];
     for (int k = 0; k < N; ++k) x[k] = k < n1 ? nm_make_key(b[k]) : (nm_key)NM_KEY_PINF;
     if (want_t) nm_moments(b, n1, &acc.mean1, &acc.var1);
-    nm_sortnet<N>::run(x, g_one, g_mone);
+    nm_sorter<N>::run(x, g_one, g_mone);
     sb[0] = NM_KEY_NINF;
-    for (int k = 0; k < N; ++k) sb[k + 1] = x[k];
+    for (int k = 0; k < N; ++k) sb[k + 1] = x[nm_sorter<N>::order(k)];
     sb[N + 1] = NM_KEY_PINF;
   }
   // iters deliberately larger than needed: lanes of a warp share the longest trip count
