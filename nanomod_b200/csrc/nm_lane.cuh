@@ -85,11 +85,11 @@ struct nm_sortloop;
 
 // The sorter of a size class: flat network for N < 72 (code <= ~20 KB), looped sort above.
 // run() leaves the k-th smallest key in x[order(k)].
-// Looped sorts are OFF by default: in isolation they win (tools/ubench3.cu), inside the lane
-// kernel the register moves push the FMA pipe to the limit and the kernel got slower
-// (profiles/round1_variants.md).  -DNM_LOOPED_MIN_N=72 turns them on for N >= 72.
+// Looped sorts are used for the largest size classes only: their flat networks (>= 50 KB of
+// code with int keys) are instruction-fetch bound, while for N <= 104 the register moves of the
+// looped form cost more than the fetch stalls they remove (profiles/round1_variants.md).
 #ifndef NM_LOOPED_MIN_N
-#define NM_LOOPED_MIN_N 1000
+#define NM_LOOPED_MIN_N 112
 #endif
 template <int N, bool LOOPED = (N >= NM_LOOPED_MIN_N)>
 struct nm_sorter;
