@@ -116,6 +116,11 @@ int nm_detect_host(nm_handle* h, const nm_pileup* pileup, const nm_params* param
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nm_launch_count(const nm_handle* h);
 
+/* Restrict the persistent lane-tier kernel to n_sms SMs (0 = all).  Multi-GPU callers leave a
+ * few SMs free so that NCCL's copy kernels can run while the next shard piece is computed. */
+int nm_set_sm_limit(nm_handle* h, int n_sms);
+int nm_sm_count(const nm_handle* h);
+
 /* Device time (ms, CUDA events on the call's stream) of the most recent nm_detect_* call:
  * ms4[0] plan kernels, [1] lane-tier kernel, [2] deep-tier kernel, [3] combine kernel. */
 int nm_last_timings(const nm_handle* h, double* ms4);

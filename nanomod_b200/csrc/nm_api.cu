@@ -382,6 +382,7 @@ struct nm_handle {
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
   nm_buf d_out[16];
   int64_t launches;
+  int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -427,6 +428,15 @@ extern "C" int64_t nm_padded_len(int64_t nvals) { return (nvals + 3) / 4 * 4 + 4
 extern "C" const char* nm_last_error(const nm_handle* h) { return h ? h->err : g_err; }
 
 extern "C" int64_t nm_launch_count(const nm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nm_set_sm_limit(nm_handle* h, int n_sms) {
+  if (!h) return NM_ERR_BAD_ARG;
+  if (n_sms < 0 || n_sms > h->sm_count) return nm_fail(h, NM_ERR_BAD_ARG, "sm limit %d out of [0,%d]", n_sms, h->sm_count);
+  h->sm_limit = n_sms;
+  return NM_OK;
+}
+
+extern "C" int nm_sm_count(const nm_handle* h) { return h ? h->sm_count : 0; }
 
 extern "C" int nm_last_timings(const nm_handle* h, double* ms4) {
   if (!h || !ms4) return NM_ERR_BAD_ARG;
@@ -508,7 +518,7 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
 static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
-    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, max_lane_n, h->sm_count, st);
+    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, max_lane_n, h->sm_limit > 0 ? h->sm_limit : h->sm_count, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
