@@ -383,6 +383,7 @@ struct nm_handle {
   nm_buf d_out[16];
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
+  int use_pair_tier;   // NANOMOD_B200_PAIR_TIER=1: two lanes per position for long rows (experimental)
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -465,6 +466,10 @@ extern "C" int nm_create(int device, nm_handle** out) {
   if (!h) return nm_fail(nullptr, NM_ERR_OOM, "nm_create: out of host memory");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  {
+    const char* f = getenv("NANOMOD_B200_PAIR_TIER");
+    h->use_pair_tier = (f && f[0] == '1') ? 1 : 0;
+  }
   int rc = NM_OK;
   do {
     if (cudaSetDevice(device) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
@@ -518,9 +523,17 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
 static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
-    const cudaError_t e = (cudaError_t)nm_launch_lane(ka, want_u, want_t, max_lane_n, h->sm_limit > 0 ? h->sm_limit : h->sm_count, st);
+    const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
+    // The pair tier (two lanes per position for long rows; KS and Welch t only) is an experiment:
+    // it doubles residency and halves the code footprint, but needs 25 % more instructions and
+    // measured slower than the lane tier in round 1 (profiles/round1_variants.md).  Off unless
+    // NANOMOD_B200_PAIR_TIER=1.
+    const bool pair = h->use_pair_tier && !want_u && max_lane_n > 64 && nm_pair_tier_available();
+    const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(ka, want_t, max_lane_n, sms, st)
+                                             : nm_launch_lane(ka, want_u, want_t, max_lane_n, sms, st));
     if (e != cudaSuccess)
-      return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
+      return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
+                     cudaGetErrorString(e));
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
@@ -599,8 +612,6 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.vals0 = pl->vals0; ka.vals1 = pl->vals1; ka.off0 = pl->off0; ka.off1 = pl->off1;
   ka.row_pos_index = tb->row_pos_index; ka.row_n0 = tb->n0; ka.row_n1 = tb->n1;
   ka.n_rows = n_rows;
-  const int ncls = (sum.max_lane_n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
-  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 2);
   ka.one = 1;
   ka.mone = -1;
   ka.tile_cursor = &h->d_sum->tile_cursor;

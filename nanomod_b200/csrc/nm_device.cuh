@@ -106,6 +106,7 @@ struct nm_kargs {
   const int32_t* row_n1;
   int64_t n_rows;
   int region_floats;  // floats per group region in shared memory (lane tier)
+  int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int* tile_cursor;   // device counter, zero at launch
   int32_t* ks_dnum;
@@ -140,6 +141,57 @@ __device__ __forceinline__ void nm_store_row(const nm_kargs& a, int64_t r, const
 }
 
 
+// sum of four accumulators that were filled by window slot (e & 3), combined in the order of the
+// ROW index class ((e - shift) & 3): the result does not depend on the row's alignment
+__device__ __forceinline__ double nm_sum4_by_row_class(const double (&s)[4], int shift) {
+  const double c0 = shift == 0 ? s[0] : shift == 1 ? s[1] : shift == 2 ? s[2] : s[3];
+  const double c1 = shift == 0 ? s[1] : shift == 1 ? s[2] : shift == 2 ? s[3] : s[0];
+  const double c2 = shift == 0 ? s[2] : shift == 1 ? s[3] : shift == 2 ? s[0] : s[1];
+  const double c3 = shift == 0 ? s[3] : shift == 1 ? s[0] : shift == 2 ? s[1] : s[2];
+  return __dadd_rn(__dadd_rn(c0, c1), __dadd_rn(c2, c3));
+}
+
+// Welch moments of one row: two-pass, fp64, four accumulators by row index mod 4, read through
+// the same aligned 128-bit window as the sort.  A ROLLED loop with explicitly rounded
+// operations: the instruction sequence applied to a row depends only on the row itself (not on
+// its alignment, its tile or the tile's network size), so results are bit-identical however
+// the genome is sharded -- and the loop body stays in the instruction cache.
+__device__ __forceinline__ void nm_lane_moments(const float* region, int base, int n, double* mean,
+                                                double* var) {
+  const int shift = base & 3;
+  const float4* raw4 = reinterpret_cast<const float4*>(region + (base - shift));
+  const int nq = __reduce_max_sync(0xffffffffu, (shift + n + 3) >> 2);
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const float4 v4 = raw4[q];
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
+      s[j] = __dadd_rn(s[j], valid ? (double)vv[j] : 0.0);
+    }
+  }
+  const double m = __ddiv_rn(nm_sum4_by_row_class(s, shift), (double)n);
+  double ss[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const float4 v4 = raw4[q];
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
+      const double d = valid ? __dsub_rn((double)vv[j], m) : 0.0;
+      ss[j] = __fma_rn(d, d, ss[j]);
+    }
+  }
+  *mean = m;
+  *var = __ddiv_rn(nm_sum4_by_row_class(ss, shift), (double)(n - 1));
+}
+
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count,
                    cudaStream_t st);
+// host-side launcher of the pair tier (nm_pair_kernel.cu): KS (+ Welch t), two lanes per position
+int nm_launch_pair(const nm_kargs& ka, bool want_t, int max_n, int sm_count, cudaStream_t st);
+bool nm_pair_tier_available();

@@ -80,6 +80,13 @@ struct nm_sortloop;
   }
 #include "nm_sortloop.inc"
 #undef NM_ROTATE
+
+// Pair tier (two lanes per position): half-size sorts + up-down merges (tools/gen_pairnet.py).
+template <int H>
+struct nm_halfsort;
+template <int H>
+struct nm_updown;
+#include "nm_pairnet.inc"
 #undef NM_CE
 #undef NM_CEB
 

@@ -31,54 +31,6 @@
     if ((q_ & 3) == 3) asm volatile("" ::: "memory");                            \
   }
 
-// sum of four accumulators that were filled by window slot (e & 3), combined in the order of the
-// ROW index class ((e - shift) & 3): the result does not depend on the row's alignment
-__device__ __forceinline__ double nm_sum4_by_row_class(const double (&s)[4], int shift) {
-  const double c0 = shift == 0 ? s[0] : shift == 1 ? s[1] : shift == 2 ? s[2] : s[3];
-  const double c1 = shift == 0 ? s[1] : shift == 1 ? s[2] : shift == 2 ? s[3] : s[0];
-  const double c2 = shift == 0 ? s[2] : shift == 1 ? s[3] : shift == 2 ? s[0] : s[1];
-  const double c3 = shift == 0 ? s[3] : shift == 1 ? s[0] : shift == 2 ? s[1] : s[2];
-  return __dadd_rn(__dadd_rn(c0, c1), __dadd_rn(c2, c3));
-}
-
-// Welch moments of one row: two-pass, fp64, four accumulators by row index mod 4, read through
-// the same aligned 128-bit window as the sort.  A ROLLED loop with explicitly rounded
-// operations: the instruction sequence applied to a row depends only on the row itself (not on
-// its alignment, its tile or the tile's network size), so results are bit-identical however
-// the genome is sharded -- and the loop body stays in the instruction cache.
-__device__ __forceinline__ void nm_lane_moments(const float* region, int base, int n, double* mean,
-                                                double* var) {
-  const int shift = base & 3;
-  const float4* raw4 = reinterpret_cast<const float4*>(region + (base - shift));
-  const int nq = __reduce_max_sync(0xffffffffu, (shift + n + 3) >> 2);
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-  for (int q = 0; q < nq; ++q) {
-    const float4 v4 = raw4[q];
-    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
-      s[j] = __dadd_rn(s[j], valid ? (double)vv[j] : 0.0);
-    }
-  }
-  const double m = __ddiv_rn(nm_sum4_by_row_class(s, shift), (double)n);
-  double ss[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-  for (int q = 0; q < nq; ++q) {
-    const float4 v4 = raw4[q];
-    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
-      const double d = valid ? __dsub_rn((double)vv[j], m) : 0.0;
-      ss[j] = __fma_rn(d, d, ss[j]);
-    }
-  }
-  *mean = m;
-  *var = __ddiv_rn(nm_sum4_by_row_class(ss, shift), (double)(n - 1));
-}
-
 // Load one group's row into registers (pad +inf), sort, write back transposed with a -inf row
 // in front and a +inf sentinel row behind (layout expected by nm_merge_walk).
 template <int N>
@@ -350,7 +302,11 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       __syncwarp();
 
       const int n0 = cur.n0, n1 = cur.n1;
-      const int nsel = (cst.nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+      // Size class of the tile.  Tiles whose longest row is more than half the call's longest
+      // row all use the call's class: a handful of extra comparators costs far less than
+      // keeping several 30-60 KB networks alive in the 32 KB instruction cache.
+      int nsel = (cst.nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+      if (2 * cst.nmax > a.class_n) nsel = a.class_n;
       nm_lane_acc acc;
       acc.dnum = acc.r2 = acc.tie = 0;
       acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
@@ -435,7 +391,11 @@ static int nm_launch_lane_t(const nm_kargs& ka, bool want_u, bool want_t, int sm
 }
 
 // max_n = longest lane-tier row of this call
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st) {
+int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st) {
+  nm_kargs ka = ka_in;
+  const int ncls = (max_n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 2);
+  ka.class_n = ncls > 0 ? ncls : NM_LANE_STEP;
   if (max_n <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, st);
   return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
 }

@@ -366,3 +366,71 @@ def test_cfg2_full_size_properties(det):
     # (6) the planted sites are what gets called
     t_pos = torch.argsort(out["stouffer_p"])[:200].cpu().numpy()
     assert np.mean(host_shift[t_pos] > 0) > 0.95
+
+
+# ---------------------------------------------------------------------------------------------
+# pair tier (two lanes per position; experimental, NANOMOD_B200_PAIR_TIER=1): used when the
+# longest row has > 64 reads and the rank statistics are not requested
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def det_pair():
+    import os
+    os.environ["NANOMOD_B200_PAIR_TIER"] = "1"
+    try:
+        d = nm.Detector(0)
+    finally:
+        del os.environ["NANOMOD_B200_PAIR_TIER"]
+    return d
+
+
+def _sweep_pileup(seed=9, lo=1, hi=141):
+    rng = np.random.default_rng(seed)
+    c0 = np.concatenate([np.arange(lo, hi), rng.integers(3, hi, 500)]).astype(np.int64)
+    c1 = np.concatenate([np.arange(lo, hi)[::-1], rng.integers(3, hi, 500)]).astype(np.int64)
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0.4, 1, off1[-1]), 2).astype(np.float32)
+    return nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(len(c0), dtype=np.int32))
+
+
+@pytest.mark.parametrize("want_t", [False, True])
+def test_pair_tier_every_coverage(det, det_pair, want_t):
+    p = _sweep_pileup()
+    opt = nm.DetectOptions(MinCoverage=3, neighborPvalues=2, testMethod="stouffer", want_u=False, want_t=want_t)
+    t = det_pair.detect(p, opt)
+    assert_table_matches(t, vec(p, opt, ("stouffer",)), opt)
+    # the two tiers agree bit for bit (the Welch moments use the same routine in both)
+    t2 = det.detect(p, opt)
+    for name in ("ks_dnum", "ks_p", "stouffer_stat") + (("t_stat", "t_p") if want_t else ()):
+        assert getattr(t, name).tobytes() == getattr(t2, name).tobytes(), name
+
+
+@pytest.mark.parametrize("variant", ["uniform100", "ties1", "gaps_two_strands", "poisson100", "n128", "n65_unaligned"])
+def test_pair_tier_variants(det_pair, variant):
+    det = det_pair
+    kw = {"uniform100": dict(n=100), "ties1": dict(n=100, round_decimals=1),
+          "gaps_two_strands": dict(n=90, drop_frac1=0.02, two_strands=True, round_decimals=2),
+          "poisson100": dict(n=100, poisson=True, clip=(2, 128), round_decimals=3),
+          "n128": dict(n=128), "n65_unaligned": dict(n=65)}[variant]
+    n = kw.pop("n")
+    p = nm.synthetic_pileup(6000, n, n if variant != "n65_unaligned" else 67, seed=nm.SYN_SEED + 3, **kw)
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True, want_u=False, want_t=True)
+    assert_table_matches(det.detect(p, opt), vec(p, opt), opt)
+
+
+def test_pair_tier_mixed_with_deep_rows(det_pair):
+    det = det_pair
+    rng = np.random.default_rng(33)
+    L = 500
+    c0 = rng.integers(60, 128, L).astype(np.int64)
+    c1 = rng.integers(60, 128, L).astype(np.int64)
+    for i in (7, 8, 130, 131, 132, 499):
+        c0[i], c1[i] = 700, 650
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 3).astype(np.float32)
+    v1 = np.round(rng.normal(0.2, 1, off1[-1]), 3).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=True)
+    assert_table_matches(det.detect(p, opt), vec(p, opt, ("stouffer",)), opt)
