@@ -212,6 +212,17 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def lane_traffic():
+    """DRAM bytes per nm_lane_kernel launch on the bench workload, from the committed ncu
+    --set full capture (profiles/lane_kernel_traffic.json); None if no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "lane_kernel_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -356,7 +367,10 @@ def run_gpu_arm(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys, i32 ranks, f64 tails",
                 "data": "synthetic", "config": workload_config(world),
                 "roofline": {"bound": "hbm", "kernel": "nm_lane_kernel", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": (lane_traffic()[0] if world == 1 and L == GENOME else None),
+                             "traffic_source": lane_traffic()[1], "algorithmic_bytes_per_launch": BYTES_PER_POS * n_local,
+                             "peak_source": peak_src,
                              "bytes_per_position": BYTES_PER_POS, "positions_per_launch": n_local,
                              "kernel_ms": lane_avg, "other_kernels_ms": {"plan": sum(plan_ms) / len(plan_ms),
                                                                          "combine": sum(comb_ms) / len(comb_ms)},

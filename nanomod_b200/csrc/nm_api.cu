@@ -67,7 +67,7 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
         } else {
           ++n_deep;
           const int64_t cap = 1 << 24;
-          const int p2 = nm_pow2ceil((int)(n0 < cap ? n0 : cap)) + nm_pow2ceil((int)(n1 < cap ? n1 : cap));
+          const int p2 = nm_deep_p2((int)(n0 < cap ? n0 : cap)) + nm_deep_p2((int)(n1 < cap ? n1 : cap));
           max_deep = max_deep > p2 ? max_deep : p2;
         }
       }
@@ -145,140 +145,6 @@ nm_plan_scatter(const int64_t* __restrict__ off0, const int64_t* __restrict__ of
       }
       ++r;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// deep tier: one CTA per position
-// ------------------------------------------------------------------------------------------
-#define NM_DEEP_THREADS 256
-
-__device__ __forceinline__ void nm_block_bitonic(float* s, int P, int tid) {
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (P >> 1); t += NM_DEEP_THREADS) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int p = i | j;
-        const float x = s[i], y = s[p];
-        const bool up = (i & k) == 0;
-        const float lo = fminf(x, y), hi = fmaxf(x, y);
-        s[i] = up ? lo : hi;
-        s[p] = up ? hi : lo;
-      }
-      __syncthreads();
-    }
-  }
-}
-
-__global__ void __launch_bounds__(NM_DEEP_THREADS) nm_deep_kernel(const nm_kargs a, const int want_u,
-                                                                  const int want_t) {
-  extern __shared__ __align__(128) unsigned char nm_smem[];
-  __shared__ double red_d[NM_DEEP_THREADS / 32];
-  __shared__ long long red_l[3][NM_DEEP_THREADS / 32];
-  __shared__ double bcast[2];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(nm_smem);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-  const int64_t r = a.deep_rows[blockIdx.x];
-  const int32_t src = a.row_pos_index[r];
-  const int n0 = a.row_n0[r], n1 = a.row_n1[r];
-  const long long s0 = a.off0[src], s1 = a.off1[src];
-  const int P0 = nm_pow2ceil(n0), P1 = nm_pow2ceil(n1);
-  const long long al0 = s0 & ~3LL, al1 = s1 & ~3LL;
-  const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
-  float* rawA = reinterpret_cast<float*>(nm_smem + 16);
-  float* rawB = rawA + P0 + 4;
-  float* sa = rawA + sh0;
-  float* sb = rawB + sh1;
-
-  // TMA bulk load of the two contiguous pileup slices
-  if (tid == 0) {
-    nm_mbar_init(bar, 1);
-    const uint32_t b0 = (uint32_t)((sh0 + n0 + 3) & ~3) * 4u;
-    const uint32_t b1 = (uint32_t)((sh1 + n1 + 3) & ~3) * 4u;
-    nm_mbar_expect_tx(bar, b0 + b1);
-    nm_bulk_g2s(rawA, a.vals0 + al0, b0, bar);
-    nm_bulk_g2s(rawB, a.vals1 + al1, b1, bar);
-  }
-  __syncthreads();
-  nm_mbar_wait(bar, 0);
-  __syncthreads();  // nobody pads before everyone has seen the copy complete
-  for (int k = n0 + tid; k < P0; k += NM_DEEP_THREADS) sa[k] = NM_INF;
-  for (int k = n1 + tid; k < P1; k += NM_DEEP_THREADS) sb[k] = NM_INF;
-
-  double mean[2] = {0.0, 0.0}, var[2] = {0.0, 0.0};
-  if (want_t) {
-    for (int g = 0; g < 2; ++g) {
-      const float* s = g ? sb : sa;
-      const int n = g ? n1 : n0;
-      double part = 0.0;
-      for (int k = tid; k < n; k += NM_DEEP_THREADS) part += (double)s[k];
-      part = nm_warp_sum_d(part);
-      if (lane == 0) red_d[wid] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
-        bcast[0] = t / (double)n;
-      }
-      __syncthreads();
-      const double m = bcast[0];
-      part = 0.0;
-      for (int k = tid; k < n; k += NM_DEEP_THREADS) {
-        const double d = (double)s[k] - m;
-        part += d * d;
-      }
-      part = nm_warp_sum_d(part);
-      __syncthreads();
-      if (lane == 0) red_d[wid] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
-        bcast[1] = t / (double)(n - 1);
-      }
-      __syncthreads();
-      mean[g] = m;
-      var[g] = bcast[1];
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  nm_block_bitonic(sa, P0, tid);
-  nm_block_bitonic(sb, P1, tid);
-
-  nm_deep_acc acc;
-  nm_deep_acc_init(&acc);
-  for (int e = tid; e < n0 + n1; e += NM_DEEP_THREADS) {
-    nm_deep_acc one;
-    nm_deep_acc_init(&one);
-    nm_deep_element(sa, n0, sb, n1, e, want_u != 0, &one);
-    nm_deep_acc_merge(&acc, one);
-  }
-  acc.dnum = nm_warp_max_ll(acc.dnum);
-  acc.r2 = nm_warp_sum_ll(acc.r2);
-  acc.tie = nm_warp_sum_ll(acc.tie);
-  if (lane == 0) {
-    red_l[0][wid] = acc.dnum;
-    red_l[1][wid] = acc.r2;
-    red_l[2][wid] = acc.tie;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    nm_deep_acc tot;
-    nm_deep_acc_init(&tot);
-    for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) {
-      nm_deep_acc one;
-      one.dnum = red_l[0][w];
-      one.r2 = red_l[1][w];
-      one.tie = red_l[2][w];
-      nm_deep_acc_merge(&tot, one);
-    }
-    nm_row_out o;
-    o.two_u = 0;
-    o.u_stat = o.u_p = o.t_stat = o.t_p = 0.0;
-    nm_deep_finish(tot, n0, n1, want_u != 0, want_t != 0, mean[0], var[0], mean[1], var[1], &o);
-    nm_store_row(a, r, o, want_u != 0, want_t != 0);
   }
 }
 
@@ -520,7 +386,7 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   return NM_OK;
 }
 
-static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int max_deep_p2, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
     const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
@@ -538,9 +404,9 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
-    NM_CUDA(h, cudaFuncSetAttribute(nm_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_smem));
-    nm_deep_kernel<<<(unsigned)n_deep, NM_DEEP_THREADS, deep_smem, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
-    NM_CUDA(h, cudaGetLastError());
+    const cudaError_t e = (cudaError_t)nm_launch_deep(ka, want_u, want_t, n_deep, max_deep_p2, deep_smem, st);
+    if (e != cudaSuccess)
+      return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[3], st));
@@ -619,8 +485,8 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
   ka.deep_rows = (const int32_t*)h->d_deep_rows.p; ka.n_deep = sum.n_deep;
-  const int deep_smem = 16 + (sum.max_deep_p2 + 8) * (int)sizeof(float);
-  rc = nm_launch_tiers(h, ka, want_u, want_t, sum.max_lane_n, deep_smem, n_rows, sum.n_deep, st);
+  const int deep_smem = 16 + (sum.max_deep_p2 + 16) * (int)sizeof(float);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;
 
   // ---- neighbour combination

@@ -1,0 +1,266 @@
+// nm_deep_kernel.cu -- the deep tier: one CTA (256 threads) per position for rows with more than
+// 128 reads in a group (getKStest, bin/scripts/myDetect.py:327-343, same statistics).
+//
+//   stage   the two contiguous pileup slices arrive by TMA bulk copy (cp.async.bulk + mbarrier)
+//   sort    each group as a power-of-two array P = E*256 (>= 512), E elements per thread held in
+//           REGISTERS: a per-thread network sorts the E-chunk, then a normalised bitonic sort
+//           (all comparators ascending: first step of every merge compares i with i ^ (k-1))
+//           runs its small strides in registers, strides that stay inside a warp through
+//           shuffles, and only the few strides that cross warps through shared memory
+//           (6 of 66 stages at P = 2048)
+//   ranks   KS only: every thread takes a contiguous piece of the pooled order (merge-path
+//           split by binary search) and walks it, evaluating c0*n1 - c1*n0 at tie-group ends;
+//           with the rank statistics: per-element counts by binary search (nm_deep.cuh)
+//   tails   thread 0, fp64
+#include "nm_device.cuh"
+
+__device__ __forceinline__ void nm_ce_up(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
+
+// exchange step of the normalised bitonic network across threads: partner thread tid ^ M,
+// partner element i (same) or E-1-i (reversed: the "flip" first step of a merge)
+template <int E>
+__device__ __forceinline__ void nm_deep_exchange(float (&x)[E], float* stage, int tid, int M, bool reversed) {
+  int hb = M;  // highest set bit of M decides who keeps the minimum
+  hb |= hb >> 1; hb |= hb >> 2; hb |= hb >> 4; hb |= hb >> 8;
+  hb = (hb + 1) >> 1;
+  const bool lower = (tid & hb) == 0;
+  if (M < 32) {
+    if (reversed) {
+#pragma unroll
+      for (int i = 0; i < (E + 1) / 2; ++i) {
+        const int r = E - 1 - i;
+        const float o1 = __shfl_xor_sync(0xffffffffu, x[r], M);  // partner's counterpart of my x[i]
+        const float o2 = __shfl_xor_sync(0xffffffffu, x[i], M);  // partner's counterpart of my x[r]
+        x[i] = lower ? fminf(x[i], o1) : fmaxf(x[i], o1);
+        if (r != i) x[r] = lower ? fminf(x[r], o2) : fmaxf(x[r], o2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const float o = __shfl_xor_sync(0xffffffffu, x[i], M);
+        x[i] = lower ? fminf(x[i], o) : fmaxf(x[i], o);
+      }
+    }
+  } else {
+    // through shared memory, transposed staging (element i of thread t at stage[i*256 + t]):
+    // conflict-free for both the writes and the permuted reads
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < E; ++i) stage[i * NM_DEEP_THREADS + tid] = x[i];
+    __syncthreads();
+    const int pt = tid ^ M;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float o = stage[(reversed ? E - 1 - i : i) * NM_DEEP_THREADS + pt];
+      x[i] = lower ? fminf(x[i], o) : fmaxf(x[i], o);
+    }
+  }
+}
+
+// sort s[0 .. E*256) ascending in place (s is also used as the staging area)
+template <int E>
+__device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
+  float x[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) x[i] = s[tid * E + i];
+  nm_sortnet<E>::run(x);
+  constexpr int P = E * NM_DEEP_THREADS;
+  for (int k = 2 * E; k <= P; k <<= 1) {
+    nm_deep_exchange<E>(x, s, tid, k / E - 1, true);
+    for (int j = k >> 2; j >= E; j >>= 1) nm_deep_exchange<E>(x, s, tid, j / E, false);
+#pragma unroll
+    for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        if ((i & j) == 0) nm_ce_up(x[i], x[i | j]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < E; ++i) s[tid * E + i] = x[i];
+  __syncthreads();
+}
+
+template <int EMAX>
+__device__ __forceinline__ void nm_deep_sort_p(float* s, int P, int tid) {
+  switch (P / NM_DEEP_THREADS) {
+    case 2: nm_deep_sort<2>(s, tid); break;
+    case 4: nm_deep_sort<4>(s, tid); break;
+    case 8: nm_deep_sort<8>(s, tid); break;
+    case 16: nm_deep_sort<16>(s, tid); break;
+    case 32: if (EMAX >= 32) nm_deep_sort<(EMAX >= 32 ? 32 : 2)>(s, tid); break;
+    case 64: if (EMAX >= 64) nm_deep_sort<(EMAX >= 64 ? 64 : 2)>(s, tid); break;
+    default: if (EMAX >= 128) nm_deep_sort<(EMAX >= 128 ? 128 : 2)>(s, tid); break;
+  }
+}
+
+// KS numerator over this thread's piece [lo, hi) of the pooled order.  sa[n0] and sb[n1] are +inf.
+__device__ __forceinline__ int nm_deep_walk(const float* sa, int n0, const float* sb, int n1, int lo, int hi) {
+  // merge-path split of diagonal lo under the rule "ties: group 0 first"
+  int il = lo - n1 > 0 ? lo - n1 : 0, ih = lo < n0 ? lo : n0;
+  while (il < ih) {
+    const int mid = (il + ih) >> 1;
+    if (sa[mid] <= sb[lo - mid - 1]) il = mid + 1; else ih = mid;
+  }
+  int i = il, j = lo - il;
+  float va = sa[i], vb = sb[j];
+  float v = fminf(va, vb);
+  int dmax = 0;
+  for (int s = lo; s < hi; ++s) {
+    const bool le = va <= vb;
+    i += le ? 1 : 0;
+    j += le ? 0 : 1;
+    va = sa[i];
+    vb = sb[j];
+    const float vn = fminf(va, vb);
+    const bool q = vn > v;
+    v = vn;
+    int d = i * n1 - j * n0;
+    d = d < 0 ? -d : d;
+    dmax = (q && d > dmax) ? d : dmax;
+  }
+  return dmax;
+}
+
+// EMAX = largest per-thread chunk compiled in: 16 covers groups of up to 4096 reads at 3 CTAs/SM,
+// 128 (groups up to 32768 reads) needs most of the register file for one CTA.
+template <int EMAX>
+__global__ void __launch_bounds__(NM_DEEP_THREADS, EMAX <= 16 ? 3 : 1)
+nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t) {
+  extern __shared__ __align__(128) unsigned char nm_smem[];
+  __shared__ double red_d[NM_DEEP_THREADS / 32];
+  __shared__ long long red_l[3][NM_DEEP_THREADS / 32];
+  __shared__ double bcast[2];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nm_smem);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  const int64_t r = a.deep_rows[blockIdx.x];
+  const int32_t src = a.row_pos_index[r];
+  const int n0 = a.row_n0[r], n1 = a.row_n1[r];
+  const long long s0 = a.off0[src], s1 = a.off1[src];
+  const int P0 = nm_deep_p2(n0), P1 = nm_deep_p2(n1);
+  const long long al0 = s0 & ~3LL, al1 = s1 & ~3LL;
+  const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
+  // [raw A: P0 + 8 floats][raw B: P1 + 8 floats]; the arrays start at the row's first value
+  float* rawA = reinterpret_cast<float*>(nm_smem + 16);
+  float* rawB = rawA + P0 + 8;
+  float* sa = rawA + sh0;
+  float* sb = rawB + sh1;
+
+  if (tid == 0) {
+    nm_mbar_init(bar, 1);
+    const uint32_t b0 = (uint32_t)((sh0 + n0 + 3) & ~3) * 4u;
+    const uint32_t b1 = (uint32_t)((sh1 + n1 + 3) & ~3) * 4u;
+    nm_mbar_expect_tx(bar, b0 + b1);
+    nm_bulk_g2s(rawA, a.vals0 + al0, b0, bar);
+    nm_bulk_g2s(rawB, a.vals1 + al1, b1, bar);
+  }
+  __syncthreads();
+  nm_mbar_wait(bar, 0);
+  __syncthreads();  // nobody pads before everyone has seen the copy complete
+  for (int k = n0 + tid; k <= P0; k += NM_DEEP_THREADS) sa[k] = NM_INF;  // pads + one sentinel
+  for (int k = n1 + tid; k <= P1; k += NM_DEEP_THREADS) sb[k] = NM_INF;
+
+  double mean[2] = {0.0, 0.0}, var[2] = {0.0, 0.0};
+  if (want_t) {
+    for (int g = 0; g < 2; ++g) {
+      const float* s = g ? sb : sa;
+      const int n = g ? n1 : n0;
+      double part = 0.0;
+      for (int k = tid; k < n; k += NM_DEEP_THREADS) part += (double)s[k];
+      part = nm_warp_sum_d(part);
+      if (lane == 0) red_d[wid] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
+        bcast[0] = t / (double)n;
+      }
+      __syncthreads();
+      const double m = bcast[0];
+      part = 0.0;
+      for (int k = tid; k < n; k += NM_DEEP_THREADS) {
+        const double d = (double)s[k] - m;
+        part += d * d;
+      }
+      part = nm_warp_sum_d(part);
+      __syncthreads();
+      if (lane == 0) red_d[wid] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
+        bcast[1] = t / (double)(n - 1);
+      }
+      __syncthreads();
+      mean[g] = m;
+      var[g] = bcast[1];
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  nm_deep_sort_p<EMAX>(sa, P0, tid);
+  nm_deep_sort_p<EMAX>(sb, P1, tid);
+
+  nm_deep_acc acc;
+  nm_deep_acc_init(&acc);
+  if (want_u) {
+    for (int e = tid; e < n0 + n1; e += NM_DEEP_THREADS) {
+      nm_deep_acc one;
+      nm_deep_acc_init(&one);
+      nm_deep_element(sa, n0, sb, n1, e, true, &one);
+      nm_deep_acc_merge(&acc, one);
+    }
+  } else {
+    const int T = n0 + n1;
+    const int per = (T + NM_DEEP_THREADS - 1) / NM_DEEP_THREADS;
+    const int lo = tid * per < T ? tid * per : T;
+    const int hi = lo + per < T ? lo + per : T;
+    acc.dnum = nm_deep_walk(sa, n0, sb, n1, lo, hi);
+  }
+  acc.dnum = nm_warp_max_ll(acc.dnum);
+  acc.r2 = nm_warp_sum_ll(acc.r2);
+  acc.tie = nm_warp_sum_ll(acc.tie);
+  if (lane == 0) {
+    red_l[0][wid] = acc.dnum;
+    red_l[1][wid] = acc.r2;
+    red_l[2][wid] = acc.tie;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    nm_deep_acc tot;
+    nm_deep_acc_init(&tot);
+    for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) {
+      nm_deep_acc one;
+      one.dnum = red_l[0][w];
+      one.r2 = red_l[1][w];
+      one.tie = red_l[2][w];
+      nm_deep_acc_merge(&tot, one);
+    }
+    nm_row_out o;
+    o.two_u = 0;
+    o.u_stat = o.u_p = o.t_stat = o.t_p = 0.0;
+    nm_deep_finish(tot, n0, n1, want_u != 0, want_t != 0, mean[0], var[0], mean[1], var[1], &o);
+    nm_store_row(a, r, o, want_u != 0, want_t != 0);
+  }
+}
+
+template <int EMAX>
+static int nm_launch_deep_t(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int smem_bytes, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(nm_deep_kernel<EMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  nm_deep_kernel<EMAX><<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+// max_p2 = largest pow2(n0) + pow2(n1) among the deep rows (each >= NM_DEEP_MIN_P)
+int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int max_p2, int smem_bytes,
+                   cudaStream_t st) {
+  // a group can be at most max_p2 - NM_DEEP_MIN_P long
+  if (max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS) return nm_launch_deep_t<16>(ka, want_u, want_t, n_deep, smem_bytes, st);
+  return nm_launch_deep_t<128>(ka, want_u, want_t, n_deep, smem_bytes, st);
+}

@@ -189,6 +189,18 @@ __device__ __forceinline__ void nm_lane_moments(const float* region, int base, i
   *var = __ddiv_rn(nm_sum4_by_row_class(ss, shift), (double)(n - 1));
 }
 
+// deep tier: each group is sorted as a power-of-two array of at least NM_DEEP_MIN_P elements
+#define NM_DEEP_THREADS 256
+#define NM_DEEP_MIN_P 512
+__host__ __device__ __forceinline__ int nm_deep_p2(int n) {
+  int p = NM_DEEP_MIN_P;
+  while (p < n) p <<= 1;
+  return p;
+}
+// host-side launcher of the deep tier (nm_deep_kernel.cu)
+int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int max_p2, int smem_bytes,
+                   cudaStream_t st);
+
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count,
                    cudaStream_t st);

@@ -40,13 +40,7 @@ NM_HD nm_key nm_make_key(float x) {
 #define NM_KEY_NINF ((int)0x807fffff)
 NM_HD int nm_min(int a, int b) { return a < b ? a : b; }
 NM_HD int nm_max(int a, int b) { return a > b ? a : b; }
-#define NM_CEB(i, j)                          \
-  {                                           \
-    const T lo_ = nm_min(x[i], x[j]);         \
-    const T t_ = x[i] * one + x[j];           \
-    x[j] = lo_ * mone + t_;                   \
-    x[i] = lo_;                               \
-  }
+#define NM_CEB(i, j) nm_ceb(x[i], x[j], one, mone);
 #else
 typedef float nm_key;
 NM_HD nm_key nm_make_key(float x) { return x; }
@@ -56,6 +50,19 @@ NM_HD nm_key nm_make_key(float x) { return x; }
 #endif
 NM_HD float nm_min(float a, float b) { return fminf(a, b); }
 NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
+// "B" flavour of the compare-exchange: for integers {min, a + b - min} with the two additions
+// written as multiply-adds by runtime +-1 (IMAD, FMA pipe); floats always use {min, max}
+NM_HD void nm_ceb(int& a, int& b, int one, int mone) {
+  const int lo = a < b ? a : b;
+  const int t = a * one + b;
+  b = lo * mone + t;
+  a = lo;
+}
+NM_HD void nm_ceb(float& a, float& b, int, int) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
 
 #define NM_CE(i, j)                    \
   {                                    \
