@@ -122,7 +122,8 @@ int nm_set_sm_limit(nm_handle* h, int n_sms);
 int nm_sm_count(const nm_handle* h);
 
 /* Device time (ms, CUDA events on the call's stream) of the most recent nm_detect_* call:
- * ms4[0] plan kernels, [1] lane-tier kernel, [2] deep-tier kernel, [3] combine kernel. */
+ * ms4[0] plan kernels, [1] lane-tier (or pair-tier) kernel, [2] deep-tier kernel + the U/t tails
+ * kernel, [3] combine kernel. */
 int nm_last_timings(const nm_handle* h, double* ms4);
 
 #ifdef __cplusplus

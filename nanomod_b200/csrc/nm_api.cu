@@ -149,6 +149,51 @@ nm_plan_scatter(const int64_t* __restrict__ off0, const int64_t* __restrict__ of
 }
 
 // ------------------------------------------------------------------------------------------
+// tails: fp64 tails of the rank-sum and Welch tests for lane/pair-tier rows (mannwhitneyu and
+// ttest_ind tails, bin/scripts/myDetect.py:331-337), from the integers / moments the sort kernels
+// left in scratch.  Deep rows are finished by nm_deep_kernel itself.
+// ------------------------------------------------------------------------------------------
+struct nm_tails_args {
+  const int32_t* row_n0;
+  const int32_t* row_n1;
+  const int* acc_r2;
+  const int* acc_tie;
+  const double* acc_mom;
+  int64_t n_rows;
+  int want_u, want_t;
+  int64_t* two_u;
+  double* u_stat;
+  double* u_p;
+  double* t_stat;
+  double* t_p;
+  uint8_t* flags;
+};
+
+__global__ void __launch_bounds__(256) nm_tails_kernel(const nm_tails_args a) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= a.n_rows) return;
+  const int n0 = a.row_n0[r], n1 = a.row_n1[r];
+  if (n0 > NM_LANE_TIER_MAX || n1 > NM_LANE_TIER_MAX) return;
+  int flag = 0;
+  if (a.want_u) {
+    double us, up;
+    int64_t two_u;
+    nm_mwu_tail(a.acc_r2[r], a.acc_tie[r], n0, n1, &us, &two_u, &up, &flag);
+    a.two_u[r] = two_u;
+    if (a.u_stat) a.u_stat[r] = us;
+    a.u_p[r] = up;
+  }
+  if (a.want_t) {
+    const double4 m = reinterpret_cast<const double4*>(a.acc_mom)[r];
+    double ts, tp;
+    nm_welch_tail(m.x, m.y, n0, m.z, m.w, n1, &ts, &tp);
+    a.t_stat[r] = ts;
+    a.t_p[r] = tp;
+  }
+  if (a.flags) a.flags[r] = (uint8_t)flag;
+}
+
+// ------------------------------------------------------------------------------------------
 // combine: sliding-window Fisher / weighted Stouffer over the KS p-values (myDetect.py:366-414)
 // ------------------------------------------------------------------------------------------
 #define NM_COMB_THREADS 256
@@ -243,7 +288,7 @@ struct nm_handle {
   cudaStream_t own_stream;
   nm_summary* d_sum;
   nm_summary* h_sum;  // pinned
-  nm_buf d_block_count, d_deep_rows;
+  nm_buf d_block_count, d_deep_rows, d_acc_r2, d_acc_tie, d_acc_mom;
   // staging for nm_detect_host
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
   nm_buf d_out[16];
@@ -357,7 +402,7 @@ extern "C" int nm_create(int device, nm_handle** out) {
 extern "C" void nm_destroy(nm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_vals0, &h->d_vals1,
+  nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -407,6 +452,18 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
     const cudaError_t e = (cudaError_t)nm_launch_deep(ka, want_u, want_t, n_deep, max_deep_p2, deep_smem, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+  }
+  if ((want_u || want_t) && n_rows > n_deep) {
+    nm_tails_args ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.row_n0 = ka.row_n0; ta.row_n1 = ka.row_n1;
+    ta.acc_r2 = ka.acc_r2; ta.acc_tie = ka.acc_tie; ta.acc_mom = ka.acc_mom;
+    ta.n_rows = n_rows; ta.want_u = want_u; ta.want_t = want_t;
+    ta.two_u = ka.two_u; ta.u_stat = ka.u_stat; ta.u_p = ka.u_p; ta.t_stat = ka.t_stat; ta.t_p = ka.t_p;
+    ta.flags = ka.flags;
+    nm_tails_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(ta);
+    NM_CUDA(h, cudaGetLastError());
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[3], st));
@@ -485,6 +542,16 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
   ka.deep_rows = (const int32_t*)h->d_deep_rows.p; ka.n_deep = sum.n_deep;
+  if (want_u) {
+    if ((rc = nm_reserve(h, &h->d_acc_r2, sizeof(int) * (size_t)n_rows)) != NM_OK) return rc;
+    if ((rc = nm_reserve(h, &h->d_acc_tie, sizeof(int) * (size_t)n_rows)) != NM_OK) return rc;
+    ka.acc_r2 = (int*)h->d_acc_r2.p;
+    ka.acc_tie = (int*)h->d_acc_tie.p;
+  }
+  if (want_t) {
+    if ((rc = nm_reserve(h, &h->d_acc_mom, sizeof(double) * 4 * (size_t)n_rows)) != NM_OK) return rc;
+    ka.acc_mom = (double*)h->d_acc_mom.p;
+  }
   const int deep_smem = 16 + (sum.max_deep_p2 + 16) * (int)sizeof(float);
   rc = nm_launch_tiers(h, ka, want_u, want_t, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;

@@ -109,6 +109,11 @@ struct nm_kargs {
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int* tile_cursor;   // device counter, zero at launch
+  // rank sums / moments of the lane and pair tiers; their fp64 tails (normal and Student-t
+  // tails: a lot of cold fp64 code) run afterwards in nm_tails_kernel, not inside the sort loop
+  int* acc_r2;        // want_u: 2 * rank sum of group 0
+  int* acc_tie;       // want_u: sum over tie groups of t^3 - t
+  double* acc_mom;    // want_t: mean0, var0, mean1, var1 per row
   int32_t* ks_dnum;
   double* ks_d;
   double* ks_p;

@@ -345,9 +345,22 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       }
 
       if (cur.ok) {
-        nm_row_out o;
-        nm_lane_finish(acc, n0, n1, want_u != 0, want_t != 0, &o);
-        nm_store_row(a, cur.r, o, want_u != 0, want_t != 0);
+        // the KS tail runs here (it overlaps other warps' sorts); rank sums and moments are
+        // handed to nm_tails_kernel
+        double d, pv;
+        nm_ks_tail(acc.dnum, n0, n1, &d, &pv);
+        a.ks_dnum[cur.r] = acc.dnum;
+        if (a.ks_d) a.ks_d[cur.r] = d;
+        a.ks_p[cur.r] = pv;
+        if (want_u) {
+          a.acc_r2[cur.r] = acc.r2;
+          a.acc_tie[cur.r] = acc.tie;
+        }
+        if (want_t) {
+          double4* mom = reinterpret_cast<double4*>(a.acc_mom) + cur.r;
+          *mom = make_double4(acc.mean0, acc.var0, acc.mean1, acc.var1);
+        }
+        if (a.flags && !want_u) a.flags[cur.r] = 0;
       }
       cur = nxt;
       cst = nst;

@@ -362,9 +362,7 @@ nm_pair_kernel(const nm_kargs a, const int want_t) {
         staged = true;
       }
 
-      // fp64 tails: lane 0 of the pair does the KS test, lane 1 the Welch test
-      const double mean_o = __shfl_xor_sync(0xffffffffu, mean_g, 1);
-      const double var_o = __shfl_xor_sync(0xffffffffu, var_g, 1);
+      // lane 0 of the pair does the KS tail; the Welch tail runs in nm_tails_kernel
       if (cur.ok) {
         if (h == 0) {
           double d, pv;
@@ -373,11 +371,10 @@ nm_pair_kernel(const nm_kargs a, const int want_t) {
           if (a.ks_d) a.ks_d[cur.r] = d;
           a.ks_p[cur.r] = pv;
           if (a.flags) a.flags[cur.r] = 0;
-        } else if (want_t) {
-          double ts, tp;
-          nm_welch_tail(mean_o, var_o, n0, mean_g, var_g, n1, &ts, &tp);
-          a.t_stat[cur.r] = ts;
-          a.t_p[cur.r] = tp;
+        }
+        if (want_t) {  // lane 0: group 0's moments, lane 1: group 1's; tails in nm_tails_kernel
+          double2* mom = reinterpret_cast<double2*>(a.acc_mom) + 2 * cur.r + h;
+          *mom = make_double2(mean_g, var_g);
         }
       }
       cur = nxt;
