@@ -18,7 +18,7 @@ def launches(path):
     for r in rows[start + 1:]:
         if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum":
             continue
-        name = r[ix["Kernel Name"]].split("(")[0].split("<")[0]
+        name = r[ix["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").strip()
         v = float(r[ix["Metric Value"]].replace(",", ""))
         unit = r[ix["Metric Unit"]]
         v *= {"ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(unit, 1.0)
