@@ -295,6 +295,7 @@ struct nm_handle {
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int use_pair_tier;   // NANOMOD_B200_PAIR_TIER=1: two lanes per position for long rows (experimental)
+  int use_pair_sync;   // NANOMOD_B200_PAIR_SYNC=0/1: lane tier, warp pairs in lock-step (nm_kargs::pair_sync)
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -380,6 +381,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
   {
     const char* f = getenv("NANOMOD_B200_PAIR_TIER");
     h->use_pair_tier = (f && f[0] == '1') ? 1 : 0;
+    const char* g = getenv("NANOMOD_B200_PAIR_SYNC");
+    h->use_pair_sync = (g && g[0] == '1') ? 1 : 0;
   }
   int rc = NM_OK;
   do {
@@ -441,7 +444,7 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
     // NANOMOD_B200_PAIR_TIER=1.
     const bool pair = h->use_pair_tier && !want_u && max_lane_n > 64 && nm_pair_tier_available();
     const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(ka, want_t, max_lane_n, sms, st)
-                                             : nm_launch_lane(ka, want_u, want_t, max_lane_n, sms, st));
+                                             : nm_launch_lane(ka, want_u, want_t, max_lane_n, sms, h->use_pair_sync, st));
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
                      cudaGetErrorString(e));

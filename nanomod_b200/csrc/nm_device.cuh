@@ -109,6 +109,7 @@ struct nm_kargs {
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int* tile_cursor;   // device counter, zero at launch
+  int pair_sync;      // lane tier: warps (w, w+4) of an 8-warp CTA step through tiles together
   // rank sums / moments of the lane and pair tiers; their fp64 tails (normal and Student-t
   // tails: a lot of cold fp64 code) run afterwards in nm_tails_kernel, not inside the sort loop
   int* acc_r2;        // want_u: 2 * rank sum of group 0
@@ -207,7 +208,7 @@ int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int
                    cudaStream_t st);
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count,
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, int pair_sync,
                    cudaStream_t st);
 // host-side launcher of the pair tier (nm_pair_kernel.cu): KS (+ Welch t), two lanes per position
 int nm_launch_pair(const nm_kargs& ka, bool want_t, int max_n, int sm_count, cudaStream_t st);

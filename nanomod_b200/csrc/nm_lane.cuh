@@ -14,7 +14,8 @@
 #include "nm_math.cuh"
 
 #define NM_LANE_MAX_N 128  // largest per-group coverage handled by the lane tier
-#define NM_LANE_STEP 8     // network sizes are multiples of this
+#define NM_LANE_STEP 4     // network sizes are multiples of this up to NM_LANE_FINE_MAX, of 8 beyond
+#define NM_LANE_FINE_MAX 104
 
 template <int N>
 struct nm_sortnet;
@@ -300,23 +301,44 @@ NM_HD double nm_build_weights(int nb, double weights_dif, double* w /* [nb+1] */
   return sqrt(s);
 }
 
-// Dispatch a runtime network size (multiple of NM_LANE_STEP, <= NM_LANE_MAX_N) to a template.
+// Network size (class) for a longest row of n values: 8, 12, ..., 104, 112, 120, 128.
+NM_HD constexpr int nm_lane_class(int n) {
+  return n <= 8 ? 8 : n <= NM_LANE_FINE_MAX ? (n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP : (n + 7) / 8 * 8;
+}
+
+// Dispatch a runtime network size (a value of nm_lane_class) to a template.
+#ifdef NM_ONLY_N  // analysis builds: a single network size (SASS inspection, tools/sass_hist.py)
+#define NM_DISPATCH_N(nsel, CALL) { CALL(NM_ONLY_N); }
+#else
 #define NM_DISPATCH_N(nsel, CALL) \
   switch (nsel) {                 \
-    case 8: { CALL(8); } break;     \
-    case 16: { CALL(16); } break;   \
-    case 24: { CALL(24); } break;   \
-    case 32: { CALL(32); } break;   \
-    case 40: { CALL(40); } break;   \
-    case 48: { CALL(48); } break;   \
-    case 56: { CALL(56); } break;   \
-    case 64: { CALL(64); } break;   \
-    case 72: { CALL(72); } break;   \
-    case 80: { CALL(80); } break;   \
-    case 88: { CALL(88); } break;   \
-    case 96: { CALL(96); } break;   \
-    case 104: { CALL(104); } break; \
-    case 112: { CALL(112); } break; \
-    case 120: { CALL(120); } break; \
+    case 8: { CALL(8); } break;   \
+    case 12: { CALL(12); } break; \
+    case 16: { CALL(16); } break; \
+    case 20: { CALL(20); } break; \
+    case 24: { CALL(24); } break; \
+    case 28: { CALL(28); } break; \
+    case 32: { CALL(32); } break; \
+    case 36: { CALL(36); } break; \
+    case 40: { CALL(40); } break; \
+    case 44: { CALL(44); } break; \
+    case 48: { CALL(48); } break; \
+    case 52: { CALL(52); } break; \
+    case 56: { CALL(56); } break; \
+    case 60: { CALL(60); } break; \
+    case 64: { CALL(64); } break; \
+    case 68: { CALL(68); } break; \
+    case 72: { CALL(72); } break; \
+    case 76: { CALL(76); } break; \
+    case 80: { CALL(80); } break; \
+    case 84: { CALL(84); } break; \
+    case 88: { CALL(88); } break; \
+    case 92: { CALL(92); } break; \
+    case 96: { CALL(96); } break; \
+    case 100: { CALL(100); } break;\
+    case 104: { CALL(104); } break;\
+    case 112: { CALL(112); } break;\
+    case 120: { CALL(120); } break;\
     default: { CALL(128); } break;  \
   }
+#endif

@@ -13,6 +13,7 @@
 #include "nm_device.cuh"
 
 #define NM_LANE_MAX_WARPS 4  // warps (= independent 32-row tiles) per CTA, chosen at launch
+#define NM_LANE_SYNC_WARPS 8 // CTA shape of the pair-synchronised mode (nm_kargs::pair_sync)
 
 // Visit the row's values through 128-bit shared-memory loads from the 16-byte aligned address
 // below the row (N/4 + 1 loads): window slot e holds row element e - shift and is valid iff
@@ -244,7 +245,7 @@ __device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
 // slices are being pulled into L2; its TMA copies are issued the moment the merge walk has
 // released the two regions, so that they overlap the fp64 tails of the current tile.
 template <int NMAX>
-__global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, NMAX <= 64 ? 3 : 2)
+__global__ void __launch_bounds__(NMAX <= 64 ? 32 * NM_LANE_MAX_WARPS : 32 * NM_LANE_SYNC_WARPS, NMAX <= 64 ? 3 : 1)
 nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -257,8 +258,20 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   const int warps_per_cta = blockDim.x >> 5;
   const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
 
+  // Pair-synchronised mode (8-warp CTA): warps w and w+4 share an SM sub-partition; they claim
+  // two consecutive tiles together and meet at a 64-thread named barrier once per tile, so they
+  // run the same 50 KB of straight-line sort code at the same time and share its instruction
+  // fetches (the kernel is instruction-fetch bound, profiles/round1_variants.md).
+  const bool psync = NMAX > 64 && a.pair_sync != 0;
+  volatile long long* slots = reinterpret_cast<volatile long long*>(
+      nm_smem + (size_t)warps_per_cta * (16 + 2 * (size_t)a.region_floats * sizeof(float)));
+  unsigned iter = 0;
+
   int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
-  if (tile >= n_tiles) return;
+  if (tile >= n_tiles) {
+    if (!psync) return;
+    tile = -1;  // keeps arriving at the pair barrier with empty tiles
+  }
   if (lane == 0) nm_mbar_init(bar, 1);
   __syncwarp();
   unsigned parity = 0;
@@ -270,11 +283,23 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   while (true) {
     // ---- claim the next tile and start fetching its metadata (consumed after the walk)
     int64_t next = -1;
-    {
+    bool done;
+    if (psync) {
+      const int pr = wib & 3;
+      volatile long long* slot = slots + ((iter & 1u) << 2) + pr;
+      if (wib < 4 && lane == 0) *slot = (long long)atomicAdd(a.tile_cursor, 2) + n_warps;
+      asm volatile("bar.sync %0, 64;" ::"r"(pr + 1) : "memory");
+      const long long t = *slot;
+      done = t >= n_tiles;
+      const long long mine = t + (wib >> 2);
+      next = mine < n_tiles ? mine : -1;
+      ++iter;
+    } else {
       long long t = 0;
       if (lane == 0) t = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
       t = __shfl_sync(0xffffffffu, t, 0);
       next = t < n_tiles ? t : -1;
+      done = next < 0;
     }
     const nm_tile_meta nxt = nm_tile_fetch(a, next, lane);
 
@@ -305,7 +330,7 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       // Size class of the tile.  Tiles whose longest row is more than half the call's longest
       // row all use the call's class: a handful of extra comparators costs far less than
       // keeping several 30-60 KB networks alive in the 32 KB instruction cache.
-      int nsel = (cst.nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+      int nsel = nm_lane_class(cst.nmax);
       if (2 * cst.nmax > a.class_n) nsel = a.class_n;
       nm_lane_acc acc;
       acc.dnum = acc.r2 = acc.tie = 0;
@@ -369,18 +394,43 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       cst = nm_tile_plan(nxt);
       staged = false;
     }
-    if (next < 0) break;
+    if (done) break;
   }
 }
 
 static int nm_lane_warp_smem(int region_floats) { return 16 + 2 * region_floats * (int)sizeof(float); }
 
 template <int NMAX>
-static int nm_launch_lane_t(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
+static int nm_launch_lane_t(const nm_kargs& ka_in, bool want_u, bool want_t, int sm_count, int pair_sync,
+                            cudaStream_t st) {
+  nm_kargs ka = ka_in;
   const int per_warp = nm_lane_warp_smem(ka.region_floats);
+  const int sync_smem = NM_LANE_SYNC_WARPS * per_warp + 64;  // + the pairs' tile slots
   cudaError_t e = cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       NM_LANE_MAX_WARPS * per_warp);
+                                       NMAX > 64 ? sync_smem : NM_LANE_MAX_WARPS * per_warp);
+  if (e != cudaSuccess && NMAX > 64) {  // the 8-warp shape does not fit (N > 104): plain mode only
+    (void)cudaGetLastError();
+    pair_sync = 0;
+    e = cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             NM_LANE_MAX_WARPS * per_warp);
+  }
   if (e != cudaSuccess) return (int)e;
+  ka.pair_sync = 0;
+  if (NMAX > 64 && pair_sync) {
+    int blocks = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_kernel<NMAX>, 32 * NM_LANE_SYNC_WARPS,
+                                                      (size_t)sync_smem);
+    if (e == cudaSuccess && blocks >= 1) {
+      ka.pair_sync = 1;
+      const int64_t tiles = (ka.n_rows + 31) / 32;
+      int64_t grid = (tiles + NM_LANE_SYNC_WARPS - 1) / NM_LANE_SYNC_WARPS;
+      if (grid > (int64_t)blocks * sm_count) grid = (int64_t)blocks * sm_count;
+      nm_lane_kernel<NMAX><<<(unsigned)grid, 32 * NM_LANE_SYNC_WARPS, (size_t)sync_smem, st>>>(
+          ka, want_u ? 1 : 0, want_t ? 1 : 0);
+      return (int)cudaGetLastError();
+    }
+    (void)cudaGetLastError();
+  }
   // CTA shape: as many resident warps per SM as shared memory and registers allow
   int best_w = 1, best_blocks = 0, best_warps = 0;
   for (int w = NM_LANE_MAX_WARPS; w >= 1; --w) {
@@ -404,11 +454,12 @@ static int nm_launch_lane_t(const nm_kargs& ka, bool want_u, bool want_t, int sm
 }
 
 // max_n = longest lane-tier row of this call
-int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st) {
+int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, int sm_count, int pair_sync,
+                   cudaStream_t st) {
   nm_kargs ka = ka_in;
-  const int ncls = (max_n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
-  ka.region_floats = 32 * ((ncls > 0 ? ncls : NM_LANE_STEP) + 2);
-  ka.class_n = ncls > 0 ? ncls : NM_LANE_STEP;
-  if (max_n <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, st);
-  return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
+  const int ncls = nm_lane_class(max_n);
+  ka.region_floats = 32 * (ncls + 2);
+  ka.class_n = ncls;
+  if (max_n <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, 0, st);
+  return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, pair_sync, st);
 }

@@ -55,7 +55,7 @@ int emul_lane_position(const float* a, int n0, const float* b, int n1, int want_
                        nm_row_out* out) {
   const int nmax = n0 > n1 ? n0 : n1;
   if (nmax > NM_LANE_MAX_N || n0 < 2 || n1 < 2) return 1;
-  const int nsel = (nmax + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP;
+  const int nsel = nm_lane_class(nmax);
   memset(out, 0, sizeof(*out));
 #define CALL(NN) lane_position<NN>(a, n0, b, n1, want_u != 0, want_t != 0, out)
   NM_DISPATCH_N(nsel, CALL)
