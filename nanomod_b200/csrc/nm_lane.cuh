@@ -24,27 +24,39 @@ struct nm_sortnet;
 // -DNM_INT_KEYS the values are mapped to order-preserving int32 keys so that two thirds of the
 // compare-exchanges can run as {min, a+b-min} with the additions issued as IMADs on the FMA
 // pipe, which is otherwise idle (the ALU pipe is the bottleneck of the sort: tools/ubench.cu).
-// x + 0.0f folds -0.0 into +0.0 first, so that -0.0 and 0.0 stay tied as they are for scipy.
+// Non-negative floats are their own bit pattern; a negative float of magnitude m maps to -m
+// (0x80000000 - bits), so -0.0 and 0.0 share key 0 and stay tied as they are for scipy.  One
+// compare + one predicated subtract per value.
 #ifdef NM_INT_KEYS
 typedef int nm_key;
 NM_HD nm_key nm_make_key(float x) {
-  const float y = x + 0.0f;
 #if defined(__CUDA_ARCH__)
-  const int k = __float_as_int(y);
+  const int k = __float_as_int(x);
 #else
   int k;
-  memcpy(&k, &y, sizeof(k));
+  memcpy(&k, &x, sizeof(k));
 #endif
-  return k ^ ((k >> 31) & 0x7fffffff);
+  return k < 0 ? (int)(0x80000000u - (unsigned)k) : k;
+}
+// same value; the subtraction written as a multiply-add by a runtime -1 (FMA pipe, not ALU)
+NM_HD nm_key nm_make_key(float x, int mone) {
+#if defined(__CUDA_ARCH__)
+  const int k = __float_as_int(x);
+#else
+  int k;
+  memcpy(&k, &x, sizeof(k));
+#endif
+  return k < 0 ? k * mone + (int)((unsigned)mone << 31) : k;  // -k + INT_MIN as one IMAD
 }
 #define NM_KEY_PINF 0x7f800000
-#define NM_KEY_NINF ((int)0x807fffff)
+#define NM_KEY_NINF ((int)0x80800000)  // key of -inf
 NM_HD int nm_min(int a, int b) { return a < b ? a : b; }
 NM_HD int nm_max(int a, int b) { return a > b ? a : b; }
 #define NM_CEB(i, j) nm_ceb(x[i], x[j], one, mone);
 #else
 typedef float nm_key;
 NM_HD nm_key nm_make_key(float x) { return x; }
+NM_HD nm_key nm_make_key(float x, int) { return x; }
 #define NM_KEY_PINF INFINITY
 #define NM_KEY_NINF (-INFINITY)
 #define NM_CEB(i, j) NM_CE(i, j)
@@ -72,7 +84,18 @@ NM_HD void nm_ceb(float& a, float& b, int, int) {
     x[i] = lo_;                        \
     x[j] = hi_;                        \
   }
+// Flavour of comparator p (index mod 12): one in NM_CE_MIX uses {min,max} on the ALU pipe, the
+// others {min, a+b-min} with IMADs.  1:2 keeps both pipes equally busy in isolation
+// (tools/ubench.cu); the rest of the kernel is ALU-heavy, see profiles/round1_variants.md.
+#ifndef NM_CE_MIX
+#define NM_CE_MIX 3
+#endif
+#define NM_CEP(p, i, j) NM_CEP_SEL((p) % NM_CE_MIX == 0, i, j)
+#define NM_CEP_SEL(isA, i, j)        \
+  if constexpr (isA) NM_CE(i, j) else { NM_CEB(i, j) }
 #include "nm_sortnet.inc"
+#undef NM_CEP
+#undef NM_CEP_SEL
 
 // Looped, small-footprint sorts for the large size classes (tools/gen_sortloop.py).
 template <int N>

@@ -34,6 +34,11 @@
 
 // Load one group's row into registers (pad +inf), sort, write back transposed with a -inf row
 // in front and a +inf sentinel row behind (layout expected by nm_merge_walk).
+#ifndef NM_KEY_ALU  // default: the negation of negative values as an IMAD (FMA pipe), 1 % faster
+#define NM_MK(v) nm_make_key(v, mone)
+#else
+#define NM_MK(v) nm_make_key(v)
+#endif
 template <int N>
 __device__ __forceinline__ void nm_lane_sort_group(float* region, int base, int n, int lane,
                                                    int one, int mone) {
@@ -45,13 +50,13 @@ __device__ __forceinline__ void nm_lane_sort_group(float* region, int base, int 
 #pragma unroll
     for (int q = 0; q < N / 4; ++q) {
       const float4 v = raw4[q];
-      x[4 * q + 0] = nm_make_key(v.x);
-      x[4 * q + 1] = nm_make_key(v.y);
-      x[4 * q + 2] = nm_make_key(v.z);
-      x[4 * q + 3] = nm_make_key(v.w);
+      x[4 * q + 0] = NM_MK(v.x);
+      x[4 * q + 1] = NM_MK(v.y);
+      x[4 * q + 2] = NM_MK(v.z);
+      x[4 * q + 3] = NM_MK(v.w);
     }
   } else {
-    NM_FOR_ROW(N / 4, raw4, shift, n, { x[e] = valid ? nm_make_key(v) : (nm_key)NM_KEY_PINF; })
+    NM_FOR_ROW(N / 4, raw4, shift, n, { x[e] = valid ? NM_MK(v) : (nm_key)NM_KEY_PINF; })
     // the last (up to 3) elements of a long shifted row lie in window slots N..N+2; slots
     // 0..shift-1 are free exactly then (N + j valid  =>  j < shift), so they wrap around
     const float4 w4 = raw4[N / 4];
@@ -59,7 +64,7 @@ __device__ __forceinline__ void nm_lane_sort_group(float* region, int base, int 
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const bool wrap = (unsigned)(N + j - shift) < (unsigned)n;
-      x[j] = wrap ? nm_make_key(ww[j]) : x[j];
+      x[j] = wrap ? NM_MK(ww[j]) : x[j];
     }
   }
   nm_sorter<N>::run(x, one, mone);
@@ -99,13 +104,19 @@ __device__ __forceinline__ void nm_lane_tile(float* regA, float* regB, int base0
 #define NM_KREG "f"
 #endif
 
+// pointer bump of a chain: on the ALU pipe, or (NM_WALK_IMAD) as a multiply-add by a runtime 1
+#ifdef NM_WALK_IMAD
+#define NM_PTR_ADD(pred, reg, imm) pred " mad.lo.s32 " reg ", %8, " imm ", " reg ";\n\t"
+#else
+#define NM_PTR_ADD(pred, reg, imm) pred " add.s32 " reg ", " reg ", " imm ";\n\t"
+#endif
+
 // one forward step: take the smaller head (ties: group 0), reload it, evaluate at a tie-group end
-#define NM_FWD_STEP(fa, fb, va, vb, v, c, dmax)                                      \
+#define NM_FWD_STEP(fa, fb, va, vb, v, c, dmax, one)                                      \
   asm volatile(                                                                      \
       "{\n\t.reg .pred p, q;\n\t.reg .s32 d;\n\t.reg ." NM_KT " vn;\n\t"              \
       "setp.le." NM_KT " p, %2, %3;\n\t"                                             \
-      "@p add.u32 %0, %0, 128;\n\t"                                                  \
-      "@!p add.u32 %1, %1, 128;\n\t"                                                 \
+      NM_PTR_ADD("@p", "%0", "128") NM_PTR_ADD("@!p", "%1", "128")                  \
       "@p ld.shared." NM_KT " %2, [%0];\n\t"                                         \
       "@!p ld.shared." NM_KT " %3, [%1];\n\t"                                        \
       "min." NM_KT " vn, %2, %3;\n\t"                                                \
@@ -115,15 +126,14 @@ __device__ __forceinline__ void nm_lane_tile(float* regA, float* regB, int base0
       "abs.s32 d, d;\n\t"                                                            \
       "@q max.s32 %5, %5, d;\n\t}"                                                   \
       : "+r"(fa), "+r"(fb), "+" NM_KREG(va), "+" NM_KREG(vb), "+" NM_KREG(v), "+r"(dmax) \
-      : "r"(T), "r"(c))
+      : "r"(T), "r"(c), "r"(one))
 
 // one backward step: take the larger tail (ties: group 1), reload it, evaluate at a group start
-#define NM_BWD_STEP(ba, bb, ea, eb, w, c, dmax)                                      \
+#define NM_BWD_STEP(ba, bb, ea, eb, w, c, dmax, one)                                      \
   asm volatile(                                                                      \
       "{\n\t.reg .pred p, q;\n\t.reg .s32 d;\n\t.reg ." NM_KT " wn;\n\t"              \
       "setp.ge." NM_KT " p, %3, %2;\n\t"                                             \
-      "@p sub.u32 %1, %1, 128;\n\t"                                                  \
-      "@!p sub.u32 %0, %0, 128;\n\t"                                                 \
+      NM_PTR_ADD("@p", "%1", "-128") NM_PTR_ADD("@!p", "%0", "-128")                \
       "@p ld.shared." NM_KT " %3, [%1];\n\t"                                         \
       "@!p ld.shared." NM_KT " %2, [%0];\n\t"                                        \
       "max." NM_KT " wn, %2, %3;\n\t"                                                \
@@ -133,14 +143,14 @@ __device__ __forceinline__ void nm_lane_tile(float* regA, float* regB, int base0
       "abs.s32 d, d;\n\t"                                                            \
       "@q max.s32 %5, %5, d;\n\t}"                                                   \
       : "+r"(ba), "+r"(bb), "+" NM_KREG(ea), "+" NM_KREG(eb), "+" NM_KREG(w), "+r"(dmax) \
-      : "r"(T), "r"(c))
+      : "r"(T), "r"(c), "r"(one))
 
 // Both chains run `iters` (warp-uniform, >= ceil(T/2) for every lane) steps, so on lanes whose
 // T is smaller than the warp maximum they overlap in the middle; every evaluated point is still
 // a genuine tie-group boundary, so the maximum is unchanged.  Requires iters <= T on every lane
 // (a chain must not run off the end of the columns).
 __device__ __forceinline__ int nm_walk_ks_fast(const nm_key* colA, const nm_key* colB, int n0,
-                                               int n1, int iters) {
+                                               int n1, int iters, int one) {
   const int T = n0 + n1;
   const unsigned A0 = nm_smem_u32(colA), B0 = nm_smem_u32(colB);
   unsigned fa = A0 + 128u, fb = B0 + 128u;
@@ -155,10 +165,64 @@ __device__ __forceinline__ int nm_walk_ks_fast(const nm_key* colA, const nm_key*
   int dmax = 0;
 #pragma unroll 4
   for (int s = 0; s < iters; ++s) {
-    NM_FWD_STEP(fa, fb, va, vb, v, cf, dmax);
-    NM_BWD_STEP(ba, bb, ea, eb, w, cb, dmax);
+    NM_FWD_STEP(fa, fb, va, vb, v, cf, dmax, one);
+    NM_BWD_STEP(ba, bb, ea, eb, w, cb, dmax, one);
     cf -= k0;
     cb += k0;
+  }
+  return dmax >> 7;
+}
+
+// Four chains: the pooled order is split at h = T/2 by a merge-path search (ties: group 0 first,
+// the order both chain kinds assume), then a forward and a backward chain work on each half.
+// The walk is latency bound (a step is compare -> pointer bump -> shared load -> compare), so
+// halving the chain length matters more than the ~60 instructions of the search.  `it` is
+// warp-uniform with 2*it >= ceil(T/2) and it <= T/2 on every lane.
+__device__ __forceinline__ int nm_walk_ks_fast4(const nm_key* colA, const nm_key* colB, int n0,
+                                                int n1, int it, int search_iters, int one) {
+  const int T = n0 + n1, h = T >> 1;
+  const unsigned A0 = nm_smem_u32(colA), B0 = nm_smem_u32(colB);
+  // smallest i with b[h-i-1] < a[i]: i elements of group 0 among the first h pooled ones
+  // (row k+1 of a column holds element k; row 0 is -inf and row n+1 is +inf)
+  int lo = h - n1 > 0 ? h - n1 : 0, hi = h < n0 ? h : n0;
+#pragma unroll 1
+  for (int k = 0; k < search_iters; ++k) {
+    const int mid = (lo + hi) >> 1;
+    const bool P = colB[(h - mid) << 5] < colA[(mid + 1) << 5];
+    hi = P ? mid : hi;
+    lo = P ? lo : mid + 1;
+  }
+  const int is = lo, js = h - lo;
+  unsigned f1a = A0 + 128u, f1b = B0 + 128u;
+  unsigned b1a = A0 + 128u * (unsigned)is, b1b = B0 + 128u * (unsigned)js;
+  unsigned f2a = b1a + 128u, f2b = b1b + 128u;
+  unsigned b2a = A0 + 128u * (unsigned)n0, b2b = B0 + 128u * (unsigned)n1;
+  nm_key v1a = colA[32], v1b = colB[32], v1 = nm_min(v1a, v1b);
+  nm_key e1a = colA[is << 5], e1b = colB[js << 5], w1 = nm_max(e1a, e1b);
+  nm_key v2a = colA[(is + 1) << 5], v2b = colB[(js + 1) << 5], v2 = nm_min(v2a, v2b);
+  nm_key e2a = colA[n0 << 5], e2b = colB[n1 << 5], w2 = nm_max(e2a, e2b);
+  const int k0 = 128 * n0;
+  // forward, m elements consumed:  128*d = (fa - A0 - 128)*T - k0*m ; backward, r remaining:
+  // 128*d = (ba - A0)*T - k0*r
+  const int cF = -(int)((A0 + 128u) * (unsigned)T), cB = -(int)(A0 * (unsigned)T);
+  int cf1 = cF - k0, cb1 = cB - k0 * (h - 1), cf2 = cF - k0 * (h + 1), cb2 = cB - k0 * (T - 1);
+  // the boundary between pooled elements h-1 and h belongs to neither half's chains
+  int dmax = 0;
+  {
+    int dj = 128 * (is * T - h * n0);
+    dj = dj < 0 ? -dj : dj;
+    if (w1 < v2) dmax = dj;
+  }
+#pragma unroll 2
+  for (int s = 0; s < it; ++s) {
+    NM_FWD_STEP(f1a, f1b, v1a, v1b, v1, cf1, dmax, one);
+    NM_BWD_STEP(b1a, b1b, e1a, e1b, w1, cb1, dmax, one);
+    NM_FWD_STEP(f2a, f2b, v2a, v2b, v2, cf2, dmax, one);
+    NM_BWD_STEP(b2a, b2b, e2a, e2b, w2, cb2, dmax, one);
+    cf1 -= k0;
+    cb1 += k0;
+    cf2 -= k0;
+    cb2 += k0;
   }
   return dmax >> 7;
 }
@@ -279,6 +343,12 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   nm_tile_meta cur = nm_tile_fetch(a, tile, lane);
   nm_tile_stage cst = nm_tile_plan(cur);
   bool staged = false;  // TMA for `cur` already issued?
+  // The tile after next is claimed one iteration early: the atomic's round trip and the two
+  // dependent metadata loads of a tile each get a whole tile of work to land.
+  long long claim = 0;
+#ifndef NM_NO_PIPE_CLAIM
+  if (!psync && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+#endif
 
   while (true) {
     // ---- claim the next tile and start fetching its metadata (consumed after the walk)
@@ -295,11 +365,15 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       next = mine < n_tiles ? mine : -1;
       ++iter;
     } else {
-      long long t = 0;
-      if (lane == 0) t = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
-      t = __shfl_sync(0xffffffffu, t, 0);
+#ifdef NM_NO_PIPE_CLAIM
+      if (lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+#endif
+      const long long t = __shfl_sync(0xffffffffu, claim, 0);
       next = t < n_tiles ? t : -1;
       done = next < 0;
+#ifndef NM_NO_PIPE_CLAIM
+      if (!done && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+#endif
     }
     const nm_tile_meta nxt = nm_tile_fetch(a, next, lane);
 
@@ -313,13 +387,13 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       int base0 = cst.base0, base1 = cst.base1;
       if (!cst.bytes0) base0 = nm_lane_gather(regA, a.vals0, cur.s0, cur.n0, lane);
       if (!cst.bytes1) base1 = nm_lane_gather(regB, a.vals1, cur.s1, cur.n1, lane);
-      // plan the next tile now (its metadata loads have had the whole staging latency to land)
-      // and pull its value slices into L2 while this tile is being sorted
+#ifdef NM_EARLY_PLAN
       const nm_tile_stage nst = nm_tile_plan(nxt);
       if (lane == 0) {
         if (nst.bytes0) nm_prefetch_l2(a.vals0 + nst.al0, nst.bytes0);
         if (nst.bytes1) nm_prefetch_l2(a.vals1 + nst.al1, nst.bytes1);
       }
+#endif
       if (cst.bytes0 | cst.bytes1) {
         nm_mbar_wait(bar, parity);
         parity ^= 1u;
@@ -345,14 +419,33 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       NM_DISPATCH_N(nsel, NM_CALL)
 #undef NM_CALL
 
+#ifndef NM_EARLY_PLAN
+      // plan the next tile (its metadata loads have had both sorts to land) and pull its value
+      // slices into L2 while this tile is walked and finished
+      const nm_tile_stage nst = nm_tile_plan(nxt);
+      if (lane == 0) {
+        if (nst.bytes0) nm_prefetch_l2(a.vals0 + nst.al0, nst.bytes0);
+        if (nst.bytes1) nm_prefetch_l2(a.vals1 + nst.al1, nst.bytes1);
+      }
+#endif
+
       const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
       const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
       const int iters = (cst.tmax + 1) >> 1;
+#ifdef NM_WALK2
       const bool fast = __all_sync(0xffffffffu, n0 + n1 >= iters);
+#else
+      const int it4 = (cst.tmax + 3) >> 2;
+      const bool fast = __all_sync(0xffffffffu, ((n0 + n1) >> 1) >= it4);
+#endif
       if (want_u)
         nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
       else if (fast)
-        acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters);
+#ifdef NM_WALK2
+        acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters, a.one);
+#else
+        acc.dnum = nm_walk_ks_fast4(colA, colB, n0, n1, it4, 32 - __clz(cst.nmax), a.one);
+#endif
       else
         nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
 
