@@ -431,21 +431,19 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
 
       const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
       const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
+      // KS-only fast walks: four chains where 8 warps/SM leave the walk latency bound (long
+      // rows), two chains where 12 warps/SM hide it and the split search is pure overhead
       const int iters = (cst.tmax + 1) >> 1;
-#ifdef NM_WALK2
-      const bool fast = __all_sync(0xffffffffu, n0 + n1 >= iters);
-#else
       const int it4 = (cst.tmax + 3) >> 2;
-      const bool fast = __all_sync(0xffffffffu, ((n0 + n1) >> 1) >= it4);
-#endif
+      constexpr bool kFour = NMAX > 64;
+      const bool fast = kFour ? __all_sync(0xffffffffu, ((n0 + n1) >> 1) >= it4)
+                              : __all_sync(0xffffffffu, n0 + n1 >= iters);
       if (want_u)
         nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
-      else if (fast)
-#ifdef NM_WALK2
-        acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters, a.one);
-#else
+      else if (fast && kFour)
         acc.dnum = nm_walk_ks_fast4(colA, colB, n0, n1, it4, 32 - __clz(cst.nmax), a.one);
-#endif
+      else if (fast)
+        acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters, a.one);
       else
         nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
 

@@ -82,6 +82,10 @@ def main():
         dev, nvals = poisson_workload(4_600_000, 100, d)
         run("cfg2p E.coli Poisson(100) clipped [5,128] KS+Stouffer", dev, nvals, 4_600_000, ks_st, 28)
         del dev
+    if "cfg2h" in which:
+        dev, _ = make_device_workload(4_600_000, 50, 50, d)
+        run("cfg2h E.coli 2x50x KS+Stouffer", dev, 4_600_000 * 100, 4_600_000, ks_st, 28)
+        del dev
     if "cfg5" in which:
         dev, _ = make_device_workload(50_000, 2000, 2000, d)
         run("cfg5 50kb plasmid 2x2000x KS+Stouffer (deep tier)", dev, 50_000 * 4000, 50_000, ks_st, 28, steps=5, warmup=2)
