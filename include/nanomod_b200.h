@@ -88,6 +88,9 @@ typedef struct nm_table {
   double* stouffer_stat;  /* NM_COMBINE_STOUFFER: weighted Z                                 */
   double* stouffer_p;
   uint8_t* flags;         /* optional: bit0 = all pooled values identical (U p is NaN)       */
+  double* moments;        /* optional, 4 doubles per row: mean0, var0, mean1, var1 (ddof=1,  */
+                          /* numpy two-pass form): the --mstd output (myDetect.py:437-438,    */
+                          /* :540-545; std there is ddof=0 = sqrt(var*(n-1)/n))               */
 } nm_table;
 
 typedef struct nm_handle nm_handle;
@@ -112,6 +115,17 @@ int nm_detect_device(nm_handle* h, const nm_pileup* pileup, const nm_params* par
  * Copies the pileup to the GPU, runs nm_detect_device, copies the n_rows result rows back. */
 int nm_detect_host(nm_handle* h, const nm_pileup* pileup, const nm_params* params,
                    const nm_table* table, int64_t* n_rows);
+
+/* Ranking of the rows (mtest2, myDetect.py:459-461): order[k] = index of the k-th row of
+ * moptions['sorted_sign_test'], i.e. a stable ascending sort on (key_comb, key_ks, key_u) --
+ * the p-value columns for rankUse='pv', the statistic columns with reverse=1 for 'st'.
+ * key_comb (testMethod 'ks') and key_u (U not computed) may be NULL.  NaN keys sort last.
+ * _device: all pointers are device memory, work is enqueued on cuda_stream and complete on
+ * return; _host: host memory. */
+int nm_rank_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                   int64_t n_rows, int reverse, int32_t* order, void* cuda_stream);
+int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                 int64_t n_rows, int reverse, int32_t* order);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nm_launch_count(const nm_handle* h);

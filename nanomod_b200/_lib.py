@@ -23,7 +23,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
                     "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings",
-                    "nm_set_sm_limit", "nm_sm_count"]
+                    "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host"]
 
 
 class NmError(RuntimeError):
@@ -45,12 +45,14 @@ class nm_pileup(C.Structure):
 
 
 TABLE_FIELDS = ["row_pos_index", "n0", "n1", "ks_dnum", "ks_d", "ks_p", "two_u", "u_stat", "u_p",
-                "t_stat", "t_p", "fisher_stat", "fisher_p", "stouffer_stat", "stouffer_p", "flags"]
+                "t_stat", "t_p", "fisher_stat", "fisher_p", "stouffer_stat", "stouffer_p", "flags",
+                "moments"]
 TABLE_DTYPES = {"row_pos_index": "int32", "n0": "int32", "n1": "int32", "ks_dnum": "int32",
                 "ks_d": "float64", "ks_p": "float64", "two_u": "int64", "u_stat": "float64",
                 "u_p": "float64", "t_stat": "float64", "t_p": "float64", "fisher_stat": "float64",
                 "fisher_p": "float64", "stouffer_stat": "float64", "stouffer_p": "float64",
-                "flags": "uint8"}
+                "flags": "uint8", "moments": "float64"}
+TABLE_WIDTH = {"moments": 4}  # columns that hold several values per row
 
 
 class nm_table(C.Structure):
@@ -93,6 +95,12 @@ def load():
     lib.nm_detect_host.restype = C.c_int
     lib.nm_detect_host.argtypes = [C.c_void_p, C.POINTER(nm_pileup), C.POINTER(nm_params),
                                    C.POINTER(nm_table), C.POINTER(C.c_int64)]
+    lib.nm_rank_device.restype = C.c_int
+    lib.nm_rank_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                   C.c_void_p, C.c_void_p]
+    lib.nm_rank_host.restype = C.c_int
+    lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                 C.c_void_p]
     _lib = lib
     return lib
 
@@ -159,3 +167,14 @@ class Handle:
                                                C.byref(table), C.byref(n_rows),
                                                C.c_void_p(int(stream))))
         return int(n_rows.value)
+
+    def rank_host(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, order) -> None:
+        """nm_rank_host on raw host addresses (0 / None = key absent)."""
+        self._check(self._lib.nm_rank_host(self._h, C.c_void_p(key_comb or 0), C.c_void_p(key_ks),
+                                           C.c_void_p(key_u or 0), int(n_rows), int(bool(reverse)),
+                                           C.c_void_p(order)))
+
+    def rank_device(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, order, stream: int = 0) -> None:
+        self._check(self._lib.nm_rank_device(self._h, C.c_void_p(key_comb or 0), C.c_void_p(key_ks),
+                                             C.c_void_p(key_u or 0), int(n_rows), int(bool(reverse)),
+                                             C.c_void_p(order), C.c_void_p(int(stream))))

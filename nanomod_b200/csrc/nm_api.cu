@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include "nm_device.cuh"
+#include "nm_rank.cuh"
 
 // ------------------------------------------------------------------------------------------
 // plan: coverage filter + ordered compaction (myDetect.py:301-314, :428-431)
@@ -291,7 +292,8 @@ struct nm_handle {
   nm_buf d_block_count, d_deep_rows, d_acc_r2, d_acc_tie, d_acc_mom;
   // staging for nm_detect_host
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
-  nm_buf d_out[16];
+  nm_buf d_out[17];
+  nm_buf d_rank, d_rank_keys[3], d_rank_order;  // nm_rank_*: scratch, staged key columns, result
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int use_pair_tier;   // NANOMOD_B200_PAIR_TIER=1: two lanes per position for long rows (experimental)
@@ -406,7 +408,8 @@ extern "C" void nm_destroy(nm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
-                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg};
+                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_rank_keys[0],
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -434,7 +437,7 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   return NM_OK;
 }
 
-static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, int max_lane_n, int max_deep_p2, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int max_lane_n, int max_deep_p2, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
     const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
@@ -443,8 +446,8 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
     // measured slower than the lane tier in round 1 (profiles/round1_variants.md).  Off unless
     // NANOMOD_B200_PAIR_TIER=1.
     const bool pair = h->use_pair_tier && !want_u && max_lane_n > 64 && nm_pair_tier_available();
-    const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(ka, want_t, max_lane_n, sms, st)
-                                             : nm_launch_lane(ka, want_u, want_t, max_lane_n, sms, h->use_pair_sync, st));
+    const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(ka, want_m, max_lane_n, sms, st)
+                                             : nm_launch_lane(ka, want_u, want_m, max_lane_n, sms, h->use_pair_sync, st));
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
                      cudaGetErrorString(e));
@@ -452,7 +455,7 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
-    const cudaError_t e = (cudaError_t)nm_launch_deep(ka, want_u, want_t, n_deep, max_deep_p2, deep_smem, st);
+    const cudaError_t e = (cudaError_t)nm_launch_deep(ka, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -551,12 +554,16 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     ka.acc_r2 = (int*)h->d_acc_r2.p;
     ka.acc_tie = (int*)h->d_acc_tie.p;
   }
-  if (want_t) {
+  // group moments: straight into the caller's array when asked for (--mstd), else scratch for t
+  const bool want_m = want_t || tb->moments != nullptr;
+  if (tb->moments) {
+    ka.acc_mom = tb->moments;
+  } else if (want_t) {
     if ((rc = nm_reserve(h, &h->d_acc_mom, sizeof(double) * 4 * (size_t)n_rows)) != NM_OK) return rc;
     ka.acc_mom = (double*)h->d_acc_mom.p;
   }
   const int deep_smem = 16 + (sum.max_deep_p2 + 16) * (int)sizeof(float);
-  rc = nm_launch_tiers(h, ka, want_u, want_t, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;
 
   // ---- neighbour combination
@@ -618,12 +625,12 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
   NM_CUDA(h, cudaMemcpyAsync(h->d_seg.p, pl->seg, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
 
   // device-side table mirrors exactly the outputs the caller asked for
-  void* const host_ptrs[16] = {tb->row_pos_index, tb->n0, tb->n1, tb->ks_dnum, tb->ks_d, tb->ks_p,
+  void* const host_ptrs[17] = {tb->row_pos_index, tb->n0, tb->n1, tb->ks_dnum, tb->ks_d, tb->ks_p,
                                tb->two_u, tb->u_stat, tb->u_p, tb->t_stat, tb->t_p, tb->fisher_stat,
-                               tb->fisher_p, tb->stouffer_stat, tb->stouffer_p, tb->flags};
-  const size_t elem[16] = {4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 1};
-  void* dev_ptrs[16];
-  for (int k = 0; k < 16; ++k) {
+                               tb->fisher_p, tb->stouffer_stat, tb->stouffer_p, tb->flags, tb->moments};
+  const size_t elem[17] = {4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 1, 32};
+  void* dev_ptrs[17];
+  for (int k = 0; k < 17; ++k) {
     dev_ptrs[k] = nullptr;
     if (host_ptrs[k]) {
       if ((rc = nm_reserve(h, &h->d_out[k], elem[k] * (size_t)n)) != NM_OK) return rc;
@@ -635,18 +642,66 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
   nm_table dtb = {(int32_t*)dev_ptrs[0], (int32_t*)dev_ptrs[1], (int32_t*)dev_ptrs[2], (int32_t*)dev_ptrs[3],
                   (double*)dev_ptrs[4], (double*)dev_ptrs[5], (int64_t*)dev_ptrs[6], (double*)dev_ptrs[7],
                   (double*)dev_ptrs[8], (double*)dev_ptrs[9], (double*)dev_ptrs[10], (double*)dev_ptrs[11],
-                  (double*)dev_ptrs[12], (double*)dev_ptrs[13], (double*)dev_ptrs[14], (uint8_t*)dev_ptrs[15]};
+                  (double*)dev_ptrs[12], (double*)dev_ptrs[13], (double*)dev_ptrs[14], (uint8_t*)dev_ptrs[15],
+                  (double*)dev_ptrs[16]};
   int64_t n_rows = 0;
   rc = nm_detect_device(h, &dpl, &prm, &dtb, &n_rows, (void*)st);
   if (rc != NM_OK) return rc;
-  const bool live[16] = {true, true, true, true, true, true,
+  const bool live[17] = {true, true, true, true, true, true,
                          prm.want_u != 0, prm.want_u != 0, prm.want_u != 0, prm.want_t != 0, prm.want_t != 0,
                          (prm.combine & NM_COMBINE_FISHER) != 0, (prm.combine & NM_COMBINE_FISHER) != 0,
-                         (prm.combine & NM_COMBINE_STOUFFER) != 0, (prm.combine & NM_COMBINE_STOUFFER) != 0, true};
-  for (int k = 0; k < 16; ++k)
+                         (prm.combine & NM_COMBINE_STOUFFER) != 0, (prm.combine & NM_COMBINE_STOUFFER) != 0, true, true};
+  for (int k = 0; k < 17; ++k)
     if (host_ptrs[k] && live[k] && n_rows > 0)
       NM_CUDA(h, cudaMemcpyAsync(host_ptrs[k], dev_ptrs[k], elem[k] * (size_t)n_rows, cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
   *n_rows_out = n_rows;
+  return NM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// ranking (myDetect.py:459-461) -- see nm_rank.cu
+// ------------------------------------------------------------------------------------------
+extern "C" int nm_rank_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                              int64_t n_rows, int reverse, int32_t* order, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
+  if (n_rows == 0) return NM_OK;
+  if (!key_ks || !order) return nm_fail(h, NM_ERR_BAD_ARG, "key_ks/order is NULL");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = nm_reserve(h, &h->d_rank, nm_rank_scratch_bytes(n_rows));
+  if (rc != NM_OK) return rc;
+  int launches = 0;
+  const cudaError_t e = (cudaError_t)nm_rank_run(key_comb, key_ks, key_u, n_rows, reverse, order, h->d_rank.p, &launches, st);
+  h->launches += launches;
+  if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "ranking failed: %s", cudaGetErrorString(e));
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  return NM_OK;
+}
+
+extern "C" int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                            int64_t n_rows, int reverse, int32_t* order) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
+  if (n_rows == 0) return NM_OK;
+  if (!key_ks || !order) return nm_fail(h, NM_ERR_BAD_ARG, "key_ks/order is NULL");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  const double* host_keys[3] = {key_comb, key_ks, key_u};
+  const double* dev_keys[3] = {nullptr, nullptr, nullptr};
+  int rc;
+  for (int k = 0; k < 3; ++k) {
+    if (!host_keys[k]) continue;
+    if ((rc = nm_reserve(h, &h->d_rank_keys[k], sizeof(double) * (size_t)n_rows)) != NM_OK) return rc;
+    NM_CUDA(h, cudaMemcpyAsync(h->d_rank_keys[k].p, host_keys[k], sizeof(double) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    dev_keys[k] = (const double*)h->d_rank_keys[k].p;
+  }
+  if ((rc = nm_reserve(h, &h->d_rank_order, sizeof(int32_t) * (size_t)n_rows)) != NM_OK) return rc;
+  rc = nm_rank_device(h, dev_keys[0], dev_keys[1], dev_keys[2], n_rows, reverse, (int32_t*)h->d_rank_order.p, (void*)st);
+  if (rc != NM_OK) return rc;
+  NM_CUDA(h, cudaMemcpyAsync(order, h->d_rank_order.p, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost, st));
+  NM_CUDA(h, cudaStreamSynchronize(st));
   return NM_OK;
 }

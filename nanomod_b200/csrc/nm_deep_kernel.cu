@@ -130,7 +130,7 @@ __device__ __forceinline__ int nm_deep_walk(const float* sa, int n0, const float
 // 128 (groups up to 32768 reads) needs most of the register file for one CTA.
 template <int EMAX>
 __global__ void __launch_bounds__(NM_DEEP_THREADS, EMAX <= 16 ? 3 : 1)
-nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t) {
+nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int want_m) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   __shared__ double red_d[NM_DEEP_THREADS / 32];
   __shared__ long long red_l[3][NM_DEEP_THREADS / 32];
@@ -166,7 +166,7 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t) {
   for (int k = n1 + tid; k <= P1; k += NM_DEEP_THREADS) sb[k] = NM_INF;
 
   double mean[2] = {0.0, 0.0}, var[2] = {0.0, 0.0};
-  if (want_t) {
+  if (want_m) {  // Welch t and/or the --mstd output
     for (int g = 0; g < 2; ++g) {
       const float* s = g ? sb : sa;
       const int n = g ? n1 : n0;
@@ -246,21 +246,22 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t) {
     o.u_stat = o.u_p = o.t_stat = o.t_p = 0.0;
     nm_deep_finish(tot, n0, n1, want_u != 0, want_t != 0, mean[0], var[0], mean[1], var[1], &o);
     nm_store_row(a, r, o, want_u != 0, want_t != 0);
+    if (want_m && a.acc_mom) reinterpret_cast<double4*>(a.acc_mom)[r] = make_double4(mean[0], var[0], mean[1], var[1]);
   }
 }
 
 template <int EMAX>
-static int nm_launch_deep_t(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int smem_bytes, cudaStream_t st) {
+static int nm_launch_deep_t(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int smem_bytes, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(nm_deep_kernel<EMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  nm_deep_kernel<EMAX><<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+  nm_deep_kernel<EMAX><<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0, want_m ? 1 : 0);
   return (int)cudaGetLastError();
 }
 
 // max_p2 = largest pow2(n0) + pow2(n1) among the deep rows (each >= NM_DEEP_MIN_P)
-int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, int n_deep, int max_p2, int smem_bytes,
+int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
                    cudaStream_t st) {
   // a group can be at most max_p2 - NM_DEEP_MIN_P long
-  if (max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS) return nm_launch_deep_t<16>(ka, want_u, want_t, n_deep, smem_bytes, st);
-  return nm_launch_deep_t<128>(ka, want_u, want_t, n_deep, smem_bytes, st);
+  if (max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS) return nm_launch_deep_t<16>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
+  return nm_launch_deep_t<128>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
 }

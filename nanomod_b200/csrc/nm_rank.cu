@@ -1,0 +1,93 @@
+// nanomod_b200 -- ranking of the result rows on the device.
+//
+// Reference: mtest2, bin/scripts/myDetect.py:459-461
+//   sorted(sign_test, key=lambda m: (m[1][sorted_ind][u], m[1][2][u], m[1][0][u]))   [::-1] for 'st'
+// i.e. a STABLE ascending sort on the tuple (combined, KS, U) of p-values (rankUse='pv') or of
+// statistics ('st', then the whole list reversed).  Here: least-significant-key-first passes of
+// a stable radix sort (CUB DeviceRadixSort -- library code, this is not the hot path) over
+// order-preserving 64-bit images of the doubles, carrying the row index.  NaN keys (the U
+// p-value of an all-identical position) sort last, as numpy's lexsort puts them; -0.0 == 0.0.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nm_rank.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long nm_rank_key(double x) {
+  if (x != x) return ~0ull;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x + 0.0);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void nm_rank_iota(int32_t* order, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[i] = (int32_t)i;
+}
+
+__global__ void nm_rank_gather_keys(const double* __restrict__ col, const int32_t* __restrict__ order,
+                                    unsigned long long* __restrict__ keys, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = nm_rank_key(col[order[i]]);
+}
+
+__global__ void nm_rank_reverse(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[n - 1 - i];
+}
+
+inline size_t nm_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// Layout of the scratch buffer: keys A | keys B | order A | order B | CUB temporary storage.
+size_t nm_rank_scratch_bytes(int64_t n) {
+  size_t cub_bytes = 0;
+  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+  cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, (int)n);
+  return 2 * nm_align256(sizeof(unsigned long long) * (size_t)n) + 2 * nm_align256(sizeof(int32_t) * (size_t)n) +
+         nm_align256(cub_bytes) + 256;
+}
+
+int nm_rank_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int32_t* order_out,
+                void* scratch, int* launches, cudaStream_t st) {
+  if (n <= 0) return (int)cudaSuccess;
+  unsigned char* p = (unsigned char*)scratch;
+  unsigned long long* kA = (unsigned long long*)p;
+  p += nm_align256(sizeof(unsigned long long) * (size_t)n);
+  unsigned long long* kB = (unsigned long long*)p;
+  p += nm_align256(sizeof(unsigned long long) * (size_t)n);
+  int32_t* oA = (int32_t*)p;
+  p += nm_align256(sizeof(int32_t) * (size_t)n);
+  int32_t* oB = (int32_t*)p;
+  p += nm_align256(sizeof(int32_t) * (size_t)n);
+  size_t cub_bytes = 0;
+  {
+    cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, (int)n);
+  }
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  cub::DoubleBuffer<unsigned long long> keys(kA, kB);
+  cub::DoubleBuffer<int32_t> ord(oA, oB);
+  nm_rank_iota<<<grid, 256, 0, st>>>(ord.Current(), n);
+  ++*launches;
+  const double* cols[3] = {u, ks, comb};  // least significant key first
+  for (int c = 0; c < 3; ++c) {
+    if (!cols[c]) continue;
+    nm_rank_gather_keys<<<grid, 256, 0, st>>>(cols[c], ord.Current(), keys.Current(), n);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs((void*)p, cub_bytes, keys, ord, (int)n, 0, 64, st);
+    if (e != cudaSuccess) return (int)e;
+    *launches += 2;
+  }
+  if (reverse) {
+    nm_rank_reverse<<<grid, 256, 0, st>>>(ord.Current(), order_out, n);
+    ++*launches;
+  } else {
+    cudaError_t e = cudaMemcpyAsync(order_out, ord.Current(), sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaGetLastError();
+}

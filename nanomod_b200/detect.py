@@ -140,6 +140,7 @@ class SignTestTable:
     stouffer_p: Optional[np.ndarray] = None
     flags: Optional[np.ndarray] = None
     row_pos_index: Optional[np.ndarray] = None
+    moments: Optional[np.ndarray] = None  # [rows, 4]: mean0, var0, mean1, var1 (ddof=1); --mstd
 
     def __len__(self) -> int:
         return int(self.pos.shape[0])
@@ -203,6 +204,47 @@ class SignTestTable:
             path = self.options.outFolder + "/" + self.options.FileID + "_sign_test.txt"
         with open(path, "w") as f:
             f.writelines(self.format_lines())
+        self.save_meanstd()  # the reference writes both files from save_test (:540-545)
+        return path
+
+    # ---- --mstd output (myDetect.py:437-438, :540-545) --------------------------------------
+    def mean_std(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """np.mean and np.std (ddof=0) of each group per row, from the device's two-pass moments
+        (var is ddof=1 there: std0 = sqrt(var * (n-1) / n))."""
+        if self.moments is None:
+            raise ValueError("the table was computed without mstd")
+        m = self.moments
+        n0 = self.n0.astype(np.float64)
+        n1 = self.n1.astype(np.float64)
+        return (m[:, 0], np.sqrt(m[:, 1] * (n0 - 1.0) / n0), m[:, 2], np.sqrt(m[:, 3] * (n1 - 1.0) / n1))
+
+    def sign_test_mstd(self) -> Dict:
+        """``moptions['sign_test_mstd']`` as mtest2 fills it (myDetect.py:437-438)."""
+        m0, s0, m1, s1 = self.mean_std()
+        out = {}
+        for r in range(len(self)):
+            sk = self.seg_names[self.seg[r]]
+            out[(sk[0], sk[1], int(self.pos[r]))] = [[float(m0[r]), float(s0[r])], [float(m1[r]), float(s1[r])]]
+        return out
+
+    def meanstd_lines(self) -> List[str]:
+        """Lines of ``<FileID>_meanstd.cvs`` (myDetect.py:540-545; position is 0-based there)."""
+        m0, s0, m1, s1 = self.mean_std()
+        lines = []
+        for r in range(len(self)):
+            sk = self.seg_names[self.seg[r]]
+            lines.append("%s %s %d %s %.3f %.3f %.3f %.3f\n" % (sk[0], sk[1], self.pos[r], chr(self.base[r]),
+                                                             m0[r], s0[r], m1[r], s1[r]))
+        return lines
+
+    def save_meanstd(self, path: Optional[str] = None) -> Optional[str]:
+        if not self.options.mstd or self.moments is None:
+            return None
+        if path is None:
+            os.makedirs(self.options.outFolder, exist_ok=True)
+            path = self.options.outFolder + "/" + self.options.FileID + "_meanstd.cvs"
+        with open(path, "w") as f:
+            f.writelines(self.meanstd_lines())
         return path
 
     # ---- ranking (myDetect.py:447-462, RegionRankbyST == 0) --------------------------------
@@ -269,7 +311,14 @@ def _wanted_columns(opt: DetectOptions) -> List[str]:
         cols += ["fisher_stat", "fisher_p"]
     if mask & _lib.NM_COMBINE_STOUFFER:
         cols += ["stouffer_stat", "stouffer_p"]
+    if opt.mstd:
+        cols += ["moments"]
     return cols
+
+
+def _col_shape(c: str, n: int):
+    w = _lib.TABLE_WIDTH.get(c, 1)
+    return (n, w) if w > 1 else (n,)
 
 
 class Detector:
@@ -291,7 +340,7 @@ class Detector:
         n = pileup.n_pos
         cols = _wanted_columns(opt)
         if out is None:
-            out = {c: np.empty(n, dtype=_lib.TABLE_DTYPES[c]) for c in cols}
+            out = {c: np.empty(_col_shape(c, n), dtype=_lib.TABLE_DTYPES[c]) for c in cols}
         tb = _lib.nm_table(**{c: out[c].ctypes.data for c in cols})
         pl = _lib.nm_pileup(pileup.vals0.ctypes.data, pileup.off0.ctypes.data, pileup.vals1.ctypes.data,
                             pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n)
@@ -304,6 +353,38 @@ class Detector:
             seg, pos, base = pileup.seg[idx], pileup.pos[idx], pileup.base[idx]
         return SignTestTable(options=opt, seg_names=pileup.seg_names, seg=seg, pos=pos, base=base,
                              **{c: res[c] for c in cols})
+
+    def rank(self, table: SignTestTable) -> np.ndarray:
+        """Row order of ``moptions['sorted_sign_test']`` (myDetect.py:459-461) computed on the GPU:
+        same result as ``SignTestTable.ranked()`` (numpy), which it replaces for large tables."""
+        use_p = table.options.rankUse == "pv"
+        comb = table.comb()
+        cols = [None if comb is None else (comb[1] if use_p else comb[0]),
+                table.ks_p if use_p else table.ks_d,
+                None if table.u_p is None else (table.u_p if use_p else table.u_stat)]
+        cols = [None if c is None else np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+        order = np.empty(len(table), dtype=np.int32)
+        if len(table):
+            self.handle.rank_host(*[None if c is None else c.ctypes.data for c in cols], len(table),
+                                  not use_p, order.ctypes.data)
+        return order
+
+    def rank_device(self, out: Dict[str, "object"], n_rows: int, options: DetectOptions,
+                    stream: Optional[int] = None):
+        """Ranking of a device-resident table (``out`` as filled by ``detect_device``): returns an
+        int32 CUDA tensor of row indices."""
+        import torch
+        use_p = options.rankUse == "pv"
+        m = options.testMethod
+        comb = None if m == "ks" else out[("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat")]
+        ks = out["ks_p" if use_p else "ks_d"]
+        u = out.get("u_p" if use_p else "u_stat")
+        order = torch.empty(n_rows, dtype=torch.int32, device=ks.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(ks.device).cuda_stream
+        self.handle.rank_device(None if comb is None else comb.data_ptr(), ks.data_ptr(),
+                                None if u is None else u.data_ptr(), n_rows, not use_p, order.data_ptr(), stream)
+        return order
 
     def detect_device(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
                       stream: Optional[int] = None) -> int:
@@ -340,5 +421,5 @@ class DevicePileup:
 def alloc_device_table(options: DetectOptions, n_pos: int, device) -> Dict[str, "object"]:
     import torch
     tdt = {"int32": torch.int32, "int64": torch.int64, "float64": torch.float64, "uint8": torch.uint8}
-    return {c: torch.empty(n_pos, dtype=tdt[_lib.TABLE_DTYPES[c]], device=device)
+    return {c: torch.empty(_col_shape(c, n_pos), dtype=tdt[_lib.TABLE_DTYPES[c]], device=device)
             for c in _wanted_columns(options)}

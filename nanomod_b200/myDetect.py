@@ -63,19 +63,12 @@ def mtest2(moptions: Dict) -> None:
     table = _run(moptions)
     moptions["_sign_test_table"] = table
     moptions["sign_test"] = table.to_sign_test()
-    if moptions.get("mstd", 0):
-        ds0 = moptions[moptions["ds2"][0]]["norm_mean"]
-        ds1 = moptions[moptions["ds2"][1]]["norm_mean"]
-        moptions["sign_test_mstd"] = {}
-        for (key, _tests) in moptions["sign_test"]:
-            sk, pk = (key[0], key[1]), key[2]
-            a, b = ds0[sk][pk], ds1[sk][pk]
-            moptions["sign_test_mstd"][(key[0], key[1], pk)] = [[np.mean(a), np.std(a)],
-                                                                 [np.mean(b), np.std(b)]]
+    if moptions.get("mstd", 0):  # means / stds come from the device's moments (:437-438)
+        moptions["sign_test_mstd"] = table.sign_test_mstd()
     if moptions.get("SaveTest", 0):
         save_test(moptions)
     st = moptions["sign_test"]
-    moptions["sorted_sign_test"] = [st[int(r)] for r in table.ranked()]
+    moptions["sorted_sign_test"] = [st[int(r)] for r in _detector(moptions).rank(table)]
 
 
 def getKStest(moptions: Dict, a, b, m_str: str) -> List:

@@ -76,8 +76,9 @@ def unpack_records(rec: np.ndarray, like: SignTestTable) -> SignTestTable:
     o = 0
     for c in cols:
         dt = np.dtype(_lib.TABLE_DTYPES[c])
-        kw[c] = np.ascontiguousarray(rec[:, o:o + dt.itemsize]).view(dt).reshape(-1)
-        o += dt.itemsize
+        wd = _lib.TABLE_WIDTH.get(c, 1)
+        kw[c] = np.ascontiguousarray(rec[:, o:o + wd * dt.itemsize]).view(dt).reshape((-1, wd) if wd > 1 else -1)
+        o += wd * dt.itemsize
     meta = {}
     for m in _META:
         dt = getattr(like, m).dtype

@@ -286,6 +286,86 @@ def test_reference_seam_mirror(det):
     assert abs(pks - 0.15504417912365295) < 1e-6 and u == 7.0
 
 
+def test_mstd_moments_and_meanstd_file(det, tmp_path):
+    """--mstd (myDetect.py:437-438, :540-545): per-group mean / std(ddof=0) from the device's
+    moments, for lane-tier and deep-tier rows, with and without the t-test, through the seam
+    mirror, and the text of <FileID>_meanstd.cvs against the oracle's."""
+    rng = np.random.default_rng(5)
+    L = 400
+    c0 = rng.integers(5, 90, L).astype(np.int64)
+    c1 = rng.integers(5, 90, L).astype(np.int64)
+    c0[7], c1[7] = 700, 300
+    c0[200], c1[200] = 130, 6
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0.3, 1.5, off0[-1]), 3).astype(np.float32)
+    v1 = np.round(rng.normal(-0.2, 0.7, off1[-1]), 3).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
+    for want_t in (True, False):
+        opt = nm.DetectOptions(neighborPvalues=2, mstd=True, want_t=want_t, want_u=want_t)
+        t = det.detect(p, opt)
+        m0, s0, m1, s1 = t.mean_std()
+        for r in range(L):
+            a = p.group(0, r).astype(np.float64)
+            b = p.group(1, r).astype(np.float64)
+            for got, want in ((m0[r], np.mean(a)), (s0[r], np.std(a)), (m1[r], np.mean(b)), (s1[r], np.std(b))):
+                assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (r, got, want)
+        if want_t:
+            assert_table_matches(t, vec(p, opt), opt)
+    # through the seam mirror, against the scalar oracle's dictionary and file text
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(neighborPvalues=2, mstd=1, SaveTest=1, outFolder=str(tmp_path), FileID="ms")
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    mo["_detector"] = det
+    myDetect.mfilter_coverage(mo)
+    myDetect.mtest2(mo)
+    ref = o.default_moptions(neighborPvalues=2, mstd=1)
+    ref["ds2"] = ["g0", "g1"]
+    ref["g0"], ref["g1"] = p.to_dicts()
+    o.mfilter_coverage(ref)
+    o.mtest2(ref, strict=False)
+    assert set(mo["sign_test_mstd"]) == set(ref["sign_test_mstd"])
+    for k, want in ref["sign_test_mstd"].items():
+        got = mo["sign_test_mstd"][k]
+        assert np.allclose(np.array(got), np.array(want), rtol=1e-12, atol=1e-12)
+    assert open(str(tmp_path) + "/ms_meanstd.cvs").readlines() == o.save_meanstd_lines(ref)
+
+
+@pytest.mark.parametrize("rank_use", ["pv", "st"])
+@pytest.mark.parametrize("method", ["stouffer", "fisher", "ks"])
+def test_device_ranking_equals_host_ranking(det, rank_use, method):
+    """nm_rank_host / nm_rank_device (mtest2 :459-461) against numpy's stable lexsort on the same
+    table: heavily tied keys (1-decimal data, coverage 6), NaN U p-values, both directions."""
+    import torch
+    p = nm.synthetic_pileup(30000, 6, 7, round_decimals=1, drop_frac1=0.01, two_strands=True)
+    p.vals0[p.off0[100]:p.off0[101]] = 0.5  # all-identical position: U p-value is NaN
+    p.vals1[p.off1[100]:p.off1[101]] = 0.5
+    opt = nm.DetectOptions(neighborPvalues=2, testMethod=method, rankUse=rank_use)
+    t = det.detect(p, opt)
+    want = t.ranked()
+    got = det.rank(t)
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+    # the scalar oracle's sorted list agrees on the leading rows (with testMethod 'ks' the keys
+    # are so heavily tied on this data that last-bit differences of U p-values between oracle
+    # and GPU decide the order; the combined methods have distinct primary keys)
+    if method != "ks":
+        ref = scalar_moptions(p, opt)
+        st = t.to_sign_test()
+        assert [st[int(r)][0] for r in got[:50]] == [m[0] for m in ref["sorted_sign_test"][:50]]
+    # device-resident variant
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    out = nm.alloc_device_table(opt, p.n_pos, "cuda:0")
+    n_rows = det.detect_device(dev, opt, out)
+    order = det.rank_device(out, n_rows, opt)
+    torch.cuda.synchronize()
+    assert np.array_equal(order.cpu().numpy(), want)
+    # without the U column
+    opt2 = nm.DetectOptions(neighborPvalues=2, testMethod=method, rankUse=rank_use, want_u=False, want_t=False)
+    t2 = det.detect(p, opt2)
+    assert np.array_equal(det.rank(t2), t2.ranked())
+
+
 def test_device_resident_entry_and_unaligned_offsets(det):
     """nm_detect_device on torch tensors; rows whose slices start at odd element offsets."""
     import torch

@@ -163,10 +163,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().nm_padded_len(5) == _lib.padded_len(5) == 12
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.nm_params) == 32
-    assert ctypes.sizeof(_lib.nm_pileup) == 56
-    assert ctypes.sizeof(_lib.nm_table) == 16 * 8
+def test_struct_layouts_match_header(tmp_path):
+    """ctypes mirrors vs the real header, measured by a C program compiled from include/."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nanomod_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(nm_params), sizeof(nm_pileup),'
+                   ' sizeof(nm_table), offsetof(nm_table, flags), offsetof(nm_table, moments));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(_lib.nm_params), ctypes.sizeof(_lib.nm_pileup), ctypes.sizeof(_lib.nm_table),
+                   _lib.nm_table.flags.offset, _lib.nm_table.moments.offset]
+    assert got[:3] == [32, 56, 17 * 8]
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -142,3 +142,16 @@ def test_mtest2_row_order_gaps_and_table_text():
     assert len(o.save_test_lines(mo)[0].split()) == 12
     sites = o.called_sites(mo)
     assert len(sites) <= mo["topN"]
+
+
+def test_meanstd_lines_format():
+    """myDetect.py:540-545: 0-based position, np.std with ddof=0, three decimals."""
+    mo = o.default_moptions(mstd=1, MinCoverage=3)
+    mo["ds2"] = ["a", "b"]
+    mo["a"] = {"norm_mean": {("chr1", "+"): {4: [0.1, 0.2, 0.4], 5: [1.0, 1.0, 1.0]}}, "base": {("chr1", "+"): {4: "A", 5: "C"}}}
+    mo["b"] = {"norm_mean": {("chr1", "+"): {4: [0.5, 0.7, 0.9], 5: [2.0, 2.5, 3.0]}}, "base": {("chr1", "+"): {4: "A", 5: "C"}}}
+    o.mfilter_coverage(mo)
+    o.mtest2(mo, strict=False)
+    lines = o.save_meanstd_lines(mo)
+    assert lines[0] == "chr1 + 4 A 0.233 0.125 0.700 0.163\n"
+    assert lines[1] == "chr1 + 5 C 1.000 0.000 2.500 0.408\n"
