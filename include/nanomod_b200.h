@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define NM_VERSION 100 /* 0.1.0 */
+#define NM_VERSION 110 /* 0.1.1: nm_table.moments, nm_rank_*, down-sampling fields */
 
 /* status codes (0 = ok).  nm_last_error(h) gives the text of the most recent failure. */
 enum {
@@ -38,6 +38,8 @@ enum { NM_COMBINE_NONE = 0, NM_COMBINE_FISHER = 1, NM_COMBINE_STOUFFER = 2 };
 #define NM_MAX_NB 32          /* largest neighborPvalues the combine kernel accepts */
 #define NM_LANE_TIER_MAX 128  /* coverage per group handled by the lane-per-position tier */
 #define NM_DEEP_TIER_MAX_POOLED 49152 /* pow2(n0)+pow2(n1) cap of the block-per-position tier */
+#define NM_DS_MAX_READS 256    /* reads per group a down-sampled position may have */
+#define NM_DS_MAX_TIMES 1024   /* largest `downsampling` */
 
 /* Options that reach the device (subset of `moptions`, read at myDetect.py:301-414).
  * Names follow NanoMod.py:354-359. */
@@ -49,6 +51,11 @@ typedef struct nm_params {
   int32_t want_u;        /* also compute mannwhitneyu (myDetect.py:331)                        */
   int32_t want_t;        /* also compute Welch ttest_ind (myDetect.py:335)                     */
   int32_t reserved;
+  /* Down-sampling branch of getKStest (myDetect.py:339-361), active for positions of a segment
+   * with nm_pileup.seg_cov > 0 where a group has more reads than that: */
+  int32_t ds_times;      /* downsampling          (default 100; <= NM_DS_MAX_TIMES)            */
+  int32_t ds_index;      /* int(downsampling * downsampling_quantile), 0 <= . < ds_times       */
+  uint64_t ds_seed;      /* seed of the library's counter-based stream (nm_downsample.cu)      */
 } nm_params;
 
 /* CSR pileup over n_pos candidate positions (the reference's
@@ -66,6 +73,10 @@ typedef struct nm_pileup {
   const int32_t* pos;  /* [n_pos] 0-based reference coordinate                     */
   const int32_t* seg;  /* [n_pos] id of the (chrom,strand) the position belongs to */
   int64_t n_pos;
+  /* optional: per segment id, the down-sampling coverage (moptions['coverages'][0 if strand is
+   * '+' else 1], myDetect.py:339); NULL or all <= 0 = no down-sampling */
+  const int32_t* seg_cov; /* [n_seg] */
+  int64_t n_seg;
 } nm_pileup;
 
 /* Per-row outputs (SoA), each with capacity n_pos.  Row r is the r-th candidate that passes

@@ -16,6 +16,8 @@ NM_OK = 0
 NM_COMBINE_NONE, NM_COMBINE_FISHER, NM_COMBINE_STOUFFER = 0, 1, 2
 NM_MAX_NB = 32
 NM_LANE_TIER_MAX = 128
+NM_DS_MAX_READS = 256
+NM_DS_MAX_TIMES = 1024
 
 ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: "NM_ERR_OOM",
                5: "NM_ERR_TOO_DEEP", 6: "NM_ERR_NO_DEVICE"}
@@ -35,13 +37,14 @@ class NmError(RuntimeError):
 class nm_params(C.Structure):
     _fields_ = [("min_coverage", C.c_int32), ("nb", C.c_int32), ("weights_dif", C.c_double),
                 ("combine", C.c_int32), ("want_u", C.c_int32), ("want_t", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("ds_times", C.c_int32), ("ds_index", C.c_int32),
+                ("ds_seed", C.c_uint64)]
 
 
 class nm_pileup(C.Structure):
     _fields_ = [("vals0", C.c_void_p), ("off0", C.c_void_p), ("vals1", C.c_void_p),
                 ("off1", C.c_void_p), ("pos", C.c_void_p), ("seg", C.c_void_p),
-                ("n_pos", C.c_int64)]
+                ("n_pos", C.c_int64), ("seg_cov", C.c_void_p), ("n_seg", C.c_int64)]
 
 
 TABLE_FIELDS = ["row_pos_index", "n0", "n1", "ks_dnum", "ks_d", "ks_p", "two_u", "u_stat", "u_p",

@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include "nm_device.cuh"
+#include "nm_downsample.cuh"
 #include "nm_rank.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -291,7 +292,7 @@ struct nm_handle {
   nm_summary* h_sum;  // pinned
   nm_buf d_block_count, d_deep_rows, d_acc_r2, d_acc_tie, d_acc_mom;
   // staging for nm_detect_host
-  nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg;
+  nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg, d_seg_cov;
   nm_buf d_out[17];
   nm_buf d_rank, d_rank_keys[3], d_rank_order;  // nm_rank_*: scratch, staged key columns, result
   int64_t launches;
@@ -408,7 +409,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
-                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_rank_keys[0],
+                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_rank_keys[0],
                     &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -434,6 +435,10 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   if (p->combine & ~(NM_COMBINE_FISHER | NM_COMBINE_STOUFFER))
     return nm_fail(h, NM_ERR_BAD_PARAM, "unknown combine mask %d", p->combine);
   if (!(p->weights_dif >= 1.0)) eff->weights_dif = 1.0;  // NanoMod.py:77-78
+  if (p->ds_times < 0 || p->ds_times > NM_DS_MAX_TIMES)
+    return nm_fail(h, NM_ERR_BAD_PARAM, "downsampling (%d) must be in [0, %d]", p->ds_times, NM_DS_MAX_TIMES);
+  if (p->ds_times > 0 && (p->ds_index < 0 || p->ds_index >= p->ds_times))
+    return nm_fail(h, NM_ERR_BAD_PARAM, "downsampling index (%d) outside [0, %d)", p->ds_index, p->ds_times);
   return NM_OK;
 }
 
@@ -500,6 +505,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   if (want_f && (!tb->fisher_stat || !tb->fisher_p)) return nm_fail(h, NM_ERR_BAD_ARG, "fisher outputs missing");
   if (want_s && (!tb->stouffer_stat || !tb->stouffer_p)) return nm_fail(h, NM_ERR_BAD_ARG, "stouffer outputs missing");
 
+  const bool ds_on = pl->seg_cov != nullptr && pl->n_seg > 0 && prm.ds_times > 0;
   NM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int64_t n_pos = pl->n_pos;
@@ -566,6 +572,17 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
   if (rc != NM_OK) return rc;
 
+  // ---- down-sampling branch (myDetect.py:345-361): replaces the KS result of deep positions
+  if (ds_on) {
+    NM_CUDA(h, cudaMemsetAsync(&h->d_sum->ds_cursor, 0, 2 * sizeof(int), st));  // cursor + too_deep
+    const cudaError_t e = (cudaError_t)nm_launch_downsample(ka, pl->pos, pl->seg, pl->seg_cov, prm.ds_times, prm.ds_index,
+                                                           prm.ds_seed, &h->d_sum->ds_cursor, &h->d_sum->ds_too_deep,
+                                                           h->sm_count, st);
+    if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_downsample_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+    NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
+  }
+
   // ---- neighbour combination
   if (want_f || want_s) {
     nm_comb_args ca;
@@ -582,6 +599,8 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   }
   NM_CUDA(h, cudaEventRecord(h->ev[4], st));
   NM_CUDA(h, cudaStreamSynchronize(st));
+  if (ds_on && h->h_sum->ds_too_deep)
+    return nm_fail(h, NM_ERR_TOO_DEEP, "down-sampling supports at most %d reads per group", NM_DS_MAX_READS);
   {
     float ms = 0.f;
     // ev[1] is re-recorded after the plan readback, so [0] covers only the plan kernels' span
@@ -637,8 +656,15 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
       dev_ptrs[k] = h->d_out[k].p;
     }
   }
+  const int32_t* d_seg_cov = nullptr;
+  if (pl->seg_cov && pl->n_seg > 0) {
+    if ((rc = nm_reserve(h, &h->d_seg_cov, sizeof(int32_t) * (size_t)pl->n_seg)) != NM_OK) return rc;
+    NM_CUDA(h, cudaMemcpyAsync(h->d_seg_cov.p, pl->seg_cov, sizeof(int32_t) * (size_t)pl->n_seg, cudaMemcpyHostToDevice, st));
+    d_seg_cov = (const int32_t*)h->d_seg_cov.p;
+  }
   nm_pileup dpl = {(const float*)h->d_vals0.p, (const int64_t*)h->d_off0.p, (const float*)h->d_vals1.p,
-                   (const int64_t*)h->d_off1.p, (const int32_t*)h->d_pos.p, (const int32_t*)h->d_seg.p, n};
+                   (const int64_t*)h->d_off1.p, (const int32_t*)h->d_pos.p, (const int32_t*)h->d_seg.p, n,
+                   d_seg_cov, d_seg_cov ? pl->n_seg : 0};
   nm_table dtb = {(int32_t*)dev_ptrs[0], (int32_t*)dev_ptrs[1], (int32_t*)dev_ptrs[2], (int32_t*)dev_ptrs[3],
                   (double*)dev_ptrs[4], (double*)dev_ptrs[5], (int64_t*)dev_ptrs[6], (double*)dev_ptrs[7],
                   (double*)dev_ptrs[8], (double*)dev_ptrs[9], (double*)dev_ptrs[10], (double*)dev_ptrs[11],

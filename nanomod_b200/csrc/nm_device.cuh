@@ -85,6 +85,8 @@ struct nm_summary {
   int max_deep_p2;  // max over deep rows of pow2ceil(n0)+pow2ceil(n1)
   int deep_cursor;
   int tile_cursor;  // lane-tier work queue (tiles beyond the first wave)
+  int ds_cursor;    // down-sampling work queue (rows, in chunks of 32)
+  int ds_too_deep;  // set by nm_downsample_kernel: a qualifying row has more than NM_DS_MAX_READS reads
   int pad;
 };
 

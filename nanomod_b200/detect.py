@@ -50,6 +50,9 @@ class DetectOptions:
     downsampling_quantile: float = 0.25
     downsampling: int = 100
     coverages: str = "0-0"
+    # not a reference option: seed of the counter-based stream the down-sampling branch draws from
+    # (the reference uses numpy's unseeded global generator, myDetect.py:351)
+    seed: int = 20190131
     # not reference options: which of the reference's three per-position tests to compute.
     # The reference always computes all three (myDetect.py:331-341).
     want_u: bool = True
@@ -82,13 +85,29 @@ class DetectOptions:
             self.percentile = 0.0
         if self.percentile >= 1:
             self.percentile = 0.99
-        cov = [int(x) for x in str(self.coverages).split("-")]
-        if any(c > 0 for c in cov):
-            err += "\n\tdown-sampling (--coverages %s) is not supported by the GPU path yet" % self.coverages
+        if any(c > 0 for c in self.coverage_pair()):
+            if not 1 <= int(self.downsampling) <= _lib.NM_DS_MAX_TIMES:
+                err += "\n\tdownsampling (%d) must be in [1, %d]" % (self.downsampling, _lib.NM_DS_MAX_TIMES)
+            elif not 0 <= int(self.downsampling * self.downsampling_quantile) < int(self.downsampling):
+                err += "\n\tdownsampling_quantile (%s) must be in [0, 1)" % self.downsampling_quantile
         if self.RegionRankbyST != 0:
             err += "\n\tRegionRankbyST=1 is not supported by the GPU path yet"
         if err:
             raise OptionError("Please provide correct parameters" + err)
+
+    def coverage_pair(self) -> Tuple[int, int]:
+        """moptions['coverages'] = [cov of '+' strands, cov of '-' strands] (NanoMod.py:174-176)."""
+        cov = [int(x) for x in str(self.coverages).split("-")]
+        if len(cov) == 1:
+            cov = [cov[0], cov[0]]
+        return cov[0], cov[1]
+
+    def seg_cov(self, seg_names) -> Optional[np.ndarray]:
+        """Per-segment down-sampling coverage (myDetect.py:339), None when it is off."""
+        cp, cm = self.coverage_pair()
+        if cp <= 0 and cm <= 0:
+            return None
+        return np.array([cp if sk[1] == "+" else cm for sk in seg_names], dtype=np.int32)
 
     def combine_mask(self) -> int:
         if self.both_combinations:
@@ -98,14 +117,16 @@ class DetectOptions:
 
     def to_params(self) -> _lib.nm_params:
         return _lib.nm_params(int(self.MinCoverage), int(self.neighborPvalues), float(self.WeightsDif),
-                              int(self.combine_mask()), int(bool(self.want_u)), int(bool(self.want_t)), 0)
+                              int(self.combine_mask()), int(bool(self.want_u)), int(bool(self.want_t)), 0,
+                              int(self.downsampling), int(self.downsampling * self.downsampling_quantile),
+                              int(self.seed))
 
     @classmethod
     def from_moptions(cls, moptions: Dict) -> "DetectOptions":
         o = cls()
         for k in ("outLevel", "FileID", "outFolder", "MinCoverage", "topN", "neighborPvalues",
                   "WeightsDif", "testMethod", "rankUse", "SaveTest", "RegionRankbyST", "percentile",
-                  "WindOvlp", "NA", "mstd"):
+                  "WindOvlp", "NA", "mstd", "downsampling", "downsampling_quantile", "seed"):
             if k in moptions:
                 setattr(o, k, moptions[k])
         if "window" in moptions:  # moptions stores the half window
@@ -342,8 +363,11 @@ class Detector:
         if out is None:
             out = {c: np.empty(_col_shape(c, n), dtype=_lib.TABLE_DTYPES[c]) for c in cols}
         tb = _lib.nm_table(**{c: out[c].ctypes.data for c in cols})
+        seg_cov = opt.seg_cov(pileup.seg_names)
         pl = _lib.nm_pileup(pileup.vals0.ctypes.data, pileup.off0.ctypes.data, pileup.vals1.ctypes.data,
-                            pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n)
+                            pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n,
+                            None if seg_cov is None else seg_cov.ctypes.data,
+                            0 if seg_cov is None else len(seg_cov))
         n_rows = self.handle.detect_host(pl, opt.to_params(), tb)
         res = {c: out[c][:n_rows] for c in cols}
         if n_rows == n:  # nothing filtered: rows are the candidates themselves
@@ -393,8 +417,11 @@ class Detector:
         import torch
         cols = _wanted_columns(options)
         tb = _lib.nm_table(**{c: out[c].data_ptr() for c in cols})
+        seg_cov = getattr(dev, "seg_cov", None)
         pl = _lib.nm_pileup(dev.vals0.data_ptr(), dev.off0.data_ptr(), dev.vals1.data_ptr(),
-                            dev.off1.data_ptr(), dev.pos.data_ptr(), dev.seg.data_ptr(), dev.n_pos)
+                            dev.off1.data_ptr(), dev.pos.data_ptr(), dev.seg.data_ptr(), dev.n_pos,
+                            None if seg_cov is None else seg_cov.data_ptr(),
+                            0 if seg_cov is None else int(seg_cov.numel()))
         if stream is None:
             stream = torch.cuda.current_stream(dev.vals0.device).cuda_stream
         return self.handle.detect_device(pl, options.to_params(), tb, stream)
@@ -410,6 +437,7 @@ class DevicePileup:
     pos: "object"
     seg: "object"
     n_pos: int
+    seg_cov: "object" = None  # optional int32 CUDA tensor [n_seg]: down-sampling coverage per segment
 
     @classmethod
     def from_host(cls, p: Pileup, device) -> "DevicePileup":

@@ -6,8 +6,9 @@ Same function names, same ``moptions`` keys read and written, same table text --
 per-position tests and the neighbour combination run on the GPU.  Differences, all deliberate:
   * a position whose pooled values are all identical does not abort the run (scipy-1.2.1
     ``mannwhitneyu`` raises ValueError there, uncaught at :331): its U p-value is NaN;
-  * the down-sampling branch (:345-361) and RegionRankbyST=1 (:463-515) are not implemented and
-    raise ``OptionError``;
+  * the down-sampling branch (:345-361) draws from the library's own seeded counter-based
+    stream (the reference uses numpy's unseeded global generator), ``moptions['seed']``;
+  * RegionRankbyST=1 (:463-515) is not implemented and raises ``OptionError``;
   * ``moptions['_detector']`` may hold a ``Detector`` to reuse (else one is made on device 0).
 """
 from __future__ import annotations

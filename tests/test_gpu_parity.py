@@ -332,6 +332,71 @@ def test_mstd_moments_and_meanstd_file(det, tmp_path):
     assert open(str(tmp_path) + "/ms_meanstd.cvs").readlines() == o.save_meanstd_lines(ref)
 
 
+@pytest.mark.parametrize("coverages,times,quantile", [("20-30", 100, 0.25), ("25", 37, 0.5), ("0-12", 64, 0.0)])
+def test_downsampling_branch(det, coverages, times, quantile):
+    """getKStest's down-sampling branch (myDetect.py:345-361) against the scalar oracle, which
+    restates the library's seeded resampling stream: bit-exact KS numerators, p within 1e-6,
+    U / t untouched, combination built on the down-sampled p-values; lane- and deep-tier rows."""
+    rng = np.random.default_rng(77)
+    L = 240
+    c0 = rng.integers(6, 70, L).astype(np.int64)
+    c1 = rng.integers(6, 70, L).astype(np.int64)
+    c0[5], c1[5] = 200, 40
+    c0[6], c1[6] = 256, 256
+    c0[100], c1[100] = 19, 140
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    shift = np.where(np.arange(L) % 40 == 7, 1.0, 0.0)
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0, 1, off1[-1]) + np.repeat(shift, c1), 2).astype(np.float32)
+    seg = (np.arange(L) >= L // 2).astype(np.int32)
+    pos = np.concatenate([np.arange(L // 2), np.arange(L - L // 2)]).astype(np.int32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, pos, seg, seg_names=[("chrA", "+"), ("chrA", "-")])
+    opt = nm.DetectOptions(neighborPvalues=2, coverages=coverages, downsampling=times,
+                           downsampling_quantile=quantile, seed=424242)
+    t = det.detect(p, opt)
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(neighborPvalues=2, coverages=list(opt.coverage_pair()), downsampling=times,
+                            downsampling_quantile=quantile, seed=424242)
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    o.mfilter_coverage(mo)
+    o.mtest2(mo, strict=False)
+    assert len(t) == len(mo["sign_test"]) == L
+    n_ds = 0
+    for r, (key, tests) in enumerate(mo["sign_test"]):
+        cov = opt.coverage_pair()[0 if key[1] == "+" else 1]
+        m0 = min(int(t.n0[r]), cov) if cov > 0 else int(t.n0[r])
+        m1 = min(int(t.n1[r]), cov) if cov > 0 else int(t.n1[r])
+        n_ds += (m0, m1) != (int(t.n0[r]), int(t.n1[r]))
+        (u, pu), (tt, pt), (d, pks), (z, pz) = tests
+        assert t.ks_dnum[r] == int(round(d * m0 * m1)), (r, key)
+        assert abs(t.ks_d[r] - d) <= 1e-12 and abs(t.ks_p[r] - pks) <= RTOL * pks
+        assert abs(t.u_p[r] - pu) <= RTOL * pu and abs(t.t_p[r] - pt) <= RTOL * pt
+        assert (z == t.stouffer_stat[r]) or abs(t.stouffer_stat[r] - z) <= RTOL * abs(z) + 1e-12
+        assert abs(t.stouffer_p[r] - pz) <= RTOL * pz
+    assert n_ds > 50
+    # same seed, same answer; another seed, another stream
+    t2 = det.detect(p, opt)
+    assert np.array_equal(t2.ks_dnum, t.ks_dnum)
+    opt3 = nm.DetectOptions(neighborPvalues=2, coverages=coverages, downsampling=times,
+                            downsampling_quantile=quantile, seed=7)
+    assert not np.array_equal(det.detect(p, opt3).ks_dnum, t.ks_dnum)
+    # shards see the same stream: it is keyed on (segment, position), not on the row index
+    lo = 60
+    ts = det.detect(p.slice_rows(lo, L), opt)
+    assert np.array_equal(ts.ks_dnum, t.ks_dnum[lo:])
+
+
+def test_downsampling_limits(det):
+    p = nm.synthetic_pileup(50, 300, 20)
+    with pytest.raises(nm.NmError) as e:
+        det.detect(p, nm.DetectOptions(coverages="50"))
+    assert e.value.code == 5  # NM_ERR_TOO_DEEP: more than 256 reads in a down-sampled group
+    with pytest.raises(nm.OptionError):
+        det.detect(p, nm.DetectOptions(coverages="50", downsampling=5000))
+
+
 @pytest.mark.parametrize("rank_use", ["pv", "st"])
 @pytest.mark.parametrize("method", ["stouffer", "fisher", "ks"])
 def test_device_ranking_equals_host_ranking(det, rank_use, method):

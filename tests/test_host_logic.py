@@ -107,8 +107,16 @@ def test_option_validation_messages():
     d = nm.DetectOptions(WeightsDif=0.5)
     d.validate()
     assert d.WeightsDif == 1.0  # NanoMod.py:77-78
-    with pytest.raises(nm.OptionError, match="down-sampling"):
-        nm.DetectOptions(coverages="50-50").validate()
+    nm.DetectOptions(coverages="50-50").validate()  # the down-sampling branch is supported
+    assert nm.DetectOptions(coverages="40").coverage_pair() == (40, 40)  # NanoMod.py:174-176
+    assert list(nm.DetectOptions(coverages="0-12").seg_cov([("c", "+"), ("c", "-"), ("d", "+")])) == [0, 12, 0]
+    assert nm.DetectOptions().seg_cov([("c", "+")]) is None
+    with pytest.raises(nm.OptionError, match="downsampling"):
+        nm.DetectOptions(coverages="50", downsampling=0).validate()
+    with pytest.raises(nm.OptionError, match="downsampling_quantile"):
+        nm.DetectOptions(coverages="50", downsampling_quantile=1.0).validate()
+    p = nm.DetectOptions(coverages="50", downsampling=100, downsampling_quantile=0.25, seed=9).to_params()
+    assert (p.ds_times, p.ds_index, p.ds_seed) == (100, 25, 9)
 
 
 @pytest.mark.parametrize("method,rank", [("stouffer", "pv"), ("fisher", "pv"), ("ks", "pv"), ("stouffer", "st")])
@@ -159,7 +167,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.nm_version.restype = ctypes.c_int
-    assert lib.nm_version() == 100
+    assert lib.nm_version() == 110
     assert _lib.load().nm_padded_len(5) == _lib.padded_len(5) == 12
 
 
@@ -175,7 +183,7 @@ def test_struct_layouts_match_header(tmp_path):
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(_lib.nm_params), ctypes.sizeof(_lib.nm_pileup), ctypes.sizeof(_lib.nm_table),
                    _lib.nm_table.flags.offset, _lib.nm_table.moments.offset]
-    assert got[:3] == [32, 56, 17 * 8]
+    assert got[:3] == [48, 72, 17 * 8]
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -155,3 +155,49 @@ def test_meanstd_lines_format():
     lines = o.save_meanstd_lines(mo)
     assert lines[0] == "chr1 + 4 A 0.233 0.125 0.700 0.163\n"
     assert lines[1] == "chr1 + 5 C 1.000 0.000 2.500 0.408\n"
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = o.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+    idx = o.downsample_indices(20190131, 3, 1234, 7, 1, 1000, 37)
+    assert idx.min() >= 0 and idx.max() < 37 and len(np.unique(idx)) == 37
+
+
+def test_downsampling_branch_matches_reference_procedure_statistically():
+    """The reference resamples with np.random.choice on an unseeded generator (myDetect.py:345-361).
+    Its procedure, run literally with a seeded numpy generator, and the oracle's branch (the
+    library's Philox stream) must give the same DISTRIBUTION of the selected p-value."""
+    rs = np.random.RandomState(3)
+    a = np.round(rs.normal(0, 1, 80), 3)
+    b = np.round(rs.normal(0.6, 1, 70), 3)
+    cov, times, q = 25, 100, 0.25
+
+    def literal(rng):
+        p_array = np.zeros(times)
+        for i in range(times):
+            _st, pks, _ = o.ks_2samp_legacy(rng.choice(a, cov), rng.choice(b, cov))
+            p_array[i] = o.m_min_float(pks)
+        return p_array[np.argsort(p_array)[int(times * q)]]
+
+    ref = np.array([literal(np.random.RandomState(1000 + k)) for k in range(120)])
+    mo = o.default_moptions(coverages=[cov, cov], downsampling=times, downsampling_quantile=q)
+    ours = []
+    for k in range(120):
+        mo["seed"] = 555 + k
+        mo["_ds_site"] = (0, k)
+        ours.append(o.getKStest(mo, a, b, "+", strict=False)[2][1])
+    ours = np.array(ours)
+    assert st.ks_2samp(np.log(ref), np.log(ours)).pvalue > 1e-3
+    assert abs(np.median(np.log(ref)) - np.median(np.log(ours))) < 0.35
+    # U and t are computed on the full groups (myDetect.py:331-337)
+    full = o.getKStest(o.default_moptions(), a, b, "+", strict=False)
+    mo["_ds_site"] = (0, 0)
+    ds = o.getKStest(mo, a, b, "+", strict=False)
+    assert ds[0] == full[0] and ds[1] == full[1] and ds[2] != full[2]
