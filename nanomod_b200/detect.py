@@ -90,8 +90,6 @@ class DetectOptions:
                 err += "\n\tdownsampling (%d) must be in [1, %d]" % (self.downsampling, _lib.NM_DS_MAX_TIMES)
             elif not 0 <= int(self.downsampling * self.downsampling_quantile) < int(self.downsampling):
                 err += "\n\tdownsampling_quantile (%s) must be in [0, 1)" % self.downsampling_quantile
-        if self.RegionRankbyST != 0:
-            err += "\n\tRegionRankbyST=1 is not supported by the GPU path yet"
         if err:
             raise OptionError("Please provide correct parameters" + err)
 
@@ -286,6 +284,77 @@ class SignTestTable:
         if not use_p:
             order = order[::-1]
         return order
+
+    # ---- region ranking (myDetect.py:463-515, RegionRankbyST == 1) --------------------------
+    def region_ranked(self) -> np.ndarray:
+        """Row indices of the window centres in the order of ``moptions['sorted_sign_test']`` when
+        RegionRankbyST is 1: windows of half-width w = half_window + 1 (the reference increments
+        moptions['window'], :465) centred every w positions (every position with WindOvlp=1) that
+        are fully covered inside one (chrom, strand); each window is scored by the percentile-th
+        smallest value of its (optionally base-filtered, --NA) combined p-values or statistics;
+        ties by the distance of the window's minimum from the centre; with WindOvlp=1 a window
+        closer than w to a better-ranked one is dropped (:503-511)."""
+        o = self.options
+        w = o.half_window + 1
+        move = 1 if o.WindOvlp == 1 else w
+        use_p = o.rankUse == "pv"
+        comb = self.comb()
+        val = (comb[1] if use_p else comb[0]) if comb is not None else (self.ks_p if use_p else self.ks_d)
+        val = np.asarray(val, dtype=np.float64)
+        na = ord(o.NA) if (o.NA is not None and len(o.NA) > 0) else None
+        n = len(self)
+        cent, score, dist = [], [], []
+        bounds = np.flatnonzero(np.diff(self.seg)) + 1
+        for lo, hi in zip(np.append(0, bounds), np.append(bounds, n)):
+            pos = self.pos[lo:hi].astype(np.int64)
+            if hi - lo < 2 * w + 1:
+                continue
+            pmin, pmax = pos[0], pos[-1]
+            r = np.arange(w, hi - lo - w)  # rows that have w rows on either side
+            ok = (pos[r + w] - pos[r - w] == 2 * w) & (pos[r + w] < pmax) & ((pos[r] - pmin) % move == 0) & (pos[r] < pmax)
+            r = r[ok]
+            if len(r) == 0:
+                continue
+            win = r[:, None] + np.arange(-w, w + 1)[None, :]
+            v = val[lo:hi][win]
+            keep = np.ones_like(v, dtype=bool) if na is None else (self.base[lo:hi][win] == na)
+            cnt = keep.sum(axis=1)
+            vm = np.where(keep, v, np.inf)
+            first_min = np.argmin(vm, axis=1)  # first occurrence, window order
+            srt = np.sort(vm, axis=1)
+            good = cnt > 5
+            k = (o.percentile * (cnt - 1) + 0.5).astype(np.int64)
+            k = np.clip(k, 0, 2 * w)
+            sc = srt[np.arange(len(r)), k]
+            before = np.cumsum(keep, axis=1) - keep  # filtered elements before each window slot
+            ds = np.abs(w - before[np.arange(len(r)), first_min])
+            cent.append((r + lo)[good])
+            score.append(sc[good])
+            dist.append(ds[good])
+        if not cent:
+            return np.zeros(0, dtype=np.int64)
+        cent, score, dist = np.concatenate(cent), np.concatenate(score), np.concatenate(dist)
+        order = cent[np.lexsort((dist, score))]
+        if o.WindOvlp != 1:
+            return order
+        out = []
+        taken: Dict[int, np.ndarray] = {}
+        for r in order:
+            sg, ps = int(self.seg[r]), int(self.pos[r])
+            m = taken.get(sg)
+            if m is None:
+                sel = self.seg == sg
+                m = taken[sg] = np.zeros(int(self.pos[sel].max()) + 2 * w + 2, dtype=bool)
+            a, b = max(0, ps - w + 1), ps + w
+            if m[a:b].any():
+                continue
+            m[ps] = True
+            out.append(r)
+        return np.asarray(out, dtype=np.int64)
+
+    def sorted_rows(self) -> np.ndarray:
+        """Row order of ``moptions['sorted_sign_test']`` for the table's options."""
+        return self.region_ranked() if self.options.RegionRankbyST != 0 else self.ranked()
 
     # ---- called sites (mboxplot :279-297 + plot1 :153-164) ---------------------------------
     def called_sites(self) -> List[Tuple[str, str, int]]:

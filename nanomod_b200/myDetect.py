@@ -8,7 +8,6 @@ per-position tests and the neighbour combination run on the GPU.  Differences, a
     ``mannwhitneyu`` raises ValueError there, uncaught at :331): its U p-value is NaN;
   * the down-sampling branch (:345-361) draws from the library's own seeded counter-based
     stream (the reference uses numpy's unseeded global generator), ``moptions['seed']``;
-  * RegionRankbyST=1 (:463-515) is not implemented and raises ``OptionError``;
   * ``moptions['_detector']`` may hold a ``Detector`` to reuse (else one is made on device 0).
 """
 from __future__ import annotations
@@ -59,7 +58,7 @@ def save_test(moptions: Dict) -> None:
 
 
 def mtest2(moptions: Dict) -> None:
-    """myDetect.py:416-462 (RegionRankbyST == 0): fills ``moptions['sign_test']`` and
+    """myDetect.py:416-520: fills ``moptions['sign_test']`` and
     ``moptions['sorted_sign_test']`` and writes the table when SaveTest is set."""
     table = _run(moptions)
     moptions["_sign_test_table"] = table
@@ -69,7 +68,11 @@ def mtest2(moptions: Dict) -> None:
     if moptions.get("SaveTest", 0):
         save_test(moptions)
     st = moptions["sign_test"]
-    moptions["sorted_sign_test"] = [st[int(r)] for r in _detector(moptions).rank(table)]
+    if moptions.get("RegionRankbyST", 0) == 0:
+        moptions["sorted_sign_test"] = [st[int(r)] for r in _detector(moptions).rank(table)]
+    else:  # :463-515; the reference widens moptions['window'] by one as a side effect (:465)
+        moptions["sorted_sign_test"] = [st[int(r)] for r in table.region_ranked()]
+        moptions["window"] = moptions["window"] + 1
 
 
 def getKStest(moptions: Dict, a, b, m_str: str) -> List:

@@ -29,11 +29,11 @@ def oracle_table(p, opt):
                          stouffer_stat=res.get("stouffer_stat"), stouffer_p=res.get("stouffer_p"))
 
 
-def oracle_moptions(p, opt):
+def oracle_moptions(p, opt, **over):
     d0, d1 = p.to_dicts()
     mo = o.default_moptions(MinCoverage=opt.MinCoverage, neighborPvalues=opt.neighborPvalues,
                             WeightsDif=opt.WeightsDif, testMethod=opt.testMethod, rankUse=opt.rankUse,
-                            topN=opt.topN, window=opt.half_window)
+                            topN=opt.topN, window=opt.half_window, **over)
     mo["ds2"] = ["g0", "g1"]
     mo["g0"], mo["g1"] = d0, d1
     o.mfilter_coverage(mo)
@@ -202,3 +202,98 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+# ---------------------------------------------------------------------------------------------
+# host packer against the oracle's literal restatement of mReadSignalBase
+# ---------------------------------------------------------------------------------------------
+def _synthetic_reads(rng, n_reads, chroms=("chrA", "chrB"), lo=80, hi=400, span=3000):
+    from nanomod_b200.packer import ReadRecord
+    reads = []
+    for _ in range(n_reads):
+        n = int(rng.integers(lo, hi))
+        reads.append(ReadRecord(str(rng.choice(chroms)), str(rng.choice(["+", "-"])), int(rng.integers(0, span)),
+                                np.round(rng.normal(0, 1, n), 3), rng.choice(np.frombuffer(b"ACGT", np.uint8), n)))
+    return reads
+
+
+def _oracle_pileup(reads0, reads1, **mo_over):
+    mo = o.default_moptions(**dict({"min_lr": 100, "min_lr_nb": 0}, **mo_over))
+    mo["ds2"] = ["g0", "g1"]
+    for name, reads in (("g0", reads0), ("g1", reads1)):
+        mo[name] = {"norm_mean": {}, "base": {}}
+        mo["cur_wrkBase"] = name
+        for r in reads:
+            o.mReadSignalBase_events(mo, r.chrom, r.start, r.strand, r.norm_mean, [chr(c) for c in r.base])
+    return nm.Pileup.from_dicts(mo["g0"], mo["g1"])
+
+
+@pytest.mark.parametrize("mode", ["plain", "region", "pos2_chr", "length_band"])
+def test_packer_matches_reference_read_loop(mode):
+    from nanomod_b200.packer import ReadFilter, pack_reads
+    rng = np.random.default_rng(11)
+    reads0, reads1 = _synthetic_reads(rng, 120), _synthetic_reads(rng, 110)
+    over, flt = {}, ReadFilter(min_lr=100)
+    if mode == "region":
+        over = {"start_pos": 1500, "end_pos": 1520}
+        flt = ReadFilter(min_lr=100, start_pos=1500, end_pos=1520)
+    elif mode == "pos2_chr":
+        over = {"Chr": "chrB", "Pos": 900, "Pos2": 1400}
+        flt = ReadFilter(min_lr=100, Chr="chrB", Pos=900, Pos2=1400)
+    elif mode == "length_band":
+        for r in reads0[:30] + reads1[:30]:  # reads that start and end near 0 / 8000
+            r.start = int(rng.integers(0, 40))
+            n = int(rng.integers(7975, 8020)) - r.start
+            r.norm_mean = np.round(rng.normal(0, 1, n), 3)
+            r.base = rng.choice(np.frombuffer(b"ACGT", np.uint8), n)
+        over = {"min_lr": 8000, "min_lr_nb": 50}
+        flt = ReadFilter(min_lr=8000, min_lr_nb=50)
+    want = _oracle_pileup(reads0, reads1, **over)
+    assert flt.__dict__ == ReadFilter.from_moptions(dict({"min_lr": 100, "min_lr_nb": 0}, **over)).__dict__
+    got = pack_reads(reads0, reads1, flt)
+    assert got.n_pos == want.n_pos and got.n_pos > 0
+    assert got.seg_names == want.seg_names
+    for f in ("vals0", "off0", "vals1", "off1", "pos", "seg", "base"):
+        a, b = getattr(got, f), getattr(want, f)
+        n = int(got.off0[-1]) if f == "vals0" else int(got.off1[-1]) if f == "vals1" else len(a)
+        assert np.array_equal(a[:n], b[:n]), f
+
+
+def test_packer_npz_roundtrip_and_missing_h5py(tmp_path):
+    from nanomod_b200 import packer
+    rng = np.random.default_rng(2)
+    reads = _synthetic_reads(rng, 9)
+    packer.save_reads_npz(str(tmp_path / "r.npz"), reads)
+    back = packer.load_reads_npz(str(tmp_path / "r.npz"))
+    assert len(back) == 9
+    for a, b in zip(reads, back):
+        assert (a.chrom, a.strand, a.start) == (b.chrom, b.strand, b.start)
+        assert np.array_equal(a.norm_mean, b.norm_mean) and np.array_equal(a.base, b.base)
+    (tmp_path / "d" / "mall").mkdir(parents=True)
+    (tmp_path / "d" / "x").mkdir()
+    for f in ("d/a.fast5", "d/x/b.fast5", "d/mall/skip.fast5", "d/x/c.txt"):
+        (tmp_path / f).write_text("")
+    assert sorted(os.path.basename(f) for f in packer.walk_fast5(str(tmp_path / "d"))) == ["a.fast5", "b.fast5"]
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            packer.read_fast5(str(tmp_path / "d" / "a.fast5"))
+
+
+@pytest.mark.parametrize("ovlp,na,rank,method", [(0, "", "pv", "stouffer"), (1, "", "pv", "stouffer"), (0, "A", "pv", "fisher"),
+                                                 (1, "C", "st", "stouffer"), (0, "", "pv", "ks")])
+def test_region_rank_mode_matches_oracle(ovlp, na, rank, method):
+    """RegionRankbyST=1 (myDetect.py:463-515): windowed percentile ranking, --NA base filter,
+    overlap suppression -- the table's vectorised version against the literal restatement."""
+    p = nm.synthetic_pileup(2500, 9, 9, drop_frac1=0.01, two_strands=True, round_decimals=1)
+    opt = nm.DetectOptions(neighborPvalues=2, testMethod=method, rankUse=rank, RegionRankbyST=1, WindOvlp=ovlp,
+                           NA=na, percentile=0.1, window=25 if na else 9)
+    mo = oracle_moptions(p, opt, RegionRankbyST=1, WindOvlp=ovlp, NA=na, percentile=0.1)
+    assert mo["window"] == opt.half_window + 1
+    t = table_from_sign_test(p, opt, mo)
+    rows = t.region_ranked()
+    got = [(t.seg_names[t.seg[r]][0], t.seg_names[t.seg[r]][1], int(t.pos[r])) for r in rows]
+    want = [(m[0][0], m[0][1], m[0][2]) for m in mo["sorted_sign_test"]]
+    assert len(want) > (5 if na else 20)
+    assert got == want
