@@ -159,7 +159,7 @@ __device__ __forceinline__ double nm_sum4_by_row_class(const double (&s)[4], int
   return __dadd_rn(__dadd_rn(c0, c1), __dadd_rn(c2, c3));
 }
 
-// Welch moments of one row: two-pass, fp64, four accumulators by row index mod 4, read through
+// Welch moments of one row: one pass, fp64, four accumulators by row index mod 4, read through
 // the same aligned 128-bit window as the sort.  A ROLLED loop with explicitly rounded
 // operations: the instruction sequence applied to a row depends only on the row itself (not on
 // its alignment, its tile or the tile's network size), so results are bit-identical however
@@ -169,7 +169,13 @@ __device__ __forceinline__ void nm_lane_moments(const float* region, int base, i
   const int shift = base & 3;
   const float4* raw4 = reinterpret_cast<const float4*>(region + (base - shift));
   const int nq = __reduce_max_sync(0xffffffffu, (shift + n + 3) >> 2);
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  // One pass over the row with the data shifted by its first value K ("shifted data" variance):
+  // sum d and sum d^2 of d = x - K, then mean = K + S/n and var = (SS - S^2/n)/(n-1).  K is a
+  // sample of the row, so the final subtraction cancels at most a few bits; one float->double
+  // conversion per value instead of two (F2F runs at a quarter of the fp64 rate and was the
+  // bottleneck of the two-pass form).
+  const double K = n > 0 ? (double)region[base] : 0.0;
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 2
   for (int q = 0; q < nq; ++q) {
     const float4 v4 = raw4[q];
@@ -177,24 +183,17 @@ __device__ __forceinline__ void nm_lane_moments(const float* region, int base, i
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
-      s[j] = __dadd_rn(s[j], valid ? (double)vv[j] : 0.0);
-    }
-  }
-  const double m = __ddiv_rn(nm_sum4_by_row_class(s, shift), (double)n);
-  double ss[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-  for (int q = 0; q < nq; ++q) {
-    const float4 v4 = raw4[q];
-    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool valid = (unsigned)(4 * q + j - shift) < (unsigned)n;
-      const double d = valid ? __dsub_rn((double)vv[j], m) : 0.0;
+      const double d = valid ? __dsub_rn((double)vv[j], K) : 0.0;
+      s[j] = __dadd_rn(s[j], d);
       ss[j] = __fma_rn(d, d, ss[j]);
     }
   }
-  *mean = m;
-  *var = __ddiv_rn(nm_sum4_by_row_class(ss, shift), (double)(n - 1));
+  const double S = nm_sum4_by_row_class(s, shift), SS = nm_sum4_by_row_class(ss, shift);
+  const double dn = (double)n;
+  const double sn = __ddiv_rn(S, dn);
+  *mean = __dadd_rn(K, sn);
+  const double num = __fma_rn(-S, sn, SS);
+  *var = __ddiv_rn(num > 0.0 ? num : 0.0, (double)(n - 1));
 }
 
 // deep tier: each group is sorted as a power-of-two array of at least NM_DEEP_MIN_P elements
