@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NM_PLAN_THREADS)
 nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1, int64_t n_pos,
               int mincov, int* __restrict__ block_count, nm_summary* __restrict__ sum) {
   const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
-  int cnt = 0, max_lane = 0, n_deep = 0, max_deep = 0;
+  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0;
 #pragma unroll
   for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
     const int64_t p = p0 + k;
@@ -66,6 +66,8 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
         const int64_t m = n0 > n1 ? n0 : n1;
         if (m <= NM_LANE_TIER_MAX) {
           max_lane = max_lane > (int)m ? max_lane : (int)m;
+          const int slack = NM_LANE_TIER_MAX - (int)m;
+          max_slack = max_slack > slack ? max_slack : slack;
         } else {
           ++n_deep;
           const int64_t cap = 1 << 24;
@@ -78,10 +80,12 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
   int total;
   (void)nm_block_excl_scan(cnt, &total);
   max_lane = __reduce_max_sync(0xffffffffu, max_lane);
+  max_slack = __reduce_max_sync(0xffffffffu, max_slack);
   max_deep = __reduce_max_sync(0xffffffffu, max_deep);
   n_deep = __reduce_add_sync(0xffffffffu, n_deep);
   if ((threadIdx.x & 31) == 0) {
     if (max_lane) atomicMax(&sum->max_lane_n, max_lane);
+    if (max_slack) atomicMax(&sum->max_lane_slack, max_slack);
     if (n_deep) {
       atomicAdd(&sum->n_deep, n_deep);
       atomicMax(&sum->max_deep_p2, max_deep);
@@ -294,11 +298,12 @@ struct nm_handle {
   // staging for nm_detect_host
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg, d_seg_cov;
   nm_buf d_out[17];
-  nm_buf d_rank, d_rank_keys[3], d_rank_order;  // nm_rank_*: scratch, staged key columns, result
+  nm_buf d_rank, d_rank_keys[3], d_rank_order;
+  nm_buf d_perm[2], d_class_scratch;  // class binning of the lane tier (nm_class_sort_run)  // nm_rank_*: scratch, staged key columns, result
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int use_pair_tier;   // NANOMOD_B200_PAIR_TIER=1: two lanes per position for long rows (experimental)
-  int use_pair_sync;   // NANOMOD_B200_PAIR_SYNC=0/1: lane tier, warp pairs in lock-step (nm_kargs::pair_sync)
+  int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -384,8 +389,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
   {
     const char* f = getenv("NANOMOD_B200_PAIR_TIER");
     h->use_pair_tier = (f && f[0] == '1') ? 1 : 0;
-    const char* g = getenv("NANOMOD_B200_PAIR_SYNC");
-    h->use_pair_sync = (g && g[0] == '1') ? 1 : 0;
+    const char* g = getenv("NANOMOD_B200_NO_CLASS_SORT");
+    h->no_class_sort = (g && g[0] == '1') ? 1 : 0;
   }
   int rc = NM_OK;
   do {
@@ -409,7 +414,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
-                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_rank_keys[0],
+                    &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
                     &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -442,21 +447,48 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
   return NM_OK;
 }
 
-static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int max_lane_n, int max_deep_p2, int deep_smem, int64_t n_rows, int n_deep, cudaStream_t st) {
+// Lane-tier launches.  perm == NULL: one launch over all rows (deep rows are skipped inside).
+// Otherwise the rows are partitioned by size group and there is one launch per group --
+// <= 64 (the 12-warps/SM instantiation), <= 104 (straight-line networks, 8 warps/SM), <= 128
+// (looped networks, 6 warps/SM) -- each with shared memory sized for its own largest class.
+static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, bool want_m, const nm_summary& sum,
+                           const int32_t* perm, int deep_smem, int64_t n_rows, cudaStream_t st) {
+  const int n_deep = sum.n_deep, max_lane_n = sum.max_lane_n, max_deep_p2 = sum.max_deep_p2;
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
     const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
+    nm_kargs kl = ka;
+    kl.perm = perm;
     // The pair tier (two lanes per position for long rows; KS and Welch t only) is an experiment:
     // it doubles residency and halves the code footprint, but needs 25 % more instructions and
     // measured slower than the lane tier in round 1 (profiles/round1_variants.md).  Off unless
     // NANOMOD_B200_PAIR_TIER=1.
-    const bool pair = h->use_pair_tier && !want_u && max_lane_n > 64 && nm_pair_tier_available();
-    const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(ka, want_m, max_lane_n, sms, st)
-                                             : nm_launch_lane(ka, want_u, want_m, max_lane_n, sms, h->use_pair_sync, st));
-    if (e != cudaSuccess)
-      return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
-                     cudaGetErrorString(e));
-    h->launches++;
+    const bool pair = h->use_pair_tier && !perm && !want_u && max_lane_n > 64 && nm_pair_tier_available();
+    if (pair || !perm) {
+      kl.row_lo = 0;
+      kl.row_hi = n_rows;
+      kl.tile_cursor = &h->d_sum->tile_cursor[0];
+      const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(kl, want_m, max_lane_n, sms, st)
+                                               : nm_launch_lane(kl, want_u, want_m, max_lane_n, sms, st));
+      if (e != cudaSuccess)
+        return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
+                       cudaGetErrorString(e));
+      h->launches++;
+    } else {
+      const int64_t n_lane = n_rows - n_deep;
+      const int64_t cut[4] = {0, sum.n_le64, sum.n_le104, n_lane};
+      const int cap[3] = {64, NM_LANE_FINE_MAX, NM_LANE_TIER_MAX};
+      for (int g = 0; g < 3; ++g) {
+        if (cut[g + 1] <= cut[g]) continue;
+        kl.row_lo = cut[g];
+        kl.row_hi = cut[g + 1];
+        kl.tile_cursor = &h->d_sum->tile_cursor[g];
+        const int max_n = max_lane_n < cap[g] ? max_lane_n : cap[g];
+        const cudaError_t e = (cudaError_t)nm_launch_lane(kl, want_u, want_m, max_n, sms, st);
+        if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
+        h->launches++;
+      }
+    }
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
@@ -549,7 +581,6 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.n_rows = n_rows;
   ka.one = 1;
   ka.mone = -1;
-  ka.tile_cursor = &h->d_sum->tile_cursor;
   ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
@@ -569,7 +600,41 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     ka.acc_mom = (double*)h->d_acc_mom.p;
   }
   const int deep_smem = 16 + (sum.max_deep_p2 + 16) * (int)sizeof(float);
-  rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum.max_lane_n, sum.max_deep_p2, deep_smem, n_rows, sum.n_deep, st);
+  // Mixed coverage.  The lane kernel runs ONE network size per launch (several sizes in flight
+  // thrash the instruction cache), normally that of the call's longest row.  If the rows span
+  // several size groups and one group holds nearly all of them, the others are outliers: split
+  // the call into one launch per group, so that 1 % of deep positions do not make the other 99 %
+  // pay for their network.  (With a broad coverage distribution the groups interleave densely,
+  // tiles stop being contiguous, and staging them row by row costs more than the smaller
+  // networks save: profiles/round1_variants.md.)
+  const int32_t* perm = nullptr;
+  nm_summary sum2 = sum;
+  const int64_t n_lane = n_rows - sum.n_deep;
+  if (!h->no_class_sort && n_lane > 0) {
+    const int cmin = nm_lane_class(NM_LANE_TIER_MAX - sum.max_lane_slack), cmax = nm_lane_class(sum.max_lane_n);
+    const int gmin = cmin <= 64 ? 0 : cmin <= NM_LANE_FINE_MAX ? 1 : 2, gmax = cmax <= 64 ? 0 : cmax <= NM_LANE_FINE_MAX ? 1 : 2;
+    if (gmin != gmax) {
+      if ((rc = nm_reserve(h, &h->d_perm[0], sizeof(int32_t) * (size_t)n_rows)) != NM_OK) return rc;
+      if ((rc = nm_reserve(h, &h->d_perm[1], sizeof(int32_t) * (size_t)n_rows)) != NM_OK) return rc;
+      if ((rc = nm_reserve(h, &h->d_class_scratch, nm_group_sort_scratch_bytes(n_rows))) != NM_OK) return rc;
+      int launches = 0;
+      cudaError_t e = (cudaError_t)nm_group_keys_run(tb->n0, tb->n1, n_rows, (int32_t*)h->d_perm[0].p, h->d_class_scratch.p,
+                                                     h->d_sum, &launches, st);
+      if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "group binning failed: %s", cudaGetErrorString(e));
+      NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
+      NM_CUDA(h, cudaStreamSynchronize(st));
+      sum2 = *h->h_sum;
+      const int64_t g0 = sum2.n_le64, g1 = (int64_t)sum2.n_le104 - sum2.n_le64, g2 = n_lane - sum2.n_le104;
+      const int64_t biggest = g0 > g1 ? (g0 > g2 ? g0 : g2) : (g1 > g2 ? g1 : g2);
+      if (biggest * 8 >= n_lane * 7 && biggest != (gmax == 2 ? g2 : gmax == 1 ? g1 : g0)) {
+        e = (cudaError_t)nm_group_sort_run(n_rows, (int32_t*)h->d_perm[0].p, (int32_t*)h->d_perm[1].p, &perm,
+                                           h->d_class_scratch.p, &launches, st);
+        if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "group binning failed: %s", cudaGetErrorString(e));
+      }
+      h->launches += launches;
+    }
+  }
+  rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum2, perm, deep_smem, n_rows, st);
   if (rc != NM_OK) return rc;
 
   // ---- down-sampling branch (myDetect.py:345-361): replaces the KS result of deep positions

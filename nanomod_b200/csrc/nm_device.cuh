@@ -46,9 +46,21 @@ __device__ __forceinline__ void nm_bulk_g2s(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// Per-thread asynchronous 16-byte copies global -> shared (LDGSTS): the scattered staging path
+// of the lane tier (many small TMA bulk copies have a low issue rate; measured 2x slower).
+__device__ __forceinline__ void nm_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nm_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void nm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void nm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // L2 prefetch of a contiguous global range (no shared memory involved)
 __device__ __forceinline__ void nm_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void nm_prefetch_l2_line(const void* src) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src) : "memory");
 }
 
 __device__ __forceinline__ long long nm_warp_min_ll(long long v) {
@@ -84,9 +96,11 @@ struct nm_summary {
   int n_deep;       // rows with max(n0,n1) > NM_LANE_TIER_MAX
   int max_deep_p2;  // max over deep rows of pow2ceil(n0)+pow2ceil(n1)
   int deep_cursor;
-  int tile_cursor;  // lane-tier work queue (tiles beyond the first wave)
-  int ds_cursor;    // down-sampling work queue (rows, in chunks of 32)
-  int ds_too_deep;  // set by nm_downsample_kernel: a qualifying row has more than NM_DS_MAX_READS reads
+  int tile_cursor[3];   // lane-tier work queues (tiles beyond the first wave), one per launch
+  int ds_cursor;        // down-sampling work queue (rows, in chunks of 32)
+  int ds_too_deep;      // set by nm_downsample_kernel: a qualifying row has more than NM_DS_MAX_READS reads
+  int max_lane_slack;   // max over lane-tier rows of NM_LANE_TIER_MAX - max(n0,n1)  (-> shortest row)
+  int n_le64, n_le104;  // class-binned calls: lane-tier rows whose network class is <= 64 / <= 104
   int pad;
 };
 
@@ -107,11 +121,15 @@ struct nm_kargs {
   const int32_t* row_n0;
   const int32_t* row_n1;
   int64_t n_rows;
+  // lane tier: the launch works on rows perm[row_lo .. row_hi) (perm == NULL: rows row_lo .. row_hi
+  // themselves).  Calls with mixed coverage sort the rows by network class first (nm_class_sort)
+  // and launch once per class group, so that every tile is homogeneous.
+  const int32_t* perm;
+  int64_t row_lo, row_hi;
   int region_floats;  // floats per group region in shared memory (lane tier)
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int* tile_cursor;   // device counter, zero at launch
-  int pair_sync;      // lane tier: warps (w, w+4) of an 8-warp CTA step through tiles together
   // rank sums / moments of the lane and pair tiers; their fp64 tails (normal and Student-t
   // tails: a lot of cold fp64 code) run afterwards in nm_tails_kernel, not inside the sort loop
   int* acc_r2;        // want_u: 2 * rank sum of group 0
@@ -209,8 +227,7 @@ int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, in
                    cudaStream_t st);
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
-int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, int pair_sync,
-                   cudaStream_t st);
+int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st);
 // host-side launcher of the pair tier (nm_pair_kernel.cu): KS (+ Welch t), two lanes per position
 int nm_launch_pair(const nm_kargs& ka, bool want_t, int max_n, int sm_count, cudaStream_t st);
 bool nm_pair_tier_available();

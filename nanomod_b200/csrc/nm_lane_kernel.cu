@@ -13,7 +13,6 @@
 #include "nm_device.cuh"
 
 #define NM_LANE_MAX_WARPS 4  // warps (= independent 32-row tiles) per CTA, chosen at launch
-#define NM_LANE_SYNC_WARPS 8 // CTA shape of the pair-synchronised mode (nm_kargs::pair_sync)
 
 // Visit the row's values through 128-bit shared-memory loads from the 16-byte aligned address
 // below the row (N/4 + 1 loads): window slot e holds row element e - shift and is valid iff
@@ -227,26 +226,7 @@ __device__ __forceinline__ int nm_walk_ks_fast4(const nm_key* colA, const nm_key
   return dmax >> 7;
 }
 
-// cooperative copy of the tile's rows when they are not one contiguous slice of vals
-__device__ __forceinline__ int nm_lane_gather(float* region, const float* __restrict__ vals,
-                                              long long start, int n, int lane) {
-  int incl = n;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const int base = incl - n;
-  for (int rlane = 0; rlane < 32; ++rlane) {
-    const int rn = __shfl_sync(0xffffffffu, n, rlane);
-    const int rbase = __shfl_sync(0xffffffffu, base, rlane);
-    const long long rstart = __shfl_sync(0xffffffffu, start, rlane);
-    for (int k = lane; k < rn; k += 32) region[rbase + k] = vals[rstart + k];
-  }
-  return base;
-}
-
-// Per-lane description of one row of a tile (tile = 32 consecutive rows, one per lane).
+// Per-lane description of one row of a tile (tile = 32 rows of the launch's row list, one per lane).
 struct nm_tile_meta {
   int64_t r;        // row index
   long long s0, s1; // start of the row's slices in vals0 / vals1
@@ -256,11 +236,13 @@ struct nm_tile_meta {
 
 __device__ __forceinline__ nm_tile_meta nm_tile_fetch(const nm_kargs& a, int64_t tile, int lane) {
   nm_tile_meta m;
-  m.r = tile * 32 + lane;
+  m.r = 0;
   m.n0 = m.n1 = 0;
   m.s0 = m.s1 = 0;
   m.ok = false;
-  if (tile >= 0 && m.r < a.n_rows) {
+  const int64_t idx = a.row_lo + tile * 32 + lane;
+  if (tile >= 0 && idx < a.row_hi) {
+    m.r = a.perm ? (int64_t)a.perm[idx] : idx;
     const int nn0 = a.row_n0[m.r], nn1 = a.row_n1[m.r];
     if (nn0 <= NM_LANE_TIER_MAX && nn1 <= NM_LANE_TIER_MAX) {
       const int32_t src = a.row_pos_index[m.r];
@@ -274,34 +256,114 @@ __device__ __forceinline__ nm_tile_meta nm_tile_fetch(const nm_kargs& a, int64_t
   return m;
 }
 
-// Warp-level plan for staging a tile: where its two value slices start, whether each is one
-// contiguous run of the CSR array (-> one TMA bulk copy) and each lane's offset in the region.
+// Warp-level plan for staging a tile.  If a group's 32 slices form one contiguous run of the CSR
+// array (the normal case when nothing was filtered and the rows are not class-binned) lane 0
+// copies it in one piece with a TMA bulk copy; otherwise every lane copies its own row's slice
+// (rounded out to 16-byte boundaries) into its own slot of the region with 16-byte cp.async.
 struct nm_tile_stage {
-  long long al0, al1;      // 16-byte aligned starts of the bulk copies
-  unsigned bytes0, bytes1; // bulk copy sizes (0: not contiguous, use the gather)
-  int base0, base1;        // this lane's row offset inside region A / B (contiguous case)
+  long long al0, al1;      // aligned source start: of the tile (contiguous) or of this lane's slice
+  unsigned bytes0, bytes1; // copy size: of the tile (contiguous, lane 0 issues) or of this lane's slice
+  int dst0, dst1;          // float offset of this lane's slot in region A / B (scattered mode; else 0)
+  int base0, base1;        // this lane's row offset inside region A / B
+  unsigned total;          // bytes the tile's mbarrier phase has to see (contiguous groups only)
   int nmax, tmax;
-  bool any;
+  bool any, contig0, contig1;
 };
 
-__device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
+__device__ __forceinline__ int nm_warp_excl_sum(int v, int lane) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  return inc - v;
+}
+
+__device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m, int lane, int region_floats) {
   nm_tile_stage st;
   const long long big = 0x7fffffffffffffffLL;
   st.any = __any_sync(0xffffffffu, m.ok);
   const long long first0 = nm_warp_min_ll(m.ok ? m.s0 : big), first1 = nm_warp_min_ll(m.ok ? m.s1 : big);
   const long long end0 = nm_warp_max_ll(m.ok ? m.s0 + m.n0 : -1), end1 = nm_warp_max_ll(m.ok ? m.s1 + m.n1 : -1);
-  const int tot0 = __reduce_add_sync(0xffffffffu, m.n0), tot1 = __reduce_add_sync(0xffffffffu, m.n1);
   st.tmax = __reduce_max_sync(0xffffffffu, m.n0 + m.n1);
-  st.al0 = first0 & ~3LL;
-  st.al1 = first1 & ~3LL;
-  const bool contig0 = st.any && (end0 - first0) == (long long)tot0;
-  const bool contig1 = st.any && (end1 - first1) == (long long)tot1;
-  st.bytes0 = contig0 ? (unsigned)(((first0 - st.al0) + tot0 + 3) & ~3LL) * 4u : 0u;
-  st.bytes1 = contig1 ? (unsigned)(((first1 - st.al1) + tot1 + 3) & ~3LL) * 4u : 0u;
-  st.base0 = m.ok ? (int)(m.s0 - st.al0) : 0;
-  st.base1 = m.ok ? (int)(m.s1 - st.al1) : 0;
   st.nmax = __reduce_max_sync(0xffffffffu, m.n0 > m.n1 ? m.n0 : m.n1);
+  // "contiguous": the span from the first to the last slice fits the region (rows skipped in
+  // between -- filtered, deep or binned elsewhere -- are copied along and ignored)
+  st.contig0 = st.any && (end0 - (first0 & ~3LL)) + 3 <= (long long)region_floats;
+  st.contig1 = st.any && (end1 - (first1 & ~3LL)) + 3 <= (long long)region_floats;
+  st.dst0 = st.dst1 = 0;
+  if (st.contig0) {
+    st.al0 = first0 & ~3LL;
+    st.bytes0 = (unsigned)((end0 - st.al0 + 3) & ~3LL) * 4u;
+    st.base0 = m.ok ? (int)(m.s0 - st.al0) : 0;
+  } else {
+    st.al0 = m.s0 & ~3LL;
+    const int len4 = m.ok ? (int)(((m.s0 - st.al0) + m.n0 + 3) & ~3LL) : 0;
+    st.bytes0 = (unsigned)len4 * 4u;
+    st.dst0 = nm_warp_excl_sum(len4, lane);
+    st.base0 = st.dst0 + (int)(m.s0 - st.al0);
+  }
+  if (st.contig1) {
+    st.al1 = first1 & ~3LL;
+    st.bytes1 = (unsigned)((end1 - st.al1 + 3) & ~3LL) * 4u;
+    st.base1 = m.ok ? (int)(m.s1 - st.al1) : 0;
+  } else {
+    st.al1 = m.s1 & ~3LL;
+    const int len4 = m.ok ? (int)(((m.s1 - st.al1) + m.n1 + 3) & ~3LL) : 0;
+    st.bytes1 = (unsigned)len4 * 4u;
+    st.dst1 = nm_warp_excl_sum(len4, lane);
+    st.base1 = st.dst1 + (int)(m.s1 - st.al1);
+  }
+  st.total = (st.contig0 ? st.bytes0 : 0u) + (st.contig1 ? st.bytes1 : 0u);
   return st;
+}
+
+// scattered rows: the warp copies one row's slice per step, 16 bytes per lane (coalesced; a
+// per-lane loop over its own row would touch 32 different lines per instruction)
+// (kept out of line: it is the rare path and must not lengthen the hot loop's code)
+__device__ __noinline__ void nm_rows_copy_async(float* region, const float* __restrict__ vals, long long al,
+                                                int dst, unsigned bytes, int lane) {
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    const long long ral = __shfl_sync(0xffffffffu, al, r);
+    const int rdst = __shfl_sync(0xffffffffu, dst, r);
+    const unsigned rbytes = __shfl_sync(0xffffffffu, bytes, r);
+    for (unsigned o = 16u * (unsigned)lane; o < rbytes; o += 512u)
+      nm_cp_async16(reinterpret_cast<unsigned char*>(region + rdst) + o,
+                    reinterpret_cast<const unsigned char*>(vals + ral) + o);
+  }
+}
+
+// issue the tile's copies: bulk copies complete on `bar`, per-lane copies on the lane's
+// cp.async group (nm_tile_wait)
+__device__ __forceinline__ void nm_tile_issue(const nm_kargs& a, const nm_tile_stage& st, float* regA, float* regB,
+                                              uint64_t* bar, int lane) {
+  if (lane == 0 && st.total) {
+    nm_mbar_expect_tx(bar, st.total);
+    if (st.contig0 && st.bytes0) nm_bulk_g2s(regA, a.vals0 + st.al0, st.bytes0, bar);
+    if (st.contig1 && st.bytes1) nm_bulk_g2s(regB, a.vals1 + st.al1, st.bytes1, bar);
+  }
+  if (!st.contig0) nm_rows_copy_async(regA, a.vals0, st.al0, st.dst0, st.bytes0, lane);
+  if (!st.contig1) nm_rows_copy_async(regB, a.vals1, st.al1, st.dst1, st.bytes1, lane);
+  if (!(st.contig0 && st.contig1)) nm_cp_async_commit();
+}
+
+__device__ __forceinline__ void nm_tile_wait(const nm_tile_stage& st, uint64_t* bar, unsigned& parity) {
+  if (st.total) {
+    nm_mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
+  if (!(st.contig0 && st.contig1)) nm_cp_async_wait_all();
+  __syncwarp();
+}
+
+// pull the tile's value slices into L2 ahead of time
+__device__ __forceinline__ void nm_tile_prefetch(const nm_kargs& a, const nm_tile_stage& st, int lane) {
+  if (lane == 0) {
+    if (st.contig0 && st.bytes0) nm_prefetch_l2(a.vals0 + st.al0, st.bytes0);
+    if (st.contig1 && st.bytes1) nm_prefetch_l2(a.vals1 + st.al1, st.bytes1);
+  }
 }
 
 // Persistent lane-tier kernel: every warp loops over tiles taken from a global cursor.  While
@@ -309,7 +371,7 @@ __device__ __forceinline__ nm_tile_stage nm_tile_plan(const nm_tile_meta& m) {
 // slices are being pulled into L2; its TMA copies are issued the moment the merge walk has
 // released the two regions, so that they overlap the fp64 tails of the current tile.
 template <int NMAX>
-__global__ void __launch_bounds__(NMAX <= 64 ? 32 * NM_LANE_MAX_WARPS : 32 * NM_LANE_SYNC_WARPS, NMAX <= 64 ? 3 : 1)
+__global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, NMAX <= 64 ? 3 : 2)
 nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -318,92 +380,42 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(my);
   float* regA = reinterpret_cast<float*>(my + 16);
   float* regB = regA + a.region_floats;
-  const int64_t n_tiles = (a.n_rows + 31) >> 5;
+  const int64_t n_tiles = (a.row_hi - a.row_lo + 31) >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
 
-  // Pair-synchronised mode (8-warp CTA): warps w and w+4 share an SM sub-partition; they claim
-  // two consecutive tiles together and meet at a 64-thread named barrier once per tile, so they
-  // run the same 50 KB of straight-line sort code at the same time and share its instruction
-  // fetches (the kernel is instruction-fetch bound, profiles/round1_variants.md).
-  const bool psync = NMAX > 64 && a.pair_sync != 0;
-  volatile long long* slots = reinterpret_cast<volatile long long*>(
-      nm_smem + (size_t)warps_per_cta * (16 + 2 * (size_t)a.region_floats * sizeof(float)));
-  unsigned iter = 0;
-
-  int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
-  if (tile >= n_tiles) {
-    if (!psync) return;
-    tile = -1;  // keeps arriving at the pair barrier with empty tiles
-  }
+  const int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
+  if (tile >= n_tiles) return;
   if (lane == 0) nm_mbar_init(bar, 1);
   __syncwarp();
   unsigned parity = 0;
 
   nm_tile_meta cur = nm_tile_fetch(a, tile, lane);
-  nm_tile_stage cst = nm_tile_plan(cur);
+  nm_tile_stage cst = nm_tile_plan(cur, lane, a.region_floats);
   bool staged = false;  // TMA for `cur` already issued?
   // The tile after next is claimed one iteration early: the atomic's round trip and the two
   // dependent metadata loads of a tile each get a whole tile of work to land.
   long long claim = 0;
-#ifndef NM_NO_PIPE_CLAIM
-  if (!psync && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
-#endif
+  if (lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
 
   while (true) {
-    // ---- claim the next tile and start fetching its metadata (consumed after the walk)
-    int64_t next = -1;
-    bool done;
-    if (psync) {
-      const int pr = wib & 3;
-      volatile long long* slot = slots + ((iter & 1u) << 2) + pr;
-      if (wib < 4 && lane == 0) *slot = (long long)atomicAdd(a.tile_cursor, 2) + n_warps;
-      asm volatile("bar.sync %0, 64;" ::"r"(pr + 1) : "memory");
-      const long long t = *slot;
-      done = t >= n_tiles;
-      const long long mine = t + (wib >> 2);
-      next = mine < n_tiles ? mine : -1;
-      ++iter;
-    } else {
-#ifdef NM_NO_PIPE_CLAIM
-      if (lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
-#endif
-      const long long t = __shfl_sync(0xffffffffu, claim, 0);
-      next = t < n_tiles ? t : -1;
-      done = next < 0;
-#ifndef NM_NO_PIPE_CLAIM
-      if (!done && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
-#endif
-    }
+    // ---- the next tile: claimed last iteration, metadata fetched now, consumed after the sorts
+    const long long t = __shfl_sync(0xffffffffu, claim, 0);
+    const int64_t next = t < n_tiles ? t : -1;
+    const bool done = next < 0;
+    if (!done && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
     const nm_tile_meta nxt = nm_tile_fetch(a, next, lane);
 
     if (cst.any) {
       // ---- stage the current tile (unless its copies were issued at the end of the last one)
-      if (!staged && (cst.bytes0 | cst.bytes1) && lane == 0) {
-        nm_mbar_expect_tx(bar, cst.bytes0 + cst.bytes1);
-        if (cst.bytes0) nm_bulk_g2s(regA, a.vals0 + cst.al0, cst.bytes0, bar);
-        if (cst.bytes1) nm_bulk_g2s(regB, a.vals1 + cst.al1, cst.bytes1, bar);
-      }
-      int base0 = cst.base0, base1 = cst.base1;
-      if (!cst.bytes0) base0 = nm_lane_gather(regA, a.vals0, cur.s0, cur.n0, lane);
-      if (!cst.bytes1) base1 = nm_lane_gather(regB, a.vals1, cur.s1, cur.n1, lane);
-#ifdef NM_EARLY_PLAN
-      const nm_tile_stage nst = nm_tile_plan(nxt);
-      if (lane == 0) {
-        if (nst.bytes0) nm_prefetch_l2(a.vals0 + nst.al0, nst.bytes0);
-        if (nst.bytes1) nm_prefetch_l2(a.vals1 + nst.al1, nst.bytes1);
-      }
-#endif
-      if (cst.bytes0 | cst.bytes1) {
-        nm_mbar_wait(bar, parity);
-        parity ^= 1u;
-      }
-      __syncwarp();
+      if (!staged) nm_tile_issue(a, cst, regA, regB, bar, lane);
+      const int base0 = cst.base0, base1 = cst.base1;
+      nm_tile_wait(cst, bar, parity);
 
       const int n0 = cur.n0, n1 = cur.n1;
-      // Size class of the tile.  Tiles whose longest row is more than half the call's longest
-      // row all use the call's class: a handful of extra comparators costs far less than
-      // keeping several 30-60 KB networks alive in the 32 KB instruction cache.
+      // Network size of the tile.  Tiles whose longest row is more than half the launch's longest
+      // row all use the launch's class: a handful of extra comparators costs far less than
+      // keeping several 30-60 KB networks alive in the instruction cache.
       int nsel = nm_lane_class(cst.nmax);
       if (2 * cst.nmax > a.class_n) nsel = a.class_n;
       nm_lane_acc acc;
@@ -419,15 +431,10 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       NM_DISPATCH_N(nsel, NM_CALL)
 #undef NM_CALL
 
-#ifndef NM_EARLY_PLAN
       // plan the next tile (its metadata loads have had both sorts to land) and pull its value
       // slices into L2 while this tile is walked and finished
-      const nm_tile_stage nst = nm_tile_plan(nxt);
-      if (lane == 0) {
-        if (nst.bytes0) nm_prefetch_l2(a.vals0 + nst.al0, nst.bytes0);
-        if (nst.bytes1) nm_prefetch_l2(a.vals1 + nst.al1, nst.bytes1);
-      }
-#endif
+      const nm_tile_stage nst = nm_tile_plan(nxt, lane, a.region_floats);
+      nm_tile_prefetch(a, nst, lane);
 
       const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
       const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
@@ -450,13 +457,9 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       // ---- the regions are free again: issue the next tile's copies before the fp64 tails
       __syncwarp();
       staged = false;
-      if (nst.any && (nst.bytes0 | nst.bytes1)) {
-        if (lane == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          nm_mbar_expect_tx(bar, nst.bytes0 + nst.bytes1);
-          if (nst.bytes0) nm_bulk_g2s(regA, a.vals0 + nst.al0, nst.bytes0, bar);
-          if (nst.bytes1) nm_bulk_g2s(regB, a.vals1 + nst.al1, nst.bytes1, bar);
-        }
+      if (nst.any) {
+        if (lane == 0 && nst.total) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nm_tile_issue(a, nst, regA, regB, bar, lane);
         staged = true;
       }
 
@@ -482,7 +485,7 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
       cst = nst;
     } else {
       cur = nxt;
-      cst = nm_tile_plan(nxt);
+      cst = nm_tile_plan(nxt, lane, a.region_floats);
       staged = false;
     }
     if (done) break;
@@ -492,36 +495,12 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
 static int nm_lane_warp_smem(int region_floats) { return 16 + 2 * region_floats * (int)sizeof(float); }
 
 template <int NMAX>
-static int nm_launch_lane_t(const nm_kargs& ka_in, bool want_u, bool want_t, int sm_count, int pair_sync,
-                            cudaStream_t st) {
+static int nm_launch_lane_t(const nm_kargs& ka_in, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
   nm_kargs ka = ka_in;
-  const int per_warp = nm_lane_warp_smem(ka.region_floats);
-  const int sync_smem = NM_LANE_SYNC_WARPS * per_warp + 64;  // + the pairs' tile slots
+  int per_warp = nm_lane_warp_smem(ka.region_floats);
   cudaError_t e = cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       NMAX > 64 ? sync_smem : NM_LANE_MAX_WARPS * per_warp);
-  if (e != cudaSuccess && NMAX > 64) {  // the 8-warp shape does not fit (N > 104): plain mode only
-    (void)cudaGetLastError();
-    pair_sync = 0;
-    e = cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             NM_LANE_MAX_WARPS * per_warp);
-  }
+                                       NM_LANE_MAX_WARPS * per_warp);
   if (e != cudaSuccess) return (int)e;
-  ka.pair_sync = 0;
-  if (NMAX > 64 && pair_sync) {
-    int blocks = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_kernel<NMAX>, 32 * NM_LANE_SYNC_WARPS,
-                                                      (size_t)sync_smem);
-    if (e == cudaSuccess && blocks >= 1) {
-      ka.pair_sync = 1;
-      const int64_t tiles = (ka.n_rows + 31) / 32;
-      int64_t grid = (tiles + NM_LANE_SYNC_WARPS - 1) / NM_LANE_SYNC_WARPS;
-      if (grid > (int64_t)blocks * sm_count) grid = (int64_t)blocks * sm_count;
-      nm_lane_kernel<NMAX><<<(unsigned)grid, 32 * NM_LANE_SYNC_WARPS, (size_t)sync_smem, st>>>(
-          ka, want_u ? 1 : 0, want_t ? 1 : 0);
-      return (int)cudaGetLastError();
-    }
-    (void)cudaGetLastError();
-  }
   // CTA shape: as many resident warps per SM as shared memory and registers allow
   int best_w = 1, best_blocks = 0, best_warps = 0;
   for (int w = NM_LANE_MAX_WARPS; w >= 1; --w) {
@@ -535,7 +514,30 @@ static int nm_launch_lane_t(const nm_kargs& ka_in, bool want_u, bool want_t, int
     }
   }
   if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
-  const int64_t tiles = (ka.n_rows + 31) / 32;
+  // Grow the regions into the shared memory this occupancy leaves unused: a tile whose rows are
+  // nearly contiguous (a few filtered / deep / differently binned rows in between) can then be
+  // staged as one span with a single bulk copy.
+  {
+    int dev = 0, smem_sm = 0, smem_blk = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int budget = smem_sm / best_blocks - 1024;  // 1 KB per resident CTA is reserved by the system
+    if (budget > smem_blk) budget = smem_blk;
+    const int grown = ((budget / best_w - 16) / 8) & ~3;  // floats per region
+    if (grown > ka.region_floats) {
+      const int pw = nm_lane_warp_smem(grown);
+      int blocks = 0;
+      if (cudaFuncSetAttribute(nm_lane_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, best_w * pw) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_kernel<NMAX>, 32 * best_w, (size_t)best_w * pw) == cudaSuccess &&
+          blocks >= best_blocks) {
+        ka.region_floats = grown;
+        per_warp = pw;
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  const int64_t tiles = (ka.row_hi - ka.row_lo + 31) / 32;
   int64_t grid = (tiles + best_w - 1) / best_w;
   const int64_t resident = (int64_t)best_blocks * sm_count;
   if (grid > resident) grid = resident;
@@ -544,13 +546,15 @@ static int nm_launch_lane_t(const nm_kargs& ka_in, bool want_u, bool want_t, int
   return (int)cudaGetLastError();
 }
 
-// max_n = longest lane-tier row of this call
-int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, int sm_count, int pair_sync,
-                   cudaStream_t st) {
+// One launch over rows [ka.row_lo, ka.row_hi) of the (optionally class-sorted) row list;
+// max_n = longest row among them.  The regions hold the transposed columns (max class + 2 rows
+// of 32) and, before that, the raw rows: 32 slices rounded out to 16-byte boundaries.
+int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st) {
   nm_kargs ka = ka_in;
+  if (ka.row_hi <= ka.row_lo) return (int)cudaSuccess;
   const int ncls = nm_lane_class(max_n);
-  ka.region_floats = 32 * (ncls + 2);
+  ka.region_floats = 32 * (ncls + 6);
   ka.class_n = ncls;
-  if (max_n <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, 0, st);
-  return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, pair_sync, st);
+  if (ncls <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, st);
+  return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
 }

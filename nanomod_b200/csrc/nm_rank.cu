@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nm_device.cuh"
 #include "nm_rank.cuh"
 
 namespace {
@@ -89,5 +90,81 @@ int nm_rank_run(const double* comb, const double* ks, const double* u, int64_t n
     cudaError_t e = cudaMemcpyAsync(order_out, ord.Current(), sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return (int)e;
   }
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Group binning of the lane tier's rows.  The lane kernel runs one sorting-network size per
+// launch; a call whose rows span several size groups -- <= 64, <= 104, <= 128 reads -- can be
+// split into one launch per group.  nm_group_keys counts the groups (the host decides whether
+// splitting pays, nm_api.cu) and nm_group_sort_run makes the stable partition of the row indices
+// by group (one 2-bit radix pass): rows keep genome order inside a group, so tiles stay nearly
+// contiguous when the other groups are sparse.  Deep rows get key 3 and end up last.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+nm_group_keys(const int32_t* __restrict__ row_n0, const int32_t* __restrict__ row_n1, int64_t n, uint8_t* __restrict__ keys,
+              int32_t* __restrict__ rows, nm_summary* __restrict__ sum) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int le64 = 0, le104 = 0;
+  if (r < n) {
+    const int m = row_n0[r] > row_n1[r] ? row_n0[r] : row_n1[r];
+    int key = 3;
+    if (m <= NM_LANE_TIER_MAX) {
+      const int cls = nm_lane_class(m);
+      le64 = cls <= 64;
+      le104 = cls <= NM_LANE_FINE_MAX;
+      key = le64 ? 0 : le104 ? 1 : 2;
+    }
+    keys[r] = (uint8_t)key;
+    rows[r] = (int32_t)r;
+  }
+  le64 = __reduce_add_sync(0xffffffffu, le64);
+  le104 = __reduce_add_sync(0xffffffffu, le104);
+  if ((threadIdx.x & 31) == 0) {
+    if (le64) atomicAdd(&sum->n_le64, le64);
+    if (le104) atomicAdd(&sum->n_le104, le104);
+  }
+}
+
+}  // namespace
+
+size_t nm_group_sort_scratch_bytes(int64_t n) {
+  size_t cub_bytes = 0;
+  cub::DoubleBuffer<uint8_t> k(nullptr, nullptr);
+  cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, (int)n, 0, 2);
+  return 2 * nm_align256((size_t)n) + nm_align256(cub_bytes) + 256;
+}
+
+// keys + identity row list + group counts (added to *sum)
+int nm_group_keys_run(const int32_t* row_n0, const int32_t* row_n1, int64_t n, int32_t* perm_a, void* scratch,
+                      nm_summary* sum, int* launches, cudaStream_t st) {
+  nm_group_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_n0, row_n1, n, (uint8_t*)scratch, perm_a, sum);
+  *launches += 1;
+  return (int)cudaGetLastError();
+}
+
+// stable partition of perm_a by the keys nm_group_keys_run left in scratch
+int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t** perm_out, void* scratch,
+                      int* launches, cudaStream_t st) {
+  unsigned char* p = (unsigned char*)scratch;
+  uint8_t* kA = p;
+  p += nm_align256((size_t)n);
+  uint8_t* kB = p;
+  p += nm_align256((size_t)n);
+  size_t cub_bytes = 0;
+  {
+    cub::DoubleBuffer<uint8_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k, v, (int)n, 0, 2);
+  }
+  cub::DoubleBuffer<uint8_t> keys(kA, kB);
+  cub::DoubleBuffer<int32_t> rows(perm_a, perm_b);
+  const cudaError_t e = cub::DeviceRadixSort::SortPairs((void*)p, cub_bytes, keys, rows, (int)n, 0, 2, st);
+  if (e != cudaSuccess) return (int)e;
+  *launches += 2;
+  *perm_out = rows.Current();
   return (int)cudaGetLastError();
 }

@@ -11,3 +11,14 @@ size_t nm_rank_scratch_bytes(int64_t n);
 // kernels launched to *launches.
 int nm_rank_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int32_t* order_out,
                 void* scratch, int* launches, cudaStream_t st);
+
+// Group binning of the lane tier (nm_rank.cu).  nm_group_keys_run writes one group key per row
+// into scratch and the identity row list into perm_a, and adds the group counts n_le64 / n_le104
+// to *sum (device); nm_group_sort_run then partitions the rows by group (stable; deep rows last)
+// into one of perm_a / perm_b and returns which in *perm_out.
+struct nm_summary;
+size_t nm_group_sort_scratch_bytes(int64_t n);
+int nm_group_keys_run(const int32_t* row_n0, const int32_t* row_n1, int64_t n, int32_t* perm_a, void* scratch,
+                      nm_summary* sum, int* launches, cudaStream_t st);
+int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t** perm_out, void* scratch,
+                      int* launches, cudaStream_t st);

@@ -431,6 +431,44 @@ def test_device_ranking_equals_host_ranking(det, rank_use, method):
     assert np.array_equal(det.rank(t2), t2.ranked())
 
 
+@pytest.mark.parametrize("want_all", [False, True])
+def test_group_binned_launches(det, want_all):
+    """Mixed coverage with a dominant size group: the call is split into one launch per group
+    (rows partitioned by group, tiles staged as spans or row by row).  Results must not depend
+    on it: same table as the oracle's and as the un-binned run of the same library."""
+    import os
+    rng = np.random.default_rng(123)
+    L = 6000
+    c0 = rng.integers(20, 40, L).astype(np.int64)
+    c1 = rng.integers(20, 40, L).astype(np.int64)
+    pick = rng.random(L)
+    mid = pick < 0.04
+    big = (pick >= 0.04) & (pick < 0.06)
+    c0[mid], c1[mid] = rng.integers(70, 104, mid.sum()), rng.integers(5, 104, mid.sum())
+    c0[big], c1[big] = rng.integers(105, 129, big.sum()), rng.integers(90, 129, big.sum())
+    c0[rng.random(L) < 0.03] = 2          # filtered by MinCoverage
+    c0[1000], c1[1000] = 300, 20          # deep rows
+    c0[4000:4040], c1[4000:4040] = 100, 100   # a run of mid rows: contiguous tiles inside a group
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0.2, 1, off1[-1]), 2).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=2, both_combinations=want_all, want_u=want_all, want_t=want_all, mstd=want_all)
+    before = det.handle.launch_count
+    t = det.detect(p, opt)
+    launches = det.handle.launch_count - before
+    assert launches >= 3 + 3 + 3 + 1  # plan, group keys + partition, three lane launches, combine
+    assert_table_matches(t, vec(p, opt), opt)
+    os.environ["NANOMOD_B200_NO_CLASS_SORT"] = "1"
+    try:
+        plain = nm.Detector(0).detect(p, opt)
+    finally:
+        del os.environ["NANOMOD_B200_NO_CLASS_SORT"]
+    for c in ("ks_dnum", "ks_p", "stouffer_p") + (("two_u", "u_p", "t_stat", "t_p", "fisher_p", "moments") if want_all else ()):
+        assert np.array_equal(getattr(t, c), getattr(plain, c), equal_nan=True), c
+
+
 def test_device_resident_entry_and_unaligned_offsets(det):
     """nm_detect_device on torch tensors; rows whose slices start at odd element offsets."""
     import torch

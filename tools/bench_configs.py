@@ -20,12 +20,20 @@ from bench import make_device_workload, hbm_peak
 
 
 def poisson_workload(length, mean, device, lo=5, hi=128, seed=7):
-    from nanomod_b200._lib import padded_len
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     lam = torch.full((length,), float(mean), device=device)
     c0 = torch.poisson(lam, generator=g).clamp_(lo, hi).long()
     c1 = torch.poisson(lam, generator=g).clamp_(lo, hi).long()
+    return workload_from_counts(c0, c1, device, g)
+
+
+def workload_from_counts(c0, c1, device, g=None):
+    from nanomod_b200._lib import padded_len
+    if g is None:
+        g = torch.Generator(device=device)
+        g.manual_seed(11)
+    length = c0.numel()
     off0 = torch.zeros(length + 1, dtype=torch.int64, device=device)
     off1 = torch.zeros(length + 1, dtype=torch.int64, device=device)
     off0[1:] = torch.cumsum(c0, 0)
@@ -81,6 +89,18 @@ def main():
     if "cfg2p" in which:
         dev, nvals = poisson_workload(4_600_000, 100, d)
         run("cfg2p E.coli Poisson(100) clipped [5,128] KS+Stouffer", dev, nvals, 4_600_000, ks_st, 28)
+        del dev
+    if "cfg2o" in which:  # mostly 2x100x with 1 % of deeper positions (outliers set the old per-call class)
+        g = torch.Generator(device=d).manual_seed(7)
+        L = 4_600_000
+        c = torch.full((L,), 100, dtype=torch.int64, device=d)
+        c[torch.rand(L, generator=g, device=d) < 0.01] = 128
+        dev, nvals = workload_from_counts(c, c.clone(), d)
+        run("cfg2o E.coli 2x100x with 1% of 2x128x positions KS+Stouffer", dev, nvals, L, ks_st, 28)
+        del dev
+    if "cfg2x" in which:  # uniform 2x128x: the largest lane-tier class
+        dev, _ = make_device_workload(2_000_000, 128, 128, d)
+        run("cfg2x 2 Mb 2x128x KS+Stouffer", dev, 2_000_000 * 256, 2_000_000, ks_st, 28)
         del dev
     if "cfg2h" in which:
         dev, _ = make_device_workload(4_600_000, 50, 50, d)
