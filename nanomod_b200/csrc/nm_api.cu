@@ -83,12 +83,27 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
   max_slack = __reduce_max_sync(0xffffffffu, max_slack);
   max_deep = __reduce_max_sync(0xffffffffu, max_deep);
   n_deep = __reduce_add_sync(0xffffffffu, n_deep);
+  // one set of atomics per block, and only when it would change the summary (every warp hitting
+  // the same address costs tens of microseconds at 4.6 M candidates)
+  __shared__ int red[4][NM_PLAN_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
-    if (max_lane) atomicMax(&sum->max_lane_n, max_lane);
-    if (max_slack) atomicMax(&sum->max_lane_slack, max_slack);
-    if (n_deep) {
-      atomicAdd(&sum->n_deep, n_deep);
-      atomicMax(&sum->max_deep_p2, max_deep);
+    const int w = threadIdx.x >> 5;
+    red[0][w] = max_lane; red[1][w] = max_slack; red[2][w] = max_deep; red[3][w] = n_deep;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ml = 0, ms = 0, md = 0, nd = 0;
+    for (int w = 0; w < NM_PLAN_THREADS / 32; ++w) {
+      ml = ml > red[0][w] ? ml : red[0][w];
+      ms = ms > red[1][w] ? ms : red[1][w];
+      md = md > red[2][w] ? md : red[2][w];
+      nd += red[3][w];
+    }
+    if (ml > *(volatile int*)&sum->max_lane_n) atomicMax(&sum->max_lane_n, ml);
+    if (ms > *(volatile int*)&sum->max_lane_slack) atomicMax(&sum->max_lane_slack, ms);
+    if (nd) {
+      atomicAdd(&sum->n_deep, nd);
+      atomicMax(&sum->max_deep_p2, md);
     }
   }
   if (threadIdx.x == 0) block_count[blockIdx.x] = total;
@@ -452,13 +467,14 @@ static int nm_check_params(nm_handle* h, const nm_params* p, nm_params* eff) {
 // <= 64 (the 12-warps/SM instantiation), <= 104 (straight-line networks, 8 warps/SM), <= 128
 // (looped networks, 6 warps/SM) -- each with shared memory sized for its own largest class.
 static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool want_t, bool want_m, const nm_summary& sum,
-                           const int32_t* perm, int deep_smem, int64_t n_rows, cudaStream_t st) {
+                           const int32_t* perm, int deep_smem, int64_t n_rows, int64_t n_pos, cudaStream_t st) {
   const int n_deep = sum.n_deep, max_lane_n = sum.max_lane_n, max_deep_p2 = sum.max_deep_p2;
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
   if (n_rows > n_deep) {
     const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
     nm_kargs kl = ka;
     kl.perm = perm;
+    kl.gaps = (perm != nullptr || n_deep > 0 || n_rows != n_pos) ? 1 : 0;
     // The pair tier (two lanes per position for long rows; KS and Welch t only) is an experiment:
     // it doubles residency and halves the code footprint, but needs 25 % more instructions and
     // measured slower than the lane tier in round 1 (profiles/round1_variants.md).  Off unless
@@ -634,7 +650,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
       h->launches += launches;
     }
   }
-  rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum2, perm, deep_smem, n_rows, st);
+  rc = nm_launch_tiers(h, ka, want_u, want_t, want_m, sum2, perm, deep_smem, n_rows, n_pos, st);
   if (rc != NM_OK) return rc;
 
   // ---- down-sampling branch (myDetect.py:345-361): replaces the KS result of deep positions

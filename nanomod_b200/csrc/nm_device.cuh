@@ -126,6 +126,7 @@ struct nm_kargs {
   // and launch once per class group, so that every tile is homogeneous.
   const int32_t* perm;
   int64_t row_lo, row_hi;
+  int gaps;           // the launch's rows are not all consecutive candidates (filtered / deep / other group rows between)
   int region_floats;  // floats per group region in shared memory (lane tier)
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
