@@ -280,10 +280,8 @@ def run_gpu_arm(args):
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
         if world > 1:
-            # pack the four result columns into 28-byte records, then ONE gather
-            for i, col in enumerate(rec_cols):
-                src = outs[b][col][halo_lo:halo_lo + L]
-                recs[b][:, rec_w[i]:rec_w[i + 1]].copy_(src.view(torch.uint8).view(L, -1))
+            # pack the four result columns into 28-byte records (one kernel), then ONE gather
+            det.pack_records(outs[b], halo_lo, L, opt, recs[b])
             comm.wait_stream(torch.cuda.current_stream(device))
             with torch.cuda.stream(comm):
                 pending[b] = [dist.gather(recs[b], gbufs[b], dst=0, async_op=True)]

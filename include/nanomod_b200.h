@@ -138,6 +138,14 @@ int nm_rank_device(nm_handle* h, const double* key_comb, const double* key_ks, c
 int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
                  int64_t n_rows, int reverse, int32_t* order);
 
+/* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
+ * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`
+ * (device, 28*n bytes): the unit a rank sends to rank 0 in multi-GPU runs.
+ * which_combine: NM_COMBINE_FISHER or NM_COMBINE_STOUFFER selects the combined columns. */
+#define NM_RECORD_BYTES 28
+int nm_pack_records_device(nm_handle* h, const nm_table* table, int64_t row_lo, int64_t n, int which_combine,
+                           void* records, void* cuda_stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nm_launch_count(const nm_handle* h);
 

@@ -18,6 +18,7 @@ NM_MAX_NB = 32
 NM_LANE_TIER_MAX = 128
 NM_DS_MAX_READS = 256
 NM_DS_MAX_TIMES = 1024
+NM_RECORD_BYTES = 28
 
 ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: "NM_ERR_OOM",
                5: "NM_ERR_TOO_DEEP", 6: "NM_ERR_NO_DEVICE"}
@@ -25,7 +26,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
                     "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings",
-                    "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host"]
+                    "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device"]
 
 
 class NmError(RuntimeError):
@@ -104,6 +105,9 @@ def load():
     lib.nm_rank_host.restype = C.c_int
     lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                  C.c_void_p]
+    lib.nm_pack_records_device.restype = C.c_int
+    lib.nm_pack_records_device.argtypes = [C.c_void_p, C.POINTER(nm_table), C.c_int64, C.c_int64, C.c_int,
+                                           C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -181,3 +185,9 @@ class Handle:
         self._check(self._lib.nm_rank_device(self._h, C.c_void_p(key_comb or 0), C.c_void_p(key_ks),
                                              C.c_void_p(key_u or 0), int(n_rows), int(bool(reverse)),
                                              C.c_void_p(order), C.c_void_p(int(stream))))
+
+    def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,
+                            stream: int = 0) -> None:
+        """nm_pack_records_device: 28-byte result records of rows [row_lo, row_lo + n)."""
+        self._check(self._lib.nm_pack_records_device(self._h, C.byref(table), int(row_lo), int(n), int(which_combine),
+                                                     C.c_void_p(records), C.c_void_p(int(stream))))

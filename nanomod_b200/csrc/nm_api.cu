@@ -812,3 +812,53 @@ extern "C" int nm_rank_host(nm_handle* h, const double* key_comb, const double* 
   NM_CUDA(h, cudaStreamSynchronize(st));
   return NM_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// result records for the multi-GPU gather: 28 bytes per row, packed
+// ------------------------------------------------------------------------------------------
+#define NM_PACK_ROWS 256
+__global__ void __launch_bounds__(NM_PACK_ROWS)
+nm_pack_kernel(const int32_t* __restrict__ dnum, const double* __restrict__ ks_p, const double* __restrict__ c_stat,
+               const double* __restrict__ c_p, int64_t row_lo, int64_t n, unsigned char* __restrict__ out) {
+  __shared__ __align__(16) unsigned char rec[NM_PACK_ROWS * NM_RECORD_BYTES];
+  const int64_t base = (int64_t)blockIdx.x * NM_PACK_ROWS;
+  const int64_t i = base + threadIdx.x;
+  if (i < n) {
+    const int64_t r = row_lo + i;
+    // 28-byte records are only 4-byte aligned: the doubles go in as two words each
+    uint32_t* w = reinterpret_cast<uint32_t*>(rec + threadIdx.x * NM_RECORD_BYTES);
+    const double v[3] = {ks_p[r], c_stat[r], c_p[r]};
+    w[0] = (uint32_t)dnum[r];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong(v[k]);
+      w[1 + 2 * k] = (uint32_t)b;
+      w[2 + 2 * k] = (uint32_t)(b >> 32);
+    }
+  }
+  __syncthreads();
+  const int64_t rows_here = n - base < NM_PACK_ROWS ? n - base : NM_PACK_ROWS;
+  const int words = (int)(rows_here * NM_RECORD_BYTES / 4);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + base * NM_RECORD_BYTES);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(rec);
+  for (int k = threadIdx.x; k < words; k += NM_PACK_ROWS) dst[k] = src[k];
+}
+
+extern "C" int nm_pack_records_device(nm_handle* h, const nm_table* tb, int64_t row_lo, int64_t n, int which_combine,
+                                      void* records, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!tb || !records || row_lo < 0 || n < 0) return nm_fail(h, NM_ERR_BAD_ARG, "table/records is NULL or a negative range");
+  const double* cs = which_combine == NM_COMBINE_FISHER ? tb->fisher_stat : tb->stouffer_stat;
+  const double* cp = which_combine == NM_COMBINE_FISHER ? tb->fisher_p : tb->stouffer_p;
+  if (which_combine != NM_COMBINE_FISHER && which_combine != NM_COMBINE_STOUFFER)
+    return nm_fail(h, NM_ERR_BAD_PARAM, "which_combine must be NM_COMBINE_FISHER or NM_COMBINE_STOUFFER");
+  if (!tb->ks_dnum || !tb->ks_p || !cs || !cp) return nm_fail(h, NM_ERR_BAD_ARG, "table lacks a column of the record");
+  if (n == 0) return NM_OK;
+  NM_CUDA(h, cudaSetDevice(h->device));
+  nm_pack_kernel<<<(unsigned)((n + NM_PACK_ROWS - 1) / NM_PACK_ROWS), NM_PACK_ROWS, 0, (cudaStream_t)cuda_stream>>>(
+      tb->ks_dnum, tb->ks_p, cs, cp, row_lo, n, (unsigned char*)records);
+  NM_CUDA(h, cudaGetLastError());
+  h->launches++;
+  return NM_OK;
+}

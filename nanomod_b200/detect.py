@@ -411,6 +411,11 @@ def _col_shape(c: str, n: int):
     return (n, w) if w > 1 else (n,)
 
 
+# numpy view of the 28-byte records of Detector.pack_records
+RECORD_DTYPE = np.dtype({"names": ["ks_dnum", "ks_p", "comb_stat", "comb_p"], "formats": ["<i4", "<f8", "<f8", "<f8"],
+                         "offsets": [0, 4, 12, 20], "itemsize": 28})
+
+
 class Detector:
     """One GPU's detection engine.  ``detect`` is the host-buffer call (numpy in, numpy out,
     H2D/D2H inside); ``detect_device`` works on torch CUDA tensors that are already resident."""
@@ -478,6 +483,19 @@ class Detector:
         self.handle.rank_device(None if comb is None else comb.data_ptr(), ks.data_ptr(),
                                 None if u is None else u.data_ptr(), n_rows, not use_p, order.data_ptr(), stream)
         return order
+
+    def pack_records(self, out: Dict[str, "object"], row_lo: int, n: int, options: DetectOptions, records,
+                     stream: Optional[int] = None) -> None:
+        """Device-resident table -> 28-byte records {ks_dnum, ks_p, comb stat, comb p} of rows
+        [row_lo, row_lo + n) in ``records`` (uint8 CUDA tensor of 28*n bytes): what a rank sends to
+        rank 0 in multi-GPU runs.  Record dtype: ``RECORD_DTYPE``."""
+        import torch
+        which = _lib.NM_COMBINE_FISHER if options.testMethod == "fisher" else _lib.NM_COMBINE_STOUFFER
+        cols = [c for c in _wanted_columns(options) if c in out]
+        tb = _lib.nm_table(**{c: out[c].data_ptr() for c in cols})
+        if stream is None:
+            stream = torch.cuda.current_stream(records.device).cuda_stream
+        self.handle.pack_records_device(tb, row_lo, n, which, records.data_ptr(), stream)
 
     def detect_device(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
                       stream: Optional[int] = None) -> int:

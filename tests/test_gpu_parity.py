@@ -469,6 +469,28 @@ def test_group_binned_launches(det, want_all):
         assert np.array_equal(getattr(t, c), getattr(plain, c), equal_nan=True), c
 
 
+@pytest.mark.parametrize("method", ["stouffer", "fisher"])
+def test_pack_records(det, method):
+    """nm_pack_records_device: the 28-byte records a rank sends to rank 0."""
+    import torch
+    from nanomod_b200.detect import RECORD_DTYPE
+    p = nm.synthetic_pileup(1000, 12, 15, round_decimals=2)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod=method, want_u=False, want_t=False)
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    out = nm.alloc_device_table(opt, p.n_pos, "cuda:0")
+    n_rows = det.detect_device(dev, opt, out)
+    lo, n = 3, n_rows - 7
+    rec = torch.empty(28 * n, dtype=torch.uint8, device="cuda:0")
+    det.pack_records(out, lo, n, opt, rec)
+    torch.cuda.synchronize()
+    r = rec.cpu().numpy().view(RECORD_DTYPE)
+    assert r.shape == (n,)
+    assert np.array_equal(r["ks_dnum"], out["ks_dnum"][lo:lo + n].cpu().numpy())
+    assert np.array_equal(r["ks_p"], out["ks_p"][lo:lo + n].cpu().numpy())
+    assert np.array_equal(r["comb_stat"], out[method + "_stat"][lo:lo + n].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(r["comb_p"], out[method + "_p"][lo:lo + n].cpu().numpy())
+
+
 def test_device_resident_entry_and_unaligned_offsets(det):
     """nm_detect_device on torch tensors; rows whose slices start at odd element offsets."""
     import torch
