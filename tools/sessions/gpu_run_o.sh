@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out/o; mkdir -p $O
 echo "== pytest gpu (default)"; timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "rc=$?"; tail -6 $O/pytest_gpu.log
-VARIANTS="${VARIANTS:-base _w2}" bash tools/gpu_run_n.sh
+VARIANTS="${VARIANTS:-base _w2}" bash tools/gpu_bench_variants.sh
 timeout 1500 python tools/bench_configs.py cfg1 cfg2p cfg4 > $O/configs.jsonl 2> $O/configs.err; python - <<PY
 import json
 for l in open("$O/configs.jsonl"):

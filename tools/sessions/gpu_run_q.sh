@@ -4,7 +4,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out/q; mkdir -p $O
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "rc=$?"; tail -4 $O/pytest_gpu.log
-VARIANTS="base" bash tools/gpu_run_n.sh
+VARIANTS="base" bash tools/gpu_bench_variants.sh
 timeout 900 python tools/bench_configs.py cfg2h cfg4 2> $O/configs.err | python -c "
 import json,sys
 for l in sys.stdin:
