@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sm-reserve", type=int, default=2, help="SMs left free for NCCL while computing (N > 1)")
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=60000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
