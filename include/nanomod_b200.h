@@ -146,6 +146,35 @@ int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, con
 int nm_pack_records_device(nm_handle* h, const nm_table* table, int64_t row_lo, int64_t n, int which_combine,
                            void* records, void* cuda_stream);
 
+/* Text of the per-position table (save_test, myDetect.py:522-538), formatted on the host by
+ * n_threads threads: '%s %s %d %s %d %d %.3f %.3E %.3f %.3E %.3f %.3E[ %.3f %.3E]\n' per row with
+ * pos + 1, exactly as the reference's Python '%' prints them.  All pointers are host memory;
+ * u_*, t_* may be NULL (printed as 0); comb_* both NULL = no combined columns (testMethod 'ks' or
+ * neighborPvalues 0).  Returns the bytes written to `out`, -(bytes needed) if out_cap is too
+ * small, -1 on a bad argument.  nm_format_bound gives a safe per-row capacity. */
+typedef struct nm_text_columns {
+  const char* const* seg_chrom;  /* [n_seg] chromosome name of each segment id */
+  const char* const* seg_strand; /* [n_seg] '+' or '-'                         */
+  int32_t n_seg;
+  int32_t reserved;
+  int64_t n_rows;
+  const int32_t* seg;  /* per row: segment id, 0-based position, base character, coverages */
+  const int32_t* pos;
+  const uint8_t* base;
+  const int32_t* n0;
+  const int32_t* n1;
+  const double* u_stat;
+  const double* u_p;
+  const double* t_stat;
+  const double* t_p;
+  const double* ks_d;
+  const double* ks_p;
+  const double* comb_stat;
+  const double* comb_p;
+} nm_text_columns;
+int64_t nm_format_bound(const nm_text_columns* columns);
+int64_t nm_format_sign_test(const nm_text_columns* columns, int n_threads, char* out, int64_t out_cap);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nm_launch_count(const nm_handle* h);
 

@@ -26,7 +26,8 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
                     "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings",
-                    "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device"]
+                    "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
+                    "nm_format_bound", "nm_format_sign_test"]
 
 
 class NmError(RuntimeError):
@@ -57,6 +58,13 @@ TABLE_DTYPES = {"row_pos_index": "int32", "n0": "int32", "n1": "int32", "ks_dnum
                 "fisher_p": "float64", "stouffer_stat": "float64", "stouffer_p": "float64",
                 "flags": "uint8", "moments": "float64"}
 TABLE_WIDTH = {"moments": 4}  # columns that hold several values per row
+
+
+class nm_text_columns(C.Structure):
+    _fields_ = [("seg_chrom", C.POINTER(C.c_char_p)), ("seg_strand", C.POINTER(C.c_char_p)), ("n_seg", C.c_int32),
+                ("reserved", C.c_int32), ("n_rows", C.c_int64)] + \
+               [(n, C.c_void_p) for n in ("seg", "pos", "base", "n0", "n1", "u_stat", "u_p", "t_stat", "t_p", "ks_d",
+                                          "ks_p", "comb_stat", "comb_p")]
 
 
 class nm_table(C.Structure):
@@ -105,6 +113,10 @@ def load():
     lib.nm_rank_host.restype = C.c_int
     lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                  C.c_void_p]
+    lib.nm_format_bound.restype = C.c_int64
+    lib.nm_format_bound.argtypes = [C.POINTER(nm_text_columns)]
+    lib.nm_format_sign_test.restype = C.c_int64
+    lib.nm_format_sign_test.argtypes = [C.POINTER(nm_text_columns), C.c_int, C.c_void_p, C.c_int64]
     lib.nm_pack_records_device.restype = C.c_int
     lib.nm_pack_records_device.argtypes = [C.c_void_p, C.POINTER(nm_table), C.c_int64, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p]
@@ -191,3 +203,41 @@ class Handle:
         """nm_pack_records_device: 28-byte result records of rows [row_lo, row_lo + n)."""
         self._check(self._lib.nm_pack_records_device(self._h, C.byref(table), int(row_lo), int(n), int(which_combine),
                                                      C.c_void_p(records), C.c_void_p(int(stream))))
+
+
+def format_sign_test(seg_names, seg, pos, base, n0, n1, u_stat, u_p, t_stat, t_p, ks_d, ks_p, comb_stat, comb_p,
+                     n_threads: int = 0):
+    """nm_format_sign_test: the text of ``<FileID>_sign_test.txt`` for these columns (numpy arrays;
+    optional ones may be None) as a uint8 numpy array.  Host code only -- needs the library, not a
+    GPU."""
+    import numpy as np
+    lib = load()
+    n = int(len(pos))
+    if n == 0:
+        return np.zeros(0, np.uint8)
+    keep = []
+
+    def arr(x, dt):
+        if x is None:
+            return None
+        a = np.ascontiguousarray(x, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+    chrom = (C.c_char_p * len(seg_names))(*[str(k[0]).encode() for k in seg_names])
+    strand = (C.c_char_p * len(seg_names))(*[str(k[1]).encode() for k in seg_names])
+    cols = nm_text_columns(chrom, strand, len(seg_names), 0, n, arr(seg, np.int32), arr(pos, np.int32),
+                           arr(base, np.uint8), arr(n0, np.int32), arr(n1, np.int32), arr(u_stat, np.float64),
+                           arr(u_p, np.float64), arr(t_stat, np.float64), arr(t_p, np.float64),
+                           arr(ks_d, np.float64), arr(ks_p, np.float64), arr(comb_stat, np.float64),
+                           arr(comb_p, np.float64))
+    if n_threads <= 0:
+        n_threads = min(32, os.cpu_count() or 1)
+    cap = n * 160 + int(lib.nm_format_bound(C.byref(cols)))
+    while True:
+        buf = np.empty(cap, np.uint8)
+        got = int(lib.nm_format_sign_test(C.byref(cols), int(n_threads), C.c_void_p(buf.ctypes.data), cap))
+        if got >= 0:
+            return buf[:got]
+        if got == -1:
+            raise NmError(1, "nm_format_sign_test: bad argument")
+        cap = -got

@@ -330,7 +330,7 @@ NM_HD constexpr int nm_lane_class(int n) {
 }
 
 // Dispatch a runtime network size (a value of nm_lane_class) to a template.
-#ifdef NM_ONLY_N  // analysis builds: a single network size (SASS inspection, tools/sass_hist.py)
+#ifdef NM_ONLY_N  // analysis builds: a single network size (SASS inspection with cuobjdump)
 #define NM_DISPATCH_N(nsel, CALL) { CALL(NM_ONLY_N); }
 #else
 #define NM_DISPATCH_N(nsel, CALL) \

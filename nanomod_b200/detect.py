@@ -214,6 +214,18 @@ class SignTestTable:
             lines.append(s)
         return lines
 
+    def format_text(self, n_threads: int = 0) -> bytes:
+        """The same text as ``''.join(format_lines())``, produced by the library's multithreaded
+        native writer (nm_format_sign_test): the reference formats and flushes one line at a time."""
+        return self._format_text_array(n_threads).tobytes()
+
+    def _format_text_array(self, n_threads: int = 0) -> np.ndarray:
+        comb = self.comb()
+        with_comb = self.options.neighborPvalues > 0 and comb is not None
+        return _lib.format_sign_test(self.seg_names, self.seg, self.pos, self.base, self.n0, self.n1, self.u_stat,
+                                     self.u_p, self.t_stat, self.t_p, self.ks_d, self.ks_p,
+                                     comb[0] if with_comb else None, comb[1] if with_comb else None, n_threads)
+
     def save_test(self, path: Optional[str] = None) -> Optional[str]:
         """Write ``<outFolder>/<FileID>_sign_test.txt`` when SaveTest != 0."""
         if self.options.SaveTest == 0:
@@ -221,8 +233,8 @@ class SignTestTable:
         if path is None:
             os.makedirs(self.options.outFolder, exist_ok=True)
             path = self.options.outFolder + "/" + self.options.FileID + "_sign_test.txt"
-        with open(path, "w") as f:
-            f.writelines(self.format_lines())
+        with open(path, "wb") as f:
+            f.write(self._format_text_array())
         self.save_meanstd()  # the reference writes both files from save_test (:540-545)
         return path
 

@@ -297,3 +297,41 @@ def test_region_rank_mode_matches_oracle(ovlp, na, rank, method):
     want = [(m[0][0], m[0][1], m[0][2]) for m in mo["sorted_sign_test"]]
     assert len(want) > (5 if na else 20)
     assert got == want
+
+
+@pytest.mark.parametrize("method,nb", [("stouffer", 2), ("fisher", 3), ("ks", 2), ("stouffer", 0)])
+def test_native_table_text_equals_python_format(method, nb, tmp_path):
+    """nm_format_sign_test (host threads in the library) against SignTestTable.format_lines, which
+    is the reference's '%' formatting (myDetect.py:522-538) -- including the values that test
+    printf: infinities, NaN, -0.0, DBL_MIN, DBL_MAX, denormals, exact halves."""
+    rng = np.random.default_rng(4)
+    n = 5000
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 2.2250738585072014e-308, 1.7976931348623157e308, 5e-324,
+                        0.0005, 0.0015, 0.0025, 1.0005, 2.5, 0.125, 1e-5, 9.9995, 9.9995e-7, 123456.7895, -1e15])
+
+    def col():
+        x = rng.normal(0, 1, n) * 10.0 ** rng.integers(-12, 6, n)
+        idx = rng.choice(n, 400, replace=False)
+        x[idx] = rng.choice(special, 400)
+        return x
+    opt = nm.DetectOptions(neighborPvalues=nb, testMethod=method, outFolder=str(tmp_path), FileID="nat")
+    kw = {}
+    if method != "ks":
+        kw = {method + "_stat": col(), method + "_p": np.abs(col())}
+    t = SignTestTable(options=opt, seg_names=[("chrI", "+"), ("chrI", "-"), ("a_very_long_contig_name_0123456789", "+")],
+                      seg=np.sort(rng.integers(0, 3, n)).astype(np.int32), pos=rng.integers(0, 2**31 - 2, n).astype(np.int32),
+                      base=rng.choice(np.frombuffer(b"ACGT", np.uint8), n), n0=rng.integers(3, 5000, n).astype(np.int32),
+                      n1=rng.integers(3, 5000, n).astype(np.int32), ks_dnum=np.zeros(n, np.int32), ks_d=np.abs(col()),
+                      ks_p=np.abs(col()), u_stat=col(), u_p=np.abs(col()), t_stat=col(), t_p=np.abs(col()), **kw)
+    want = "".join(t.format_lines()).encode()
+    for threads in (1, 3, 16):
+        assert t.format_text(threads) == want
+    path = t.save_test()
+    assert open(path, "rb").read() == want
+    # columns that were not computed print as zeros, as in format_lines
+    t2 = SignTestTable(options=opt, seg_names=t.seg_names, seg=t.seg, pos=t.pos, base=t.base, n0=t.n0, n1=t.n1,
+                       ks_dnum=t.ks_dnum, ks_d=t.ks_d, ks_p=t.ks_p, **kw)
+    assert t2.format_text() == "".join(t2.format_lines()).encode()
+    empty = SignTestTable(options=opt, seg_names=t.seg_names, seg=t.seg[:0], pos=t.pos[:0], base=t.base[:0], n0=t.n0[:0],
+                          n1=t.n1[:0], ks_dnum=t.ks_dnum[:0], ks_d=t.ks_d[:0], ks_p=t.ks_p[:0])
+    assert empty.format_text() == b""
