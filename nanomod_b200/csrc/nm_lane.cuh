@@ -324,6 +324,96 @@ NM_HD double nm_build_weights(int nb, double weights_dif, double* w /* [nb+1] */
   return sqrt(s);
 }
 
+// ------------------------------------------------------------------------------------------
+// Plain-C++ statement of the KS-only fast walks of nm_lane_kernel.cu (nm_walk_ks_fast and
+// nm_walk_ks_fast4 are spelled in inline PTX there).  Same chains, same start states, same
+// evaluation points, same requirements on the trip count -- kept here so that the algorithm is
+// checked against the oracle on the CPU (tests/test_host_emul.py); the kernel does not call it.
+// Columns with stride S: row 0 = -inf, rows 1..n = sorted keys, rows n+1.. = +inf.
+//   forward step : take the smaller head (ties: group 0), evaluate |i*T - m*n0| (i = group-0
+//                  elements taken, m = all elements taken) when the next pooled value is larger
+//   backward step: take the larger tail (ties: group 1), evaluate |i*T - r*n0| (i, r = group-0 /
+//                  all elements remaining) when the next pooled value below is smaller
+// ------------------------------------------------------------------------------------------
+struct nm_chain {
+  int ia, ib;     // forward: heads (rows ia+1 / ib+1); backward: tails (rows ia / ib)
+  nm_key va, vb;  // their values
+  nm_key v;       // value of the element taken last (start: see nm_walk_ks4)
+  int m;          // forward: elements taken so far; backward: elements remaining
+};
+
+template <int S>
+NM_HD void nm_chain_fwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int n0, int T, int* dmax) {
+  const bool p = c.va <= c.vb;
+  if (p) { ++c.ia; c.va = colA[(c.ia + 1) * S]; } else { ++c.ib; c.vb = colB[(c.ib + 1) * S]; }
+  ++c.m;
+  const nm_key vn = nm_min(c.va, c.vb);
+  const bool q = vn > c.v;
+  c.v = vn;
+  int d = c.ia * T - c.m * n0;
+  d = d < 0 ? -d : d;
+  if (q && d > *dmax) *dmax = d;
+}
+
+template <int S>
+NM_HD void nm_chain_bwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int n0, int T, int* dmax) {
+  const bool p = c.vb >= c.va;
+  if (p) { --c.ib; c.vb = colB[c.ib * S]; } else { --c.ia; c.va = colA[c.ia * S]; }
+  --c.m;
+  const nm_key wn = nm_max(c.va, c.vb);
+  const bool q = wn < c.v;
+  c.v = wn;
+  int d = c.ia * T - c.m * n0;
+  d = d < 0 ? -d : d;
+  if (q && d > *dmax) *dmax = d;
+}
+
+// two chains meeting in the middle; iters >= ceil(T/2) and iters <= T
+template <int S>
+NM_HD int nm_walk_ks2(const nm_key* colA, const nm_key* colB, int n0, int n1, int iters) {
+  const int T = n0 + n1;
+  nm_chain f = {0, 0, colA[S], colB[S], nm_min(colA[S], colB[S]), 0};
+  nm_chain b = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max(colA[n0 * S], colB[n1 * S]), T};
+  int dmax = 0;
+  for (int s = 0; s < iters; ++s) {
+    nm_chain_fwd<S>(f, colA, colB, n0, T, &dmax);
+    nm_chain_bwd<S>(b, colA, colB, n0, T, &dmax);
+  }
+  return dmax;
+}
+
+// four chains: merge-path split of the pooled order at h = T/2 (ties: group 0 first), a forward
+// and a backward chain per half; 2*it >= ceil(T/2), it <= T/2, 2^search_iters > max(n0, n1)
+template <int S>
+NM_HD int nm_walk_ks4(const nm_key* colA, const nm_key* colB, int n0, int n1, int it, int search_iters) {
+  const int T = n0 + n1, h = T >> 1;
+  int lo = h - n1 > 0 ? h - n1 : 0, hi = h < n0 ? h : n0;
+  for (int k = 0; k < search_iters; ++k) {
+    const int mid = (lo + hi) >> 1;
+    const bool P = colB[(h - mid) * S] < colA[(mid + 1) * S];
+    hi = P ? mid : hi;
+    lo = P ? lo : mid + 1;
+  }
+  const int is = lo, js = h - lo;
+  nm_chain f1 = {0, 0, colA[S], colB[S], nm_min(colA[S], colB[S]), 0};
+  nm_chain b1 = {is, js, colA[is * S], colB[js * S], nm_max(colA[is * S], colB[js * S]), h};
+  nm_chain f2 = {is, js, colA[(is + 1) * S], colB[(js + 1) * S], nm_min(colA[(is + 1) * S], colB[(js + 1) * S]), h};
+  nm_chain b2 = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max(colA[n0 * S], colB[n1 * S]), T};
+  int dmax = 0;
+  {  // the boundary between pooled elements h-1 and h belongs to neither half's chains
+    int dj = is * T - h * n0;
+    dj = dj < 0 ? -dj : dj;
+    if (b1.v < f2.v) dmax = dj;
+  }
+  for (int s = 0; s < it; ++s) {
+    nm_chain_fwd<S>(f1, colA, colB, n0, T, &dmax);
+    nm_chain_bwd<S>(b1, colA, colB, n0, T, &dmax);
+    nm_chain_fwd<S>(f2, colA, colB, n0, T, &dmax);
+    nm_chain_bwd<S>(b2, colA, colB, n0, T, &dmax);
+  }
+  return dmax;
+}
+
 // Network size (class) for a longest row of n values: 8, 12, ..., 104, 112, 120, 128.
 NM_HD constexpr int nm_lane_class(int n) {
   return n <= 8 ? 8 : n <= NM_LANE_FINE_MAX ? (n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP : (n + 7) / 8 * 8;

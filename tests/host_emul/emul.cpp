@@ -51,6 +51,29 @@ void lane_position(const float* a, int n0, const float* b, int n1, bool want_u, 
 
 extern "C" {
 
+// KS numerator by the two-chain / four-chain fast walks (plain-C++ statement of the kernel's PTX
+// walks) on already sorted groups.  tmax >= n0 + n1 plays the longest row of the warp: the
+// trip counts are derived from it exactly as nm_lane_kernel does.  Returns -1 if the walk's
+// precondition (the kernel's `fast` test) does not hold for this row.
+int emul_fast_walk(const float* a_sorted, int n0, const float* b_sorted, int n1, int tmax, int chains) {
+  const int nmax = n0 > n1 ? n0 : n1;
+  std::vector<nm_key> sa(nmax + 2 + 4, (nm_key)NM_KEY_PINF), sb(nmax + 2 + 4, (nm_key)NM_KEY_PINF);
+  sa[0] = sb[0] = NM_KEY_NINF;
+  for (int k = 0; k < n0; ++k) sa[k + 1] = nm_make_key(a_sorted[k]);
+  for (int k = 0; k < n1; ++k) sb[k + 1] = nm_make_key(b_sorted[k]);
+  const int T = n0 + n1;
+  if (chains == 2) {
+    const int iters = (tmax + 1) >> 1;
+    if (T < iters) return -1;
+    return nm_walk_ks2<1>(sa.data(), sb.data(), n0, n1, iters);
+  }
+  const int it4 = (tmax + 3) >> 2;
+  if ((T >> 1) < it4) return -1;
+  int bits = 0;
+  while ((1 << bits) <= nmax) ++bits;  // 32 - clz(nmax)
+  return nm_walk_ks4<1>(sa.data(), sb.data(), n0, n1, it4, bits);
+}
+
 int emul_lane_position(const float* a, int n0, const float* b, int n1, int want_u, int want_t,
                        nm_row_out* out) {
   const int nmax = n0 > n1 ? n0 : n1;

@@ -143,3 +143,34 @@ def test_special_functions_against_golden_and_scipy(emul):
         assert rel_err(emul.emul_chi2_sf_even(x, k), want) < 1e-11
     for z, want in GOLD["special"]["ndtr"]:
         assert rel_err(emul.emul_norm_sf(z), want) < 1e-13
+
+
+@pytest.mark.parametrize("chains", [2, 4])
+def test_fast_walks_match_oracle(emul, chains):
+    """The KS-only fast walks of the lane kernel (two chains; four chains with a merge-path split),
+    in their plain-C++ statement, against the oracle's searchsorted form: ties inside and across
+    groups, every split position, trip counts taken from a longer row of the same warp."""
+    import ctypes
+    rng = np.random.default_rng(9 + chains)
+    f = emul.emul_fast_walk
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int,
+                  ctypes.c_int, ctypes.c_int]
+    ran = 0
+    for case in range(1500):
+        n0, n1 = int(rng.integers(3, 129)), int(rng.integers(3, 129))
+        dec = int(rng.choice([0, 1, 2, 6]))
+        a = np.sort(np.round(rng.normal(0, 1, n0), dec).astype(np.float32))
+        b = np.sort(np.round(rng.normal(rng.choice([0, 0.5, 3.0, -9.0]), 1, n1), dec).astype(np.float32))
+        if case % 7 == 0:
+            b[:] = a[rng.integers(0, n0, n1)]
+            b.sort()
+        tmax = n0 + n1 + int(rng.choice([0, 0, 1, 5, 40]))
+        got = f(a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n0, b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n1,
+                tmax, chains)
+        if got < 0:
+            continue
+        ran += 1
+        want = o.per_position(a.astype(np.float64), b.astype(np.float64))["dnum"]
+        assert got == want, (case, n0, n1, tmax, got, want)
+    assert ran > 1000
