@@ -370,14 +370,19 @@ class SignTestTable:
 
     # ---- called sites (mboxplot :279-297 + plot1 :153-164) ---------------------------------
     def called_sites(self) -> List[Tuple[str, str, int]]:
-        nb = self.options.neighborPvalues
-        closesize = nb * 2
-        nearby = self.options.half_window
+        o = self.options
+        closesize = o.neighborPvalues * 2
+        # region mode: mtest2 leaves moptions['window'] incremented by one (:465); mboxplot then
+        # uses closesize = window (:280-282) and plot1 2*window rows either side (:153-154)
+        nearby = o.half_window + (1 if o.RegionRankbyST != 0 else 0)
+        if o.RegionRankbyST == 1:
+            closesize = max(1, nearby)
+            nearby = 2 * nearby
         n = len(self)
         out: List[Tuple[str, str, int]] = []
         acc_seg: List[int] = []
         acc_pos: List[int] = []
-        for r in self.ranked():
+        for r in self.sorted_rows():
             r = int(r)
             sg, ps = int(self.seg[r]), int(self.pos[r])
             if any(s == sg and abs(p - ps) < closesize for s, p in zip(acc_seg, acc_pos)):

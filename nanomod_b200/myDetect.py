@@ -44,9 +44,20 @@ def _detector(moptions: Dict) -> Detector:
     return det
 
 
+OUTPUT_ERROR = 3  # myCom.py:6
+
+
 def _run(moptions: Dict) -> SignTestTable:
     opt = DetectOptions.from_moptions(moptions)
-    pileup = Pileup.from_dicts(moptions[moptions["ds2"][0]], moptions[moptions["ds2"][1]])
+    ds0, ds1 = moptions[moptions["ds2"][0]], moptions[moptions["ds2"][1]]
+    pileup = Pileup.from_dicts(ds0, ds1)
+    if moptions.get("outLevel", 2) <= OUTPUT_ERROR:  # the diagnostic of myDetect.py:432-434
+        for sk, pk, b1, b0 in pileup.base_mismatch:
+            extra = []
+            for ds in (ds1, ds0):
+                bd = ds.get("basedict")
+                extra.append(list(bd[sk][pk].items()) if bd is not None else [])
+            print("Error not equal", sk, pk, b1, b0, extra[0], extra[1])
     return _detector(moptions).detect(pileup, opt)
 
 

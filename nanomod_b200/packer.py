@@ -27,9 +27,17 @@ from .pileup import Pileup
 
 SegKey = Tuple[str, str]
 
-# HDF5 locations of the Annotate stage's output (myFast5.py:80-113, myCom.py:61-63)
-FAST5_EVENTS = "/Analyses/RawGenomeCorrected_000/BaseCalled_template/Events"
-FAST5_ALIGNMENT = "/Analyses/RawGenomeCorrected_000/BaseCalled_template/Alignment"
+# HDF5 locations of the Annotate stage's output, assembled from the same constants as the
+# reference: myCom.py:35-56 (analyses_base, the NanoMod override of rawGenomeCorrected_base at
+# :48-51 -- "NanomoCorrected_000", NOT nanoraw's "RawGenomeCorrected_000" --
+# rawBaseCalled_template_base, rawAlignment_base, raw_event_base) and myFast5.py:92,113.
+ANALYSES_BASE = "Analyses"
+FAST5_MO_CORRECTION = "NanomoCorrected_000"          # myCom.py:48, :51
+RAW_BASECALLED_TEMPLATE_BASE = "BaseCalled_template"  # myCom.py:52
+RAW_ALIGNMENT_BASE = "Alignment"                      # myCom.py:53
+RAW_EVENT_BASE = "Events"                             # myCom.py:56
+FAST5_EVENTS = "/%s/%s/%s/%s" % (ANALYSES_BASE, FAST5_MO_CORRECTION, RAW_BASECALLED_TEMPLATE_BASE, RAW_EVENT_BASE)
+FAST5_ALIGNMENT = "/%s/%s/%s/%s" % (ANALYSES_BASE, FAST5_MO_CORRECTION, RAW_BASECALLED_TEMPLATE_BASE, RAW_ALIGNMENT_BASE)
 
 
 @dataclass

@@ -33,6 +33,9 @@ class Pileup:
     seg: np.ndarray            # int32 [n_pos], index into seg_names, non-decreasing
     base: np.ndarray           # uint8 [n_pos], ASCII of group 1's base (myDetect.py:436)
     seg_names: List[SegKey] = field(default_factory=list)
+    # positions whose recorded base differs between the groups: (segment key, pos, base of group 1,
+    # base of group 0) -- what mtest2 reports as 'Error not equal' (myDetect.py:432-434)
+    base_mismatch: List[Tuple[SegKey, int, str, str]] = field(default_factory=list)
 
     @property
     def n_pos(self) -> int:
@@ -57,6 +60,8 @@ class Pileup:
         assert self.vals0.shape[0] >= padded_len(self.off0[-1])
         assert self.vals1.shape[0] >= padded_len(self.off1[-1])
         assert np.all(np.diff(self.seg) >= 0) and (n == 0 or self.seg.min() >= 0)
+        # the device indexes per-segment arrays (seg_cov, chromosome names) with these ids
+        assert n == 0 or int(self.seg.max()) < len(self.seg_names), "segment id without a seg_names entry"
 
     # ---- construction -------------------------------------------------------------------
     @staticmethod
@@ -83,7 +88,8 @@ class Pileup:
             v1 = cls._pad(v1[:off1[-1]])
         p = cls(np.ascontiguousarray(v0), off0, np.ascontiguousarray(v1), off1, pos, seg,
                 np.ascontiguousarray(base, dtype=np.uint8),
-                list(seg_names) if seg_names is not None else [("syn", "+")])
+                list(seg_names) if seg_names is not None else
+                [("syn", "+")] + [("syn%d" % k, "+") for k in range(1, int(seg.max()) + 1 if n else 1)])
         p.validate()
         return p
 
@@ -101,6 +107,7 @@ class Pileup:
         c1: List[int] = []
         chunks0: List[np.ndarray] = []
         chunks1: List[np.ndarray] = []
+        mismatch: List[Tuple[SegKey, int, str, str]] = []
         for sk in sorted(ds0["norm_mean"].keys()):
             if sk not in ds1["norm_mean"]:
                 continue
@@ -115,6 +122,8 @@ class Pileup:
                 pos.append(pk)
                 seg.append(sid)
                 base.append(ord(ds1["base"][sk][pk]))
+                if ds1["base"][sk][pk] != ds0["base"][sk][pk]:
+                    mismatch.append((sk, pk, ds1["base"][sk][pk], ds0["base"][sk][pk]))
                 c0.append(a.shape[0])
                 c1.append(b.shape[0])
                 chunks0.append(a)
@@ -125,8 +134,10 @@ class Pileup:
         np.cumsum(c1, out=off1[1:])
         v0 = np.concatenate(chunks0) if chunks0 else np.zeros(0, np.float32)
         v1 = np.concatenate(chunks1) if chunks1 else np.zeros(0, np.float32)
-        return cls.from_arrays(v0, off0, v1, off1, np.asarray(pos, np.int32),
-                               np.asarray(seg, np.int32), np.asarray(base, np.uint8), seg_names)
+        p = cls.from_arrays(v0, off0, v1, off1, np.asarray(pos, np.int32),
+                            np.asarray(seg, np.int32), np.asarray(base, np.uint8), seg_names)
+        p.base_mismatch = mismatch
+        return p
 
     def to_dicts(self) -> Tuple[Dict, Dict]:
         """Inverse of from_dicts (float32 values upcast to Python floats) -- used to feed the
