@@ -184,9 +184,15 @@ int nm_set_sm_limit(nm_handle* h, int n_sms);
 int nm_sm_count(const nm_handle* h);
 
 /* Device time (ms, CUDA events on the call's stream) of the most recent nm_detect_* call:
- * ms4[0] plan kernels, [1] lane-tier (or pair-tier) kernel, [2] deep-tier kernel + the U/t tails
+ * ms4[0] plan kernels, [1] lane-tier kernel, [2] deep-tier kernel + the U/t tails
  * kernel, [3] combine kernel. */
 int nm_last_timings(const nm_handle* h, double* ms4);
+
+/* Which code path the most recent nm_detect_* call took: 0 general (plan + compaction, lane /
+ * deep tiers, combine), 1 dense (rows == candidates: no compaction pass, no indirection),
+ * 2 dense launched on the previous call's shape without waiting for the plan summary,
+ * 3 such a launch refused by the device-side check and the call re-run on the general path. */
+int nm_last_path(const nm_handle* h);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -99,6 +99,8 @@ def load():
     lib.nm_set_sm_limit.argtypes = [C.c_void_p, C.c_int]
     lib.nm_sm_count.restype = C.c_int
     lib.nm_sm_count.argtypes = [C.c_void_p]
+    lib.nm_last_path.restype = C.c_int
+    lib.nm_last_path.argtypes = [C.c_void_p]
     lib.nm_last_timings.restype = C.c_int
     lib.nm_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.nm_detect_device.restype = C.c_int
@@ -166,6 +168,10 @@ class Handle:
     def set_sm_limit(self, n_sms: int) -> None:
         """Let the persistent lane kernel use only n_sms SMs (0 = all): leaves room for NCCL."""
         self._check(self._lib.nm_set_sm_limit(self._h, int(n_sms)))
+
+    def last_path(self) -> int:
+        """0 general, 1 dense, 2 dense (speculative launch), 3 speculative launch refused and re-run"""
+        return int(self._lib.nm_last_path(self._h))
 
     def last_timings(self):
         """Device ms of the last call: {'plan','lane','deep','combine'} (CUDA events)."""

@@ -15,12 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libnanomod_b200.so")
-UNITS = ["nm_api.cu", "nm_lane_kernel.cu", "nm_pair_kernel.cu", "nm_deep_kernel.cu", "nm_rank.cu", "nm_downsample.cu", "nm_format.cu"]
+UNITS = ["nm_api.cu", "nm_lane_kernel.cu", "nm_deep_kernel.cu", "nm_rank.cu", "nm_downsample.cu", "nm_format.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-# Default configuration of the lane tier (profiles/round1_variants.md): order-preserving int32
-# sort keys with the mixed ALU/FMA compare-exchange (CTA shape is chosen at launch).
-DEFAULT_DEFS = ("NM_INT_KEYS",)
+# Default configuration of the lane tier: float32 sort keys, compare-exchanges mixed 1:2 between
+# {FMNMX, FMNMX} (ALU pipe) and {FMNMX, a + b - min on the bit patterns as two IMADs} (FMA pipe).
+# No key conversion at all; measured 0.8 % faster than the int32-key form (-DNM_INT_KEYS) of
+# round 1 (profiles/round2_lane_variants.md).
+DEFAULT_DEFS = ("NM_FLOAT_IMAD",)
 
 
 def _deps():

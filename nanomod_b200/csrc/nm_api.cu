@@ -52,15 +52,20 @@ __device__ __forceinline__ int nm_block_excl_scan(int v, int* total) {
 
 __global__ void __launch_bounds__(NM_PLAN_THREADS)
 nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1, int64_t n_pos,
-              int mincov, int* __restrict__ block_count, nm_summary* __restrict__ sum) {
+              int mincov, const int32_t* __restrict__ seg, int n_seg, int* __restrict__ block_count,
+              nm_summary* __restrict__ sum) {
   const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
-  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0;
+  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0;
+  bool bad = false;
 #pragma unroll
   for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
     const int64_t p = p0 + k;
     if (p < n_pos) {
       const int64_t n0 = off0[p + 1] - off0[p];
       const int64_t n1 = off1[p + 1] - off1[p];
+      ++n_cand;
+      bad |= (n0 < 0) | (n1 < 0);
+      if (n_seg > 0) bad |= (unsigned)seg[p] >= (unsigned)n_seg;  // per-segment arrays are indexed with it
       if (n0 >= mincov && n1 >= mincov) {
         ++cnt;
         const int64_t m = n0 > n1 ? n0 : n1;
@@ -79,6 +84,12 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
   }
   int total;
   (void)nm_block_excl_scan(cnt, &total);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) sum->bad_input = 1;
+  {
+    int cand_total;
+    (void)nm_block_excl_scan(n_cand, &cand_total);
+    if (threadIdx.x == 0 && cand_total != total) atomicAdd(&sum->n_filtered, cand_total - total);
+  }
   max_lane = __reduce_max_sync(0xffffffffu, max_lane);
   max_slack = __reduce_max_sync(0xffffffffu, max_slack);
   max_deep = __reduce_max_sync(0xffffffffu, max_deep);
@@ -170,7 +181,7 @@ nm_plan_scatter(const int64_t* __restrict__ off0, const int64_t* __restrict__ of
 }
 
 // ------------------------------------------------------------------------------------------
-// tails: fp64 tails of the rank-sum and Welch tests for lane/pair-tier rows (mannwhitneyu and
+// tails: fp64 tails of the rank-sum and Welch tests for lane-tier rows (mannwhitneyu and
 // ttest_ind tails, bin/scripts/myDetect.py:331-337), from the integers / moments the sort kernels
 // left in scratch.  Deep rows are finished by nm_deep_kernel itself.
 // ------------------------------------------------------------------------------------------
@@ -227,6 +238,10 @@ struct nm_comb_args {
   const int32_t* row_n1;
   const int32_t* pos;
   const int32_t* seg;
+  const double* z_pre;     // norm.isf(ks_p) left by the dense lane kernel, or NULL
+  const double* ln_pre;    // ln(ks_p) left by the dense lane kernel, or NULL
+  const double* ks_d;      // the table's D column when present (nb == 0 returns the KS tuple)
+  const int32_t* seg_cov;  // down-sampling thresholds per segment (nb == 0, D of resampled rows), or NULL
   int64_t n_rows;
   int nb;
   int want_fisher, want_stouffer;
@@ -265,12 +280,11 @@ __global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_co
     double z = -INFINITY, l = 0.0;
     int ps = 0, sg = -1;
     if (r >= 0 && r < a.n_rows) {
-      const double p = a.ks_p[r];
-      const int32_t src = a.row_pos_index[r];
+      const int64_t src = a.row_pos_index ? (int64_t)a.row_pos_index[r] : r;  // dense path: row == candidate
       ps = a.pos[src];
       sg = a.seg[src];
-      if (a.want_stouffer) z = nm_norm_isf(p);
-      if (a.want_fisher) l = log(p);
+      if (a.want_stouffer) z = a.z_pre ? a.z_pre[r] : nm_norm_isf(a.ks_p[r]);
+      if (a.want_fisher) l = a.ln_pre ? a.ln_pre[r] : log(a.ks_p[r]);
     }
     z_s[t] = z;
     l_s[t] = l;
@@ -282,7 +296,23 @@ __global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_co
   if (r >= a.n_rows) return;
   if (nb == 0) {
     // get_combin_pvalue returns the KS tuple itself when neighborPvalues == 0 (:413)
-    const double d = (double)a.ks_dnum[r] / ((double)a.row_n0[r] * (double)a.row_n1[r]);
+    // D as the table has it; without that column it is rebuilt from the numerator, which for a
+    // down-sampled row is relative to the resampled sizes min(n, cov) (nm_downsample.cu)
+    double d;
+    if (a.ks_d) {
+      d = a.ks_d[r];
+    } else {
+      int m0 = a.row_n0[r], m1 = a.row_n1[r];
+      if (a.seg_cov) {
+        const int64_t src = a.row_pos_index ? (int64_t)a.row_pos_index[r] : r;
+        const int cov = a.seg_cov[a.seg[src]];
+        if (cov > 0 && (m0 > cov || m1 > cov)) {
+          m0 = m0 < cov ? m0 : cov;
+          m1 = m1 < cov ? m1 : cov;
+        }
+      }
+      d = nm_max_float((double)a.ks_dnum[r] / ((double)m0 * (double)m1));
+    }
     const double p = a.ks_p[r];
     if (a.want_fisher) { a.f_stat[r] = d; a.f_p[r] = p; }
     if (a.want_stouffer) { a.s_stat[r] = d; a.s_p[r] = p; }
@@ -317,8 +347,12 @@ struct nm_handle {
   nm_buf d_perm[2], d_class_scratch;  // class binning of the lane tier (nm_class_sort_run)  // nm_rank_*: scratch, staged key columns, result
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
-  int use_pair_tier;   // NANOMOD_B200_PAIR_TIER=1: two lanes per position for long rows (experimental)
   int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
+  int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
+  int dense_class;     // network class of the previous call when it had the dense shape (else 0): the next
+                       // call is launched on that assumption without waiting for its plan summary
+  int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 speculative launch refused (re-run)
+  nm_buf d_comb_z, d_comb_ln;
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -380,6 +414,8 @@ extern "C" int nm_last_timings(const nm_handle* h, double* ms4) {
   return NM_OK;
 }
 
+extern "C" int nm_last_path(const nm_handle* h) { return h ? h->last_path : -1; }
+
 extern "C" int nm_create(int device, nm_handle** out) {
   if (!out) return nm_fail(nullptr, NM_ERR_BAD_ARG, "nm_create: out is NULL");
   *out = nullptr;
@@ -402,10 +438,10 @@ extern "C" int nm_create(int device, nm_handle** out) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   {
-    const char* f = getenv("NANOMOD_B200_PAIR_TIER");
-    h->use_pair_tier = (f && f[0] == '1') ? 1 : 0;
     const char* g = getenv("NANOMOD_B200_NO_CLASS_SORT");
     h->no_class_sort = (g && g[0] == '1') ? 1 : 0;
+    const char* d = getenv("NANOMOD_B200_NO_DENSE");
+    h->no_dense = (d && d[0] == '1') ? 1 : 0;
   }
   int rc = NM_OK;
   do {
@@ -430,7 +466,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -475,20 +511,13 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
     nm_kargs kl = ka;
     kl.perm = perm;
     kl.gaps = (perm != nullptr || n_deep > 0 || n_rows != n_pos) ? 1 : 0;
-    // The pair tier (two lanes per position for long rows; KS and Welch t only) is an experiment:
-    // it doubles residency and halves the code footprint, but needs 25 % more instructions and
-    // measured slower than the lane tier in round 1 (profiles/round1_variants.md).  Off unless
-    // NANOMOD_B200_PAIR_TIER=1.
-    const bool pair = h->use_pair_tier && !perm && !want_u && max_lane_n > 64 && nm_pair_tier_available();
-    if (pair || !perm) {
+    if (!perm) {
       kl.row_lo = 0;
       kl.row_hi = n_rows;
       kl.tile_cursor = &h->d_sum->tile_cursor[0];
-      const cudaError_t e = (cudaError_t)(pair ? nm_launch_pair(kl, want_m, max_lane_n, sms, st)
-                                               : nm_launch_lane(kl, want_u, want_m, max_lane_n, sms, st));
+      const cudaError_t e = (cudaError_t)nm_launch_lane(kl, want_u, want_m, max_lane_n, sms, st);
       if (e != cudaSuccess)
-        return nm_fail(h, NM_ERR_CUDA, "%s launch failed: %s", pair ? "nm_pair_kernel" : "nm_lane_kernel",
-                       cudaGetErrorString(e));
+        return nm_fail(h, NM_ERR_CUDA, "nm_lane_kernel launch failed: %s", cudaGetErrorString(e));
       h->launches++;
     } else {
       const int64_t n_lane = n_rows - n_deep;
@@ -529,6 +558,112 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   return NM_OK;
 }
 
+// the shape the dense lane kernel assumes (it re-checks the same conditions on the device)
+static bool nm_dense_shape(const nm_summary& s) {
+  return s.n_filtered == 0 && s.n_deep == 0 && s.bad_input == 0 && s.max_lane_n > 0 &&
+         nm_lane_group(NM_LANE_TIER_MAX - s.max_lane_slack) == nm_lane_group(s.max_lane_n);
+}
+
+static void nm_fill_comb_args(nm_comb_args* ca, const nm_pileup* pl, const nm_params& prm, const nm_table* tb,
+                              int64_t n_rows, bool ds_on) {
+  memset(ca, 0, sizeof(*ca));
+  ca->ks_p = tb->ks_p; ca->ks_dnum = tb->ks_dnum; ca->row_pos_index = tb->row_pos_index;
+  ca->row_n0 = tb->n0; ca->row_n1 = tb->n1; ca->pos = pl->pos; ca->seg = pl->seg;
+  ca->ks_d = tb->ks_d; ca->seg_cov = ds_on ? pl->seg_cov : nullptr;
+  ca->n_rows = n_rows; ca->nb = prm.nb;
+  ca->want_fisher = (prm.combine & NM_COMBINE_FISHER) != 0; ca->want_stouffer = (prm.combine & NM_COMBINE_STOUFFER) != 0;
+  ca->wnorm = nm_build_weights(prm.nb, prm.weights_dif, ca->w);
+  ca->f_stat = tb->fisher_stat; ca->f_p = tb->fisher_p; ca->s_stat = tb->stouffer_stat; ca->s_p = tb->stouffer_p;
+}
+
+// Dense path: plan_count has been launched; lane kernel (+ U/t tails) + combine stencil, one sync
+// at the end.  *refused is set when the kernel found another shape than `class_n` was sized for
+// (only possible for a speculative launch); nothing was computed then.
+static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb, int class_n,
+                        cudaStream_t st, nm_summary* sum_out, bool* refused) {
+  const bool want_u = prm.want_u != 0, want_t = prm.want_t != 0;
+  const bool want_f = (prm.combine & NM_COMBINE_FISHER) != 0, want_s = (prm.combine & NM_COMBINE_STOUFFER) != 0;
+  const int64_t n = pl->n_pos;
+  int rc;
+  nm_kargs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.vals0 = pl->vals0; ka.vals1 = pl->vals1; ka.off0 = pl->off0; ka.off1 = pl->off1;
+  ka.row_pos_index = tb->row_pos_index; ka.row_n0 = tb->n0; ka.row_n1 = tb->n1;
+  ka.w_row_pos_index = tb->row_pos_index; ka.w_n0 = tb->n0; ka.w_n1 = tb->n1;
+  ka.n_rows = n; ka.n_pos = n; ka.one = 1; ka.mone = -1;
+  ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
+  ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
+  ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
+  ka.sum = h->d_sum;
+  ka.tile_cursor = &h->d_sum->dense_tile_cursor;
+  if (want_u) {
+    if ((rc = nm_reserve(h, &h->d_acc_r2, sizeof(int) * (size_t)n)) != NM_OK) return rc;
+    if ((rc = nm_reserve(h, &h->d_acc_tie, sizeof(int) * (size_t)n)) != NM_OK) return rc;
+    ka.acc_r2 = (int*)h->d_acc_r2.p;
+    ka.acc_tie = (int*)h->d_acc_tie.p;
+  }
+  const bool want_m = want_t || tb->moments != nullptr;
+  if (tb->moments) {
+    ka.acc_mom = tb->moments;
+  } else if (want_t) {
+    if ((rc = nm_reserve(h, &h->d_acc_mom, sizeof(double) * 4 * (size_t)n)) != NM_OK) return rc;
+    ka.acc_mom = (double*)h->d_acc_mom.p;
+  }
+  if (prm.nb > 0 && want_s) {
+    if ((rc = nm_reserve(h, &h->d_comb_z, sizeof(double) * (size_t)n)) != NM_OK) return rc;
+    ka.comb_z = (double*)h->d_comb_z.p;
+  }
+  if (prm.nb > 0 && want_f) {
+    if ((rc = nm_reserve(h, &h->d_comb_ln, sizeof(double) * (size_t)n)) != NM_OK) return rc;
+    ka.comb_ln = (double*)h->d_comb_ln.p;
+  }
+  const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
+  cudaError_t e = (cudaError_t)nm_launch_lane_dense(ka, want_u, want_m, class_n, sms, st);
+  if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_lane_dense_kernel launch failed: %s", cudaGetErrorString(e));
+  h->launches++;
+  NM_CUDA(h, cudaEventRecord(h->ev[2], st));
+  if (want_u || want_t) {
+    nm_tails_args ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.row_n0 = tb->n0; ta.row_n1 = tb->n1;
+    ta.acc_r2 = ka.acc_r2; ta.acc_tie = ka.acc_tie; ta.acc_mom = ka.acc_mom;
+    ta.n_rows = n; ta.want_u = want_u; ta.want_t = want_t;
+    ta.two_u = tb->two_u; ta.u_stat = tb->u_stat; ta.u_p = tb->u_p; ta.t_stat = tb->t_stat; ta.t_p = tb->t_p;
+    ta.flags = tb->flags;
+    nm_tails_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ta);
+    NM_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  NM_CUDA(h, cudaEventRecord(h->ev[3], st));
+  if (want_f || want_s) {
+    nm_comb_args ca;
+    nm_fill_comb_args(&ca, pl, prm, tb, n, false);
+    ca.row_pos_index = nullptr;  // row == candidate
+    ca.z_pre = ka.comb_z;
+    ca.ln_pre = ka.comb_ln;
+    nm_combine_kernel<<<(unsigned)((n + NM_COMB_THREADS - 1) / NM_COMB_THREADS), NM_COMB_THREADS, 0, st>>>(ca);
+    NM_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  NM_CUDA(h, cudaEventRecord(h->ev[4], st));
+  NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  *sum_out = *h->h_sum;
+  *refused = sum_out->dense_retry != 0;
+  if (*refused) {
+    h->launches -= 1 + ((want_u || want_t) ? 1 : 0) + ((want_f || want_s) ? 1 : 0);  // they did not compute
+    // the refused kernels ran on an unvalidated shape: the tails / combine launches read rows the
+    // lane kernel never wrote, which is harmless (every column is rewritten by the general path)
+    return NM_OK;
+  }
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->last_ms[0] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->last_ms[1] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->last_ms[2] = ms;
+  if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->last_ms[3] = ms;
+  return NM_OK;
+}
+
 extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_params* params,
                                 const nm_table* tb, int64_t* n_rows_out, void* cuda_stream) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
@@ -561,33 +696,81 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   if ((rc = nm_reserve(h, &h->d_block_count, sizeof(int) * (size_t)nblk)) != NM_OK) return rc;
   if ((rc = nm_reserve(h, &h->d_deep_rows, sizeof(int32_t) * (size_t)n_pos)) != NM_OK) return rc;
 
-  // ---- plan: filter + ordered compaction
+  // ---- plan, first pass: coverage filter counts and the shape summary
   for (int k = 0; k < 4; ++k) h->last_ms[k] = 0.0;
   NM_CUDA(h, cudaEventRecord(h->ev[0], st));
   NM_CUDA(h, cudaMemsetAsync(h->d_sum, 0, sizeof(nm_summary), st));
-  nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
-                                                  (int*)h->d_block_count.p, h->d_sum);
-  nm_plan_scan<<<1, NM_PLAN_THREADS, 0, st>>>((int*)h->d_block_count.p, nblk, h->d_sum);
-  nm_plan_scatter<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
-                                                    (const int*)h->d_block_count.p, tb->row_pos_index,
-                                                    tb->n0, tb->n1, (int32_t*)h->d_deep_rows.p, h->d_sum);
+  nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage, pl->seg,
+                                                  pl->n_seg > 0 ? pl->n_seg : 0, (int*)h->d_block_count.p, h->d_sum);
   NM_CUDA(h, cudaGetLastError());
-  h->launches += 3;
+  h->launches += 1;
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
-  NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
-  NM_CUDA(h, cudaStreamSynchronize(st));
+
+  // ---- dense path: nothing filtered, nothing deep, one size group.  After a call of that shape
+  // the next one is launched on the same assumption WITHOUT waiting for its summary (the kernel
+  // validates it on the device and refuses to compute if it does not hold).
+  const bool dense_allowed = !h->no_dense && !ds_on;
+  nm_summary sum;
+  bool have_sum = false;
+  int dense_class = 0;
+  h->last_path = 0;
+  if (dense_allowed && h->dense_class > 0) {
+    dense_class = h->dense_class;
+    h->last_path = 2;
+  } else {
+    NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
+    NM_CUDA(h, cudaStreamSynchronize(st));
+    sum = *h->h_sum;
+    have_sum = true;
+    if (dense_allowed && nm_dense_shape(sum)) {
+      dense_class = nm_lane_class(sum.max_lane_n);
+      h->last_path = 1;
+    }
+  }
+  if (dense_class > 0) {
+    bool refused = false;
+    rc = nm_run_dense(h, pl, prm, tb, dense_class, st, &sum, &refused);
+    if (rc != NM_OK) return rc;
+    if (!refused) {
+      h->dense_class = nm_lane_class(sum.max_lane_n);
+      *n_rows_out = n_pos;
+      return NM_OK;
+    }
+    have_sum = true;  // nm_run_dense read the summary back
+    h->last_path = 3;
+    if (nm_dense_shape(sum)) {  // dense after all, only another network class: launch it again, sized right
+      NM_CUDA(h, cudaMemsetAsync(&h->d_sum->dense_retry, 0, 2 * sizeof(int), st));  // + dense_tile_cursor
+      rc = nm_run_dense(h, pl, prm, tb, nm_lane_class(sum.max_lane_n), st, &sum, &refused);
+      if (rc != NM_OK) return rc;
+      if (refused) return nm_fail(h, NM_ERR_CUDA, "internal: dense launch refused after validation");
+      h->dense_class = nm_lane_class(sum.max_lane_n);
+      *n_rows_out = n_pos;
+      return NM_OK;
+    }
+  }
+  h->dense_class = 0;
+  if (!have_sum) return nm_fail(h, NM_ERR_CUDA, "internal: plan summary missing");
+  if (sum.bad_input)
+    return nm_fail(h, NM_ERR_BAD_ARG, "offsets are not non-decreasing, or a segment id is outside [0, n_seg)");
+
+  // ---- plan, second pass: ordered compaction of the kept candidates into rows
   {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->last_ms[0] = ms;
   }
-  const nm_summary sum = *h->h_sum;
-  const int64_t n_rows = (int64_t)sum.n_rows;
+  const int64_t n_rows = n_pos - (int64_t)sum.n_filtered;
   *n_rows_out = n_rows;
   if (n_rows == 0) return NM_OK;
   if (sum.n_deep > 0 && sum.max_deep_p2 > NM_DEEP_TIER_MAX_POOLED)
     return nm_fail(h, NM_ERR_TOO_DEEP,
                    "a position has pow2(n0)+pow2(n1) = %d > %d values; deeper pileups are not supported",
                    sum.max_deep_p2, NM_DEEP_TIER_MAX_POOLED);
+  nm_plan_scan<<<1, NM_PLAN_THREADS, 0, st>>>((int*)h->d_block_count.p, nblk, h->d_sum);
+  nm_plan_scatter<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
+                                                    (const int*)h->d_block_count.p, tb->row_pos_index,
+                                                    tb->n0, tb->n1, (int32_t*)h->d_deep_rows.p, h->d_sum);
+  NM_CUDA(h, cudaGetLastError());
+  h->launches += 2;
 
   // ---- per-position tests
   nm_kargs ka;
@@ -667,12 +850,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   // ---- neighbour combination
   if (want_f || want_s) {
     nm_comb_args ca;
-    memset(&ca, 0, sizeof(ca));
-    ca.ks_p = tb->ks_p; ca.ks_dnum = tb->ks_dnum; ca.row_pos_index = tb->row_pos_index;
-    ca.row_n0 = tb->n0; ca.row_n1 = tb->n1; ca.pos = pl->pos; ca.seg = pl->seg;
-    ca.n_rows = n_rows; ca.nb = prm.nb; ca.want_fisher = want_f; ca.want_stouffer = want_s;
-    ca.wnorm = nm_build_weights(prm.nb, prm.weights_dif, ca.w);
-    ca.f_stat = tb->fisher_stat; ca.f_p = tb->fisher_p; ca.s_stat = tb->stouffer_stat; ca.s_p = tb->stouffer_p;
+    nm_fill_comb_args(&ca, pl, prm, tb, n_rows, ds_on);
     const unsigned grid = (unsigned)((n_rows + NM_COMB_THREADS - 1) / NM_COMB_THREADS);
     nm_combine_kernel<<<grid, NM_COMB_THREADS, 0, st>>>(ca);
     NM_CUDA(h, cudaGetLastError());

@@ -51,6 +51,9 @@ __device__ __forceinline__ void nm_bulk_g2s(void* dst, const void* src, uint32_t
 __device__ __forceinline__ void nm_cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nm_smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void nm_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(nm_smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void nm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void nm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -101,6 +104,10 @@ struct nm_summary {
   int ds_too_deep;      // set by nm_downsample_kernel: a qualifying row has more than NM_DS_MAX_READS reads
   int max_lane_slack;   // max over lane-tier rows of NM_LANE_TIER_MAX - max(n0,n1)  (-> shortest row)
   int n_le64, n_le104;  // class-binned calls: lane-tier rows whose network class is <= 64 / <= 104
+  int n_filtered;       // candidates dropped by the coverage filter (0 => rows == candidates)
+  int bad_input;        // a candidate with a negative read count (offsets not monotonic) / segment id out of range
+  int dense_retry;      // set by nm_lane_dense_kernel: the call does not have the shape the launch assumed
+  int dense_tile_cursor;
   int pad;
 };
 
@@ -131,7 +138,7 @@ struct nm_kargs {
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
   int* tile_cursor;   // device counter, zero at launch
-  // rank sums / moments of the lane and pair tiers; their fp64 tails (normal and Student-t
+  // rank sums / moments of the lane tier; their fp64 tails (normal and Student-t
   // tails: a lot of cold fp64 code) run afterwards in nm_tails_kernel, not inside the sort loop
   int* acc_r2;        // want_u: 2 * rank sum of group 0
   int* acc_tie;       // want_u: sum over tie groups of t^3 - t
@@ -147,6 +154,16 @@ struct nm_kargs {
   uint8_t* flags;
   const int32_t* deep_rows;
   int n_deep;
+  // dense path (nm_lane_dense_kernel): rows == candidates, no deep rows.  The kernel validates
+  // that against the plan summary on the device, writes the row index / coverage columns itself
+  // and leaves norm.isf(p) / ln p of the KS p-value for the combine stencil.
+  nm_summary* sum;
+  int64_t n_pos;
+  int32_t* w_row_pos_index;
+  int32_t* w_n0;
+  int32_t* w_n1;
+  double* comb_z;   // norm.isf(ks_p) per row (Stouffer), or NULL
+  double* comb_ln;  // ln(ks_p) per row (Fisher), or NULL
 };
 
 
@@ -229,6 +246,5 @@ int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, in
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st);
-// host-side launcher of the pair tier (nm_pair_kernel.cu): KS (+ Welch t), two lanes per position
-int nm_launch_pair(const nm_kargs& ka, bool want_t, int max_n, int sm_count, cudaStream_t st);
-bool nm_pair_tier_available();
+// dense variant: rows == candidates (nothing filtered, nothing deep); class_n = network class of the launch
+int nm_launch_lane_dense(const nm_kargs& ka, bool want_u, bool want_t, int class_n, int sm_count, cudaStream_t st);

@@ -59,7 +59,11 @@ NM_HD nm_key nm_make_key(float x) { return x; }
 NM_HD nm_key nm_make_key(float x, int) { return x; }
 #define NM_KEY_PINF INFINITY
 #define NM_KEY_NINF (-INFINITY)
+#ifdef NM_FLOAT_IMAD
+#define NM_CEB(i, j) nm_ceb(x[i], x[j], one, mone);
+#else
 #define NM_CEB(i, j) NM_CE(i, j)
+#endif
 #endif
 NM_HD float nm_min(float a, float b) { return fminf(a, b); }
 NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
@@ -71,11 +75,34 @@ NM_HD void nm_ceb(int& a, int& b, int one, int mone) {
   b = lo * mone + t;
   a = lo;
 }
+#ifdef NM_FLOAT_IMAD
+// Float keys, no key conversion: lo = fminf (FMNMX, ALU pipe); hi = a + b - lo on the raw bit
+// patterns as two IMADs (FMA pipe) -- exact because fminf returns one of its operands bit for
+// bit (inputs are finite or the +inf padding; -0.0 / +0.0 may come out in either order, which
+// the walk's float compares treat as the tie it is).
+NM_HD void nm_ceb(float& a, float& b, int one, int mone) {
+  const float lo = fminf(a, b);
+#if defined(__CUDA_ARCH__)
+  const int ia = __float_as_int(a), ib = __float_as_int(b), il = __float_as_int(lo);
+  const int t = ia * one + ib;
+  b = __int_as_float(il * mone + t);
+#else
+  int ia, ib, il;
+  memcpy(&ia, &a, 4);
+  memcpy(&ib, &b, 4);
+  memcpy(&il, &lo, 4);
+  const int hi = (int)((unsigned)il * (unsigned)mone + ((unsigned)ia * (unsigned)one + (unsigned)ib));
+  memcpy(&b, &hi, 4);
+#endif
+  a = lo;
+}
+#else
 NM_HD void nm_ceb(float& a, float& b, int, int) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
   a = lo;
   b = hi;
 }
+#endif
 
 #define NM_CE(i, j)                    \
   {                                    \
@@ -112,12 +139,6 @@ struct nm_sortloop;
 #include "nm_sortloop.inc"
 #undef NM_ROTATE
 
-// Pair tier (two lanes per position): half-size sorts + up-down merges (tools/gen_pairnet.py).
-template <int H>
-struct nm_halfsort;
-template <int H>
-struct nm_updown;
-#include "nm_pairnet.inc"
 #undef NM_CE
 #undef NM_CEB
 
@@ -417,6 +438,12 @@ NM_HD int nm_walk_ks4(const nm_key* colA, const nm_key* colB, int n0, int n1, in
 // Network size (class) for a longest row of n values: 8, 12, ..., 104, 112, 120, 128.
 NM_HD constexpr int nm_lane_class(int n) {
   return n <= 8 ? 8 : n <= NM_LANE_FINE_MAX ? (n + NM_LANE_STEP - 1) / NM_LANE_STEP * NM_LANE_STEP : (n + 7) / 8 * 8;
+}
+
+// Size group of a longest row of n values: the lane tier launches once per group when a call
+// mixes them (<= 64: 12+ warps/SM; <= 104: straight-line networks; <= 128: looped networks).
+NM_HD constexpr int nm_lane_group(int n) {
+  return nm_lane_class(n) <= 64 ? 0 : nm_lane_class(n) <= NM_LANE_FINE_MAX ? 1 : 2;
 }
 
 // Dispatch a runtime network size (a value of nm_lane_class) to a template.

@@ -563,6 +563,194 @@ nm_lane_kernel(const nm_kargs a, const int want_u, const int want_t) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Dense variant: rows == candidates (the coverage filter dropped nothing, no position is deeper
+// than the lane tier).  That is the normal shape of a call, and it removes every indirection of
+// the general kernel: row r IS candidate r, its slices are [off[r], off[r+1]), a tile's 32 rows
+// are always one contiguous span.  Per warp, shared memory additionally holds the 33 + 33 CSR
+// offsets of the current and of the next tile (double-buffered, fetched with cp.async one tile
+// ahead: no register is tied up, no load is waited for), from which the TMA copies of the next
+// tile are issued the moment the merge walk has released the regions.
+// The launch ASSUMES the shape (it may be issued before the plan summary has reached the host);
+// every warp validates the assumption against the device-side summary first and the kernel
+// raises `dense_retry` instead of computing when it does not hold.
+// Besides the KS columns the kernel writes row_pos_index / n0 / n1 (there is no scatter pass on
+// this path) and norm.isf(p) / ln p for the combine stencil (the fp64 pipe is idle here).
+// ------------------------------------------------------------------------------------------
+#define NM_DENSE_META_I64 (2 * 2 * 33)  // two buffers x (off0[33] + off1[33])
+
+__device__ __forceinline__ void nm_dense_meta_load(const nm_kargs& a, int64_t tile, long long* buf, int lane) {
+  // entries k = 0..32 of both offset arrays, index clamped to n_pos (rows past the end get n = 0)
+  const int64_t i0 = tile * 32 + lane;
+  const int64_t i = i0 < a.n_pos ? i0 : a.n_pos;
+  nm_cp_async8(buf + lane, a.off0 + i);
+  nm_cp_async8(buf + 33 + lane, a.off1 + i);
+  if (lane == 0) {
+    const int64_t j0 = tile * 32 + 32;
+    const int64_t j = j0 < a.n_pos ? j0 : a.n_pos;
+    nm_cp_async8(buf + 32, a.off0 + j);
+    nm_cp_async8(buf + 33 + 32, a.off1 + j);
+  }
+  nm_cp_async_commit();
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, NMAX <= 64 ? 4 : 2)
+nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
+  extern __shared__ __align__(128) unsigned char nm_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  {  // the shape this launch was sized for must be the shape the plan found
+    const nm_summary* S = a.sum;
+    const bool shape_ok = S->n_filtered == 0 && S->n_deep == 0 && S->bad_input == 0 &&
+                          nm_lane_class(S->max_lane_n) == a.class_n &&
+                          nm_lane_group(NM_LANE_TIER_MAX - S->max_lane_slack) == nm_lane_group(S->max_lane_n);
+    if (!shape_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.sum->dense_retry = 1;
+      return;
+    }
+  }
+  const size_t per_warp = 16 + NM_DENSE_META_I64 * sizeof(long long) + 2 * (size_t)a.region_floats * sizeof(float);
+  unsigned char* my = nm_smem + (size_t)wib * per_warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(my);
+  long long* meta = reinterpret_cast<long long*>(my + 16);
+  float* regA = reinterpret_cast<float*>(my + 16 + NM_DENSE_META_I64 * sizeof(long long));
+  float* regB = regA + a.region_floats;
+  const int64_t n_rows = a.n_pos;
+  const int64_t n_tiles = (n_rows + 31) >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
+
+  int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
+  if (tile >= n_tiles) return;
+  if (lane == 0) nm_mbar_init(bar, 1);
+  __syncwarp();
+  unsigned parity = 0;
+  int mb = 0;
+  nm_dense_meta_load(a, tile, meta, lane);
+  long long claim = 0;
+  if (lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+  bool staged = false;
+
+  while (true) {
+    const long long t = __shfl_sync(0xffffffffu, claim, 0);
+    const int64_t next = t < n_tiles ? t : -1;
+    const bool done = next < 0;
+    if (!done && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+
+    // ---- this tile's offsets (landed a tile ago), then the next tile's go on their way
+    nm_cp_async_wait_all();
+    __syncwarp();
+    const long long* m0 = meta + mb * 66;
+    const long long* m1 = m0 + 33;
+    const long long o0 = m0[lane], o1 = m1[lane];
+    const int n0 = (int)(m0[lane + 1] - o0), n1 = (int)(m1[lane + 1] - o1);
+    const long long al0 = m0[0] & ~3LL, al1 = m1[0] & ~3LL;
+    const unsigned bytes0 = (unsigned)((m0[32] - al0 + 3) & ~3LL) * 4u, bytes1 = (unsigned)((m1[32] - al1 + 3) & ~3LL) * 4u;
+    const int64_t r = tile * 32 + lane;
+    const bool ok = r < n_rows;
+    const int base0 = ok ? (int)(o0 - al0) : 0, base1 = ok ? (int)(o1 - al1) : 0;
+    if (!done) nm_dense_meta_load(a, next, meta + (mb ^ 1) * 66, lane);
+
+    if (!staged && lane == 0) {
+      nm_mbar_expect_tx(bar, bytes0 + bytes1);
+      nm_bulk_g2s(regA, a.vals0 + al0, bytes0, bar);
+      nm_bulk_g2s(regB, a.vals1 + al1, bytes1, bar);
+    }
+    nm_mbar_wait(bar, parity);
+    parity ^= 1u;
+    __syncwarp();
+
+    const int nmax = __reduce_max_sync(0xffffffffu, n0 > n1 ? n0 : n1);
+    const int tmax = __reduce_max_sync(0xffffffffu, n0 + n1);
+    int nsel = nm_lane_class(nmax);
+    if (2 * nmax > a.class_n) nsel = a.class_n;
+    nm_lane_acc acc;
+    acc.dnum = acc.r2 = acc.tie = 0;
+    acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
+    if (want_t) {
+      nm_lane_moments(regA, base0, n0, &acc.mean0, &acc.var0);
+      nm_lane_moments(regB, base1, n1, &acc.mean1, &acc.var1);
+    }
+#define NM_CALL(NN)                                                                          \
+  if (NN <= NMAX)                                                                            \
+    nm_lane_tile<(NN <= NMAX ? NN : NMAX)>(regA, regB, base0, base1, n0, n1, lane, a.one, a.mone)
+    NM_DISPATCH_N(nsel, NM_CALL)
+#undef NM_CALL
+
+    // ---- the next tile's span: known from its offsets (in shared memory by now); pull it into L2
+    long long nal0 = 0, nal1 = 0;
+    unsigned nbytes0 = 0, nbytes1 = 0;
+    if (!done) {
+      nm_cp_async_wait_all();
+      __syncwarp();
+      const long long* q0 = meta + (mb ^ 1) * 66;
+      const long long* q1 = q0 + 33;
+      nal0 = q0[0] & ~3LL;
+      nal1 = q1[0] & ~3LL;
+      nbytes0 = (unsigned)((q0[32] - nal0 + 3) & ~3LL) * 4u;
+      nbytes1 = (unsigned)((q1[32] - nal1 + 3) & ~3LL) * 4u;
+      if (lane == 0) {
+        nm_prefetch_l2(a.vals0 + nal0, nbytes0);
+        nm_prefetch_l2(a.vals1 + nal1, nbytes1);
+      }
+    }
+
+    const nm_key* colA = reinterpret_cast<const nm_key*>(regA) + lane;
+    const nm_key* colB = reinterpret_cast<const nm_key*>(regB) + lane;
+    const int iters = (tmax + 1) >> 1;
+    const int it4 = (tmax + 3) >> 2;
+    constexpr bool kFour = NMAX > 64;
+    const bool fast = kFour ? __all_sync(0xffffffffu, ((n0 + n1) >> 1) >= it4)
+                            : __all_sync(0xffffffffu, n0 + n1 >= iters);
+    if (want_u)
+      nm_merge_walk<true, 32>(colA, colB, n0, n1, iters, &acc);
+    else if (fast && kFour)
+      acc.dnum = nm_walk_ks_fast4(colA, colB, n0, n1, it4, 32 - __clz(nmax), a.one);
+    else if (fast)
+      acc.dnum = nm_walk_ks_fast(colA, colB, n0, n1, iters, a.one);
+    else
+      nm_merge_walk<false, 32>(colA, colB, n0, n1, iters, &acc);
+
+    // ---- the regions are free again: the next tile's copies overlap the fp64 tails
+    __syncwarp();
+    staged = false;
+    if (!done) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nm_mbar_expect_tx(bar, nbytes0 + nbytes1);
+        nm_bulk_g2s(regA, a.vals0 + nal0, nbytes0, bar);
+        nm_bulk_g2s(regB, a.vals1 + nal1, nbytes1, bar);
+      }
+      staged = true;
+    }
+
+    if (ok) {
+      double d, pv;
+      nm_ks_tail(acc.dnum, n0, n1, &d, &pv);
+      a.w_row_pos_index[r] = (int32_t)r;
+      a.w_n0[r] = n0;
+      a.w_n1[r] = n1;
+      a.ks_dnum[r] = acc.dnum;
+      if (a.ks_d) a.ks_d[r] = d;
+      a.ks_p[r] = pv;
+      if (a.comb_z) a.comb_z[r] = nm_norm_isf(pv);
+      if (a.comb_ln) a.comb_ln[r] = log(pv);
+      if (want_u) {
+        a.acc_r2[r] = acc.r2;
+        a.acc_tie[r] = acc.tie;
+      }
+      if (want_t) {
+        double4* mom = reinterpret_cast<double4*>(a.acc_mom) + r;
+        *mom = make_double4(acc.mean0, acc.var0, acc.mean1, acc.var1);
+      }
+      if (a.flags && !want_u) a.flags[r] = 0;
+    }
+    if (done) break;
+    tile = next;
+    mb ^= 1;
+  }
+}
+
 static int nm_lane_warp_smem(int region_floats) { return 16 + 2 * region_floats * (int)sizeof(float); }
 
 template <int NMAX>
@@ -631,4 +819,39 @@ int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, i
   ka.class_n = ncls;
   if (ncls <= 64) return nm_launch_lane_t<64>(ka, want_u, want_t, sm_count, st);
   return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
+}
+
+template <int NMAX>
+static int nm_launch_lane_dense_t(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
+  const int per_warp = 16 + NM_DENSE_META_I64 * (int)sizeof(long long) + 2 * ka.region_floats * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(nm_lane_dense_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       NM_LANE_MAX_WARPS * per_warp);
+  if (e != cudaSuccess) return (int)e;
+  int best_w = 1, best_blocks = 0, best_warps = 0;
+  for (int w = NM_LANE_MAX_WARPS; w >= 1; --w) {
+    int blocks = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_dense_kernel<NMAX>, 32 * w, (size_t)w * per_warp);
+    if (e != cudaSuccess) return (int)e;
+    if (blocks * w > best_warps) {
+      best_warps = blocks * w;
+      best_w = w;
+      best_blocks = blocks;
+    }
+  }
+  if (best_warps == 0) return (int)cudaErrorInvalidConfiguration;
+  const int64_t tiles = (ka.n_pos + 31) / 32;
+  int64_t grid = (tiles + best_w - 1) / best_w;
+  const int64_t resident = (int64_t)best_blocks * sm_count;
+  if (grid > resident) grid = resident;
+  nm_lane_dense_kernel<NMAX><<<(unsigned)grid, 32 * best_w, (size_t)best_w * per_warp, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+int nm_launch_lane_dense(const nm_kargs& ka_in, bool want_u, bool want_t, int class_n, int sm_count, cudaStream_t st) {
+  nm_kargs ka = ka_in;
+  if (ka.n_pos <= 0) return (int)cudaSuccess;
+  ka.region_floats = 32 * (class_n + 2);
+  ka.class_n = class_n;
+  if (class_n <= 64) return nm_launch_lane_dense_t<64>(ka, want_u, want_t, sm_count, st);
+  return nm_launch_lane_dense_t<128>(ka, want_u, want_t, sm_count, st);
 }

@@ -21,11 +21,12 @@ class RowOut(ctypes.Structure):
                 ("t_stat", ctypes.c_double), ("t_p", ctypes.c_double), ("flags", ctypes.c_int)]
 
 
-@pytest.fixture(scope="session", params=["float_keys", "int_keys"])
+@pytest.fixture(scope="session", params=["float_imad", "float_keys", "int_keys"])
 def emul(request):
     """g++ build of tests/host_emul/emul.cpp: the product's host/device headers compiled for the
-    CPU so their logic can be checked without a GPU.  Test harness only.  Built twice: with the
-    default float32 sort keys and with -DNM_INT_KEYS (order-preserving int32 keys)."""
+    CPU so their logic can be checked without a GPU.  Test harness only.  Built three times: with
+    -DNM_FLOAT_IMAD (the product's default: float32 keys, {fmin, a+b-min on the bit patterns}
+    compare-exchanges), with plain float32 keys and with -DNM_INT_KEYS (int32 key images)."""
     src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
     out_dir = os.path.join(ROOT, "tests", "host_emul", "_build")
     os.makedirs(out_dir, exist_ok=True)
@@ -33,7 +34,7 @@ def emul(request):
     deps = [src] + [os.path.join(ROOT, "nanomod_b200", "csrc", f)
                     for f in ("nm_math.cuh", "nm_lane.cuh", "nm_deep.cuh", "nm_sortnet.inc", "nm_sortloop.inc")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        defs = ["-DNM_INT_KEYS"] if request.param == "int_keys" else []
+        defs = {"int_keys": ["-DNM_INT_KEYS"], "float_imad": ["-DNM_FLOAT_IMAD"], "float_keys": []}[request.param]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + defs + ["-x", "c++", src, "-o", lib])
     L = ctypes.CDLL(lib)
     assert L.emul_sizeof_row_out() == ctypes.sizeof(RowOut)

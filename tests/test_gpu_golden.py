@@ -58,11 +58,37 @@ def test_cuda_path_reproduces_reference_golden(det, name, tmp_path):
         assert [int(r) for r in t.sorted_rows()] == case["sorted"]
     assert [list(s) for s in t.called_sites()] == case["called_sites"]
     got_lines, want_lines = t.format_lines(), case["sign_test_txt"].splitlines(keepends=True)
-    same = sum(a == b for a, b in zip(got_lines, want_lines))
-    assert len(got_lines) == len(want_lines) and same >= 0.995 * len(want_lines), (same, len(want_lines))
+    assert len(got_lines) == len(want_lines)
+    assert all(same_line(a, b) for a, b in zip(got_lines, want_lines))
+    assert sum(a == b for a, b in zip(got_lines, want_lines)) >= 0.98 * len(want_lines)
     if case["meanstd_cvs"] is not None:
         got_m, want_m = t.meanstd_lines(), case["meanstd_cvs"].splitlines(keepends=True)
-        assert len(got_m) == len(want_m) and sum(a == b for a, b in zip(got_m, want_m)) >= 0.99 * len(want_m)
+        assert len(got_m) == len(want_m) and all(same_line(a, b) for a, b in zip(got_m, want_m))
+
+
+def same_line(a, b):
+    """two table lines agree: identical text, or every numeric field within one unit of its last
+    printed digit.  (D = Dnum/(n0*n1) is one rounding here and |c0/n0 - c1/n1| -- two divisions
+    and a subtraction -- in scipy: at exact decimal ties such as 0.0125 the `%.3f` of the two
+    doubles, one ulp apart, prints differently.)"""
+    if a == b:
+        return True
+    fa, fb = a.split(), b.split()
+    if len(fa) != len(fb):
+        return False
+    for x, y in zip(fa, fb):
+        if x == y:
+            continue
+        try:
+            vx, vy = float(x), float(y)
+        except ValueError:
+            return False
+        if "E" in x:
+            if abs(vx - vy) > 1.001e-3 * 10.0 ** int(y.split("E")[1]):
+                return False
+        elif abs(vx - vy) > 1.001e-3:
+            return False
+    return True
 
 
 def _single_position_pileup(pairs):

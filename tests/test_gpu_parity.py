@@ -574,68 +574,72 @@ def test_cfg2_full_size_properties(det):
 
 
 # ---------------------------------------------------------------------------------------------
-# pair tier (two lanes per position; experimental, NANOMOD_B200_PAIR_TIER=1): used when the
-# longest row has > 64 reads and the rank statistics are not requested
+# dense path (rows == candidates) vs general path: same tables, and the speculative launch
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
-def det_pair():
+def det_general():
     import os
-    os.environ["NANOMOD_B200_PAIR_TIER"] = "1"
+    os.environ["NANOMOD_B200_NO_DENSE"] = "1"
     try:
         d = nm.Detector(0)
     finally:
-        del os.environ["NANOMOD_B200_PAIR_TIER"]
+        del os.environ["NANOMOD_B200_NO_DENSE"]
     return d
 
 
-def _sweep_pileup(seed=9, lo=1, hi=141):
-    rng = np.random.default_rng(seed)
-    c0 = np.concatenate([np.arange(lo, hi), rng.integers(3, hi, 500)]).astype(np.int64)
-    c1 = np.concatenate([np.arange(lo, hi)[::-1], rng.integers(3, hi, 500)]).astype(np.int64)
-    off0 = np.concatenate([[0], np.cumsum(c0)])
-    off1 = np.concatenate([[0], np.cumsum(c1)])
-    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
-    v1 = np.round(rng.normal(0.4, 1, off1[-1]), 2).astype(np.float32)
-    return nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(len(c0), dtype=np.int32))
+def _tables_identical(a, b):
+    assert len(a) == len(b)
+    for name in ("row_pos_index", "n0", "n1", "ks_dnum", "two_u", "flags"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for name in ("ks_d", "ks_p", "u_stat", "u_p", "t_stat", "t_p", "fisher_stat", "fisher_p", "stouffer_stat", "stouffer_p"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert np.array_equal(x, y, equal_nan=True), name  # bit for bit: same arithmetic on both paths
 
 
-@pytest.mark.parametrize("want_t", [False, True])
-def test_pair_tier_every_coverage(det, det_pair, want_t):
-    p = _sweep_pileup()
-    opt = nm.DetectOptions(MinCoverage=3, neighborPvalues=2, testMethod="stouffer", want_u=False, want_t=want_t)
-    t = det_pair.detect(p, opt)
-    assert_table_matches(t, vec(p, opt, ("stouffer",)), opt)
-    # the two tiers agree bit for bit (the Welch moments use the same routine in both)
-    t2 = det.detect(p, opt)
-    for name in ("ks_dnum", "ks_p", "stouffer_stat") + (("t_stat", "t_p") if want_t else ()):
-        assert getattr(t, name).tobytes() == getattr(t2, name).tobytes(), name
+@pytest.mark.parametrize("n", [9, 50, 64, 65, 100, 104, 128])
+def test_dense_path_equals_general_path(det, det_general, n):
+    p = nm.synthetic_pileup(3000 + n, n, max(5, n - 3), round_decimals=2)
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True)
+    t = det.detect(p, opt)
+    assert det.handle.last_path() in (1, 2)
+    g = det_general.detect(p, opt)
+    assert det_general.handle.last_path() == 0
+    _tables_identical(t, g)
+    assert_table_matches(t, vec(p, opt), opt)
+    ks = nm.DetectOptions(neighborPvalues=2, testMethod="fisher", want_u=False, want_t=False)
+    _tables_identical(det.detect(p, ks), det_general.detect(p, ks))
+    nb0 = nm.DetectOptions(neighborPvalues=0, testMethod="stouffer")
+    _tables_identical(det.detect(p, nb0), det_general.detect(p, nb0))
 
 
-@pytest.mark.parametrize("variant", ["uniform100", "ties1", "gaps_two_strands", "poisson100", "n128", "n65_unaligned"])
-def test_pair_tier_variants(det_pair, variant):
-    det = det_pair
-    kw = {"uniform100": dict(n=100), "ties1": dict(n=100, round_decimals=1),
-          "gaps_two_strands": dict(n=90, drop_frac1=0.02, two_strands=True, round_decimals=2),
-          "poisson100": dict(n=100, poisson=True, clip=(2, 128), round_decimals=3),
-          "n128": dict(n=128), "n65_unaligned": dict(n=65)}[variant]
-    n = kw.pop("n")
-    p = nm.synthetic_pileup(6000, n, n if variant != "n65_unaligned" else 67, seed=nm.SYN_SEED + 3, **kw)
-    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True, want_u=False, want_t=True)
-    assert_table_matches(det.detect(p, opt), vec(p, opt), opt)
+def test_speculative_dense_launch_and_refusal(det):
+    """After a dense-shaped call the next one is launched without waiting for its plan summary;
+    when its shape differs the device refuses and the call is re-run -- results are right either way."""
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer")
+    a = nm.synthetic_pileup(2000, 40, 40)
+    b = nm.synthetic_pileup(2000, 40, 40, seed=7)
+    c = nm.synthetic_pileup(2000, 100, 90)                      # another network class
+    d = nm.synthetic_pileup(2000, 40, 40, drop_frac1=0.05)      # filtered rows: not dense at all
+    e2 = nm.synthetic_pileup(400, 40, 40)                       # dense again
+    fresh = nm.Detector(0)
+    paths = []
+    for p in (a, b, c, d, e2, a):
+        t = fresh.detect(p, opt)
+        paths.append(fresh.handle.last_path())
+        assert_table_matches(t, vec(p, opt), opt)
+    assert paths == [1, 2, 3, 0, 1, 2], paths
 
 
-def test_pair_tier_mixed_with_deep_rows(det_pair):
-    det = det_pair
-    rng = np.random.default_rng(33)
-    L = 500
-    c0 = rng.integers(60, 128, L).astype(np.int64)
-    c1 = rng.integers(60, 128, L).astype(np.int64)
-    for i in (7, 8, 130, 131, 132, 499):
-        c0[i], c1[i] = 700, 650
-    off0 = np.concatenate([[0], np.cumsum(c0)])
-    off1 = np.concatenate([[0], np.cumsum(c1)])
-    v0 = np.round(rng.normal(0, 1, off0[-1]), 3).astype(np.float32)
-    v1 = np.round(rng.normal(0.2, 1, off1[-1]), 3).astype(np.float32)
-    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
-    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=True)
-    assert_table_matches(det.detect(p, opt), vec(p, opt, ("stouffer",)), opt)
+def test_bad_offsets_and_segment_ids_are_rejected(det):
+    p = nm.synthetic_pileup(500, 20, 20)
+    off = p.off0.copy()
+    off[100] = off[101] + 5  # not monotonic
+    bad = nm.Pileup(vals0=p.vals0, off0=off, vals1=p.vals1, off1=p.off1, pos=p.pos, seg=p.seg, base=p.base,
+                    seg_names=p.seg_names)
+    with pytest.raises(nm.NmError) as e:
+        det.detect(bad, nm.DetectOptions())
+    assert e.value.code == 1
+    t = det.detect(p, nm.DetectOptions())  # the handle is still usable
+    assert len(t) == 500
