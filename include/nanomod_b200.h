@@ -138,6 +138,16 @@ int nm_rank_device(nm_handle* h, const double* key_comb, const double* key_ks, c
 int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
                  int64_t n_rows, int reverse, int32_t* order);
 
+/* The first rows of that ranking without sorting all of them -- what the called-site rule
+ * (mboxplot / plot1, myDetect.py:279-297, :153-164) needs, and all that has to leave a GPU when
+ * the genome is sharded.  Keys are DEVICE columns as for nm_rank_device; rows_out is HOST memory
+ * with room for `cap` indices.  On return rows_out[0 .. *n_head) are the leading rows of the
+ * ranking in order, *n_head >= min(want, n_rows): every row whose primary key shares the cut's
+ * exponent bin is included, so rows not returned rank strictly after every row returned. */
+int nm_rank_head_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                        int64_t n_rows, int reverse, int64_t want, int64_t* rows_out, int64_t cap,
+                        int64_t* n_head, void* cuda_stream);
+
 /* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
  * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`
  * (device, 28*n bytes): the unit a rank sends to rank 0 in multi-GPU runs.
@@ -191,7 +201,8 @@ int nm_last_timings(const nm_handle* h, double* ms4);
 /* Which code path the most recent nm_detect_* call took: 0 general (plan + compaction, lane /
  * deep tiers, combine), 1 dense (rows == candidates: no compaction pass, no indirection),
  * 2 dense launched on the previous call's shape without waiting for the plan summary,
- * 3 such a launch refused by the device-side check and the call re-run on the general path. */
+ * 3 such a launch refused by the device-side check and the call re-run dense with the right network
+ * class, 4 refused and re-run on the general path. */
 int nm_last_path(const nm_handle* h);
 
 #ifdef __cplusplus

@@ -20,12 +20,13 @@ NM_DS_MAX_READS = 256
 NM_DS_MAX_TIMES = 1024
 NM_RECORD_BYTES = 28
 
+NM_ERR_BAD_ARG = 1
 ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: "NM_ERR_OOM",
                5: "NM_ERR_TOO_DEEP", 6: "NM_ERR_NO_DEVICE"}
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_rank_head_device",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -113,6 +114,9 @@ def load():
     lib.nm_rank_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                    C.c_void_p, C.c_void_p]
     lib.nm_rank_host.restype = C.c_int
+    lib.nm_rank_head_device.restype = C.c_int
+    lib.nm_rank_head_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
+                                        C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
     lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                  C.c_void_p]
     lib.nm_format_bound.restype = C.c_int64
@@ -170,7 +174,8 @@ class Handle:
         self._check(self._lib.nm_set_sm_limit(self._h, int(n_sms)))
 
     def last_path(self) -> int:
-        """0 general, 1 dense, 2 dense (speculative launch), 3 speculative launch refused and re-run"""
+        """0 general, 1 dense, 2 dense (speculative launch), 3 / 4 speculative launch refused and the call re-run
+        dense / on the general path"""
         return int(self._lib.nm_last_path(self._h))
 
     def last_timings(self):
@@ -203,6 +208,13 @@ class Handle:
         self._check(self._lib.nm_rank_device(self._h, C.c_void_p(key_comb or 0), C.c_void_p(key_ks),
                                              C.c_void_p(key_u or 0), int(n_rows), int(bool(reverse)),
                                              C.c_void_p(order), C.c_void_p(int(stream))))
+
+    def rank_head_device(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, want: int, rows_out, cap: int,
+                         stream: int = 0) -> int:
+        n_head = C.c_int64(0)
+        self._check(self._lib.nm_rank_head_device(self._h, key_comb, key_ks, key_u, n_rows, 1 if reverse else 0, want,
+                                                  rows_out, cap, C.byref(n_head), C.c_void_p(stream)))
+        return int(n_head.value)
 
     def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,
                             stream: int = 0) -> None:

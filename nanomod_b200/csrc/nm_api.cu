@@ -11,6 +11,8 @@
 // There is no CPU path: every entry point fails with NM_ERR_NO_DEVICE / NM_ERR_CUDA when the
 // GPU is not usable.
 #include <stdarg.h>
+
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -351,7 +353,8 @@ struct nm_handle {
   int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
   int dense_class;     // network class of the previous call when it had the dense shape (else 0): the next
                        // call is launched on that assumption without waiting for its plan summary
-  int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 speculative launch refused (re-run)
+  int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 / 4 speculative launch refused and
+                       // the call re-run dense with the right network class / on the general path
   nm_buf d_comb_z, d_comb_ln;
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
@@ -747,6 +750,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
       *n_rows_out = n_pos;
       return NM_OK;
     }
+    h->last_path = 4;
   }
   h->dense_class = 0;
   if (!have_sum) return nm_fail(h, NM_ERR_CUDA, "internal: plan summary missing");
@@ -991,6 +995,64 @@ extern "C" int nm_rank_host(nm_handle* h, const double* key_comb, const double* 
   return NM_OK;
 }
 
+
+// Head of the ranking: the first rows of what nm_rank_device would return, found with three
+// streaming passes over the primary key instead of a full sort (nm_rank.cu); the selected
+// records (a few thousand) are ordered on the host.
+extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                                   int64_t n_rows, int reverse, int64_t want, int64_t* rows_out, int64_t cap,
+                                   int64_t* n_head, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!n_head || !rows_out || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "rows_out/n_head is NULL or cap <= 0");
+  *n_head = 0;
+  if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
+  if (n_rows == 0 || want <= 0) return NM_OK;
+  if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int64_t dev_cap = cap < 65536 ? 65536 : cap;
+  unsigned info[4] = {0, 0, 0, 0};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int rc = nm_reserve(h, &h->d_rank, nm_head_scratch_bytes(dev_cap));
+    if (rc != NM_OK) return rc;
+    int launches = 0;
+    const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want, dev_cap, h->d_rank.p,
+                                                   h->sm_count, &launches, st);
+    h->launches += launches;
+    if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
+    NM_CUDA(h, cudaMemcpyAsync(info, (const unsigned*)h->d_rank.p + 4096, sizeof(info), cudaMemcpyDeviceToHost, st));
+    NM_CUDA(h, cudaStreamSynchronize(st));
+    if ((int64_t)info[1] <= dev_cap) break;
+    dev_cap = (int64_t)info[1];  // the cut bin holds more rows than fit: once more with room for all of them
+  }
+  const int64_t n_sel = (int64_t)info[1];
+  if (n_sel > dev_cap) return nm_fail(h, NM_ERR_CUDA, "internal: head selection overflow");
+  if (n_sel > cap)
+    return nm_fail(h, NM_ERR_BAD_ARG, "the ranking head holds %lld rows (ties at the cut), rows_out has room for %lld",
+                   (long long)n_sel, (long long)cap);
+  nm_head_record* recs = (nm_head_record*)malloc(sizeof(nm_head_record) * (size_t)(n_sel > 0 ? n_sel : 1));
+  if (!recs) return nm_fail(h, NM_ERR_OOM, "out of host memory");
+  const unsigned char* d_recs = (const unsigned char*)h->d_rank.p + ((sizeof(unsigned) * (4096 + 4) + 255) & ~(size_t)255);
+  cudaError_t e = cudaMemcpyAsync(recs, d_recs, sizeof(nm_head_record) * (size_t)n_sel, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free(recs);
+    return nm_fail(h, NM_ERR_CUDA, "head readback failed: %s", cudaGetErrorString(e));
+  }
+  struct Less {
+    int reverse;
+    bool operator()(const nm_head_record& a, const nm_head_record& b) const {
+      for (int k = 0; k < 3; ++k)
+        if (a.key[k] != b.key[k]) return a.key[k] < b.key[k];
+      return reverse ? a.row > b.row : a.row < b.row;  // the stable order, reversed for rankUse='st'
+    }
+  };
+  std::sort(recs, recs + n_sel, Less{reverse});
+  for (int64_t i = 0; i < n_sel; ++i) rows_out[i] = recs[i].row;
+  free(recs);
+  *n_head = n_sel;
+  return NM_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // result records for the multi-GPU gather: 28 bytes per row, packed

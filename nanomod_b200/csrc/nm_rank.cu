@@ -168,3 +168,116 @@ int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t
   *perm_out = rows.Current();
   return (int)cudaGetLastError();
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Head of the ranking without sorting every row.  The called-site rule (mboxplot / plot1,
+// myDetect.py:279-297, :153-164) walks the ranked list from the top and stops after topN
+// accepted sites, so only a short prefix of `sorted_sign_test` is ever looked at; on several
+// GPUs only that prefix has to leave a shard.  Three passes over the primary key column:
+//   nm_head_hist     4096-bin histogram of the top 12 bits (sign, exponent) of the key image
+//   nm_head_cut      smallest bin b whose cumulative count reaches `want`
+//   nm_head_compact  every row in a bin <= b becomes a 32-byte record (row, three key images)
+// All rows of bins <= b precede every other row in the full ranking, so the records, sorted
+// lexicographically (host side: a few thousand of them), ARE the first rows of the ranking.
+// reverse (rankUse='st': the ascending list reversed) uses complemented images and prefers the
+// higher row index, which is the reversed stable order.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+#define NM_HEAD_BINS 4096
+
+__device__ __forceinline__ unsigned long long nm_head_image(const double* col, int64_t r, int reverse) {
+  const unsigned long long k = col ? nm_rank_key(col[r]) : 0ull;
+  return reverse ? ~k : k;
+}
+
+__global__ void __launch_bounds__(256) nm_head_hist(const double* __restrict__ k0, int64_t n, int reverse,
+                                                    unsigned* __restrict__ hist) {
+  __shared__ unsigned h[NM_HEAD_BINS];
+  for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 256) h[b] = 0;
+  __syncthreads();
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
+    atomicAdd(&h[(unsigned)(nm_head_image(k0, r, reverse) >> 52)], 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 256)
+    if (h[b]) atomicAdd(&hist[b], h[b]);
+}
+
+// hist[NM_HEAD_BINS] = cut bin, hist[NM_HEAD_BINS + 1] = rows in bins <= cut, [+2] = compaction cursor (0)
+__global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want) {
+  __shared__ unsigned part[256];
+  unsigned s = 0;
+  for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned cum = 0;
+    int cut = NM_HEAD_BINS - 1;
+    bool found = false;
+    for (int t = 0; t < 256 && !found; ++t) {
+      if (cum + part[t] >= want) {
+        for (int b = 0; b < NM_HEAD_BINS / 256; ++b) {
+          cum += hist[t * (NM_HEAD_BINS / 256) + b];
+          if (cum >= want) {
+            cut = t * (NM_HEAD_BINS / 256) + b;
+            found = true;
+            break;
+          }
+        }
+      } else {
+        cum += part[t];
+      }
+    }
+    hist[NM_HEAD_BINS] = (unsigned)cut;
+    hist[NM_HEAD_BINS + 1] = cum;  // all rows when `want` exceeds them
+    hist[NM_HEAD_BINS + 2] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, int64_t n,
+                int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap) {
+  const unsigned cut = hist[NM_HEAD_BINS];
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256) {
+    const unsigned long long i0 = nm_head_image(k0, r, reverse);
+    if ((unsigned)(i0 >> 52) <= cut) {
+      const unsigned slot = atomicAdd(&hist[NM_HEAD_BINS + 2], 1u);
+      if (slot < cap) {
+        nm_head_record rec;
+        rec.row = (long long)r;
+        rec.key[0] = i0;
+        rec.key[1] = nm_head_image(k1, r, reverse);
+        rec.key[2] = nm_head_image(k2, r, reverse);
+        out[slot] = rec;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t nm_head_scratch_bytes(int64_t cap) {
+  return nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)) + sizeof(nm_head_record) * (size_t)cap;
+}
+
+int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
+                void* scratch, int sm_count, int* launches, cudaStream_t st) {
+  unsigned* hist = (unsigned*)scratch;
+  nm_head_record* recs = (nm_head_record*)((unsigned char*)scratch + nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)));
+  // primary key = the first present column, as in nm_rank_run (absent columns do not order)
+  const double* cols[3] = {comb, ks, u};
+  const double* k[3] = {nullptr, nullptr, nullptr};
+  int m = 0;
+  for (int c = 0; c < 3; ++c)
+    if (cols[c]) k[m++] = cols[c];
+  cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(unsigned) * (NM_HEAD_BINS + 4), st);
+  if (e != cudaSuccess) return (int)e;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8 * (int64_t)sm_count) blocks = 8 * (int64_t)sm_count;
+  nm_head_hist<<<(unsigned)blocks, 256, 0, st>>>(k[0], n, reverse, hist);
+  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n));
+  nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap);
+  *launches += 3;
+  return (int)cudaGetLastError();
+}

@@ -22,3 +22,15 @@ int nm_group_keys_run(const int32_t* row_n0, const int32_t* row_n1, int64_t n, i
                       nm_summary* sum, int* launches, cudaStream_t st);
 int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t** perm_out, void* scratch,
                       int* launches, cudaStream_t st);
+
+// Head of the ranking (nm_rank.cu): records of every row whose primary key falls into the
+// lowest exponent bins that together hold >= want rows.  scratch (device): a 4096 + 4 word
+// histogram block followed by `cap` records; word [4096 + 1] = rows selected, [4096 + 2] = rows
+// the compaction met (== selected; more than cap => the records are truncated).
+struct nm_head_record {
+  long long row;
+  unsigned long long key[3];  // order-preserving images of (combined, KS, U); 0 where absent
+};
+size_t nm_head_scratch_bytes(int64_t cap);
+int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
+                void* scratch, int sm_count, int* launches, cudaStream_t st);

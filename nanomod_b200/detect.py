@@ -501,6 +501,32 @@ class Detector:
                                 None if u is None else u.data_ptr(), n_rows, not use_p, order.data_ptr(), stream)
         return order
 
+    def rank_head_device(self, out: Dict[str, "object"], n_rows: int, options: DetectOptions, want: int,
+                         stream: Optional[int] = None) -> np.ndarray:
+        """The first rows (>= ``want``) of ``rank_device``'s order without sorting the whole
+        table: int64 row indices on the host.  Every row that ties with the cut's exponent bin
+        is included, so rows not returned rank strictly after all rows returned."""
+        import torch
+        use_p = options.rankUse == "pv"
+        m = options.testMethod
+        comb = None if m == "ks" else out[("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat")]
+        ks = out["ks_p" if use_p else "ks_d"]
+        u = out.get("u_p" if use_p else "u_stat") if options.want_u else None
+        if stream is None:
+            stream = torch.cuda.current_stream(ks.device).cuda_stream
+        cap = max(4 * want, 65536)
+        while True:
+            rows = np.empty(cap, dtype=np.int64)
+            try:
+                n = self.handle.rank_head_device(None if comb is None else comb.data_ptr(), ks.data_ptr(),
+                                                 None if u is None else u.data_ptr(), n_rows, not use_p, want,
+                                                 rows.ctypes.data, cap, stream)
+                return rows[:n]
+            except _lib.NmError as e:  # more ties at the cut than `cap`: the message carries the count
+                if e.code != _lib.NM_ERR_BAD_ARG or cap >= n_rows:
+                    raise
+                cap = min(n_rows, cap * 8)
+
     def pack_records(self, out: Dict[str, "object"], row_lo: int, n: int, options: DetectOptions, records,
                      stream: Optional[int] = None) -> None:
         """Device-resident table -> 28-byte records {ks_dnum, ks_p, comb stat, comb p} of rows
