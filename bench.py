@@ -5,17 +5,25 @@ Contract: ``python bench.py --gpus N --steps K --warmup W`` (N>1 under torchrun,
 GPU) prints ONE JSON line on rank 0.  A "step" is one pass of the detection stage (coverage
 filter, per-position KS test, window combination) over one synthetic pileup:
 BASELINE.json configs[1] -- E. coli K-12 scale, 4.6 Mb, 2x100x, float32 Gaussian currents with
-planted shifted sites -- per GPU (weak scaling: rank r holds its own 4.6 Mb shard
-plus a halo of neighborPvalues positions per side; the only communication is the NCCL gather of
-the 28-byte result records to rank 0, inside the timed region).
+planted shifted sites.
 
-  value      whole-job positions/s with the pileup already resident in HBM (nm_detect_device)
-  e2e        the same through Detector.detect(): pinned HOST buffers in, H2D + kernels + D2H
-  roofline   nm_lane_kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
-  cpu_baseline  the scalar oracle (the reference's scipy-1.2.1 arithmetic restated) on one host
-             core, on a bounded sample of the same workload
-``--impl reference`` times that oracle on all host cores instead (the reference itself is
-Python-2-only and cannot run here -- DESIGN.md).
+  value      whole-job positions/s with the pileup already resident in HBM.  N = 1:
+             ``Detector.detect_device`` (nm_detect_device).  N > 1 (weak scaling: every rank holds its
+             own 4.6 Mb shard plus a halo): the product's sharded path,
+             ``ShardedDetector.detect_shard`` + ``merged_head`` -- the table stays sharded, each
+             rank selects the head of its own ranking (nm_rank_head_device) and the heads are
+             all-gathered over NCCL: the only communication, inside the timed region.
+  e2e        the same through the host-facing API with pinned HOST buffers: H2D + kernels + D2H
+             (+ the head exchange at N > 1) in the timed region
+  roofline   the lane kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's OWN code (oracle/_ref: bin/scripts/myDetect.py rendered to Python 3,
+             scipy-1.2.1 call semantics) on one host core, on a bounded sample of the same
+             workload, doing the same tests as the GPU arm (KS + combination; the reference's
+             mannwhitneyu / ttest_ind calls are switched off for it, see ``tests``)
+  variants   (N = 1) the other BASELINE configs through the same call, a few steps each:
+             all tests (U + Welch t + KS, Fisher + Stouffer), Poisson coverage, chr20 2x30x, 2x2000x
+``--impl reference`` times the reference's code on all host cores (one process per core), primary
+value with the same tests as the GPU arm, the all-tests rate next to it.
 """
 from __future__ import annotations
 
@@ -44,14 +52,21 @@ MIN_COV = 5
 SEED = 20190131
 BYTES_PER_POS = 4 * (COV + COV) + 16 + 28  # fp32 values + two int64 offsets + outputs
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+HEAD_WANT = 2048           # rows of each rank's ranking head exchanged per step at N > 1
 
 
 def workload_config(n_gpus: int):
     return {"workload": "E. coli K-12 scale synthetic pileup, %d positions/GPU, 2x%dx, KS + weighted "
                         "Stouffer window +-%d" % (GENOME, COV, NB),
             "positions_per_gpu": GENOME, "coverage": [COV, COV], "neighborPvalues": NB, "WeightsDif": WEIGHTS_DIF,
-            "MinCoverage": MIN_COV, "testMethod": "stouffer", "tests": "ks",
-            "parallelism": "genome shards x%d, halo %d; NCCL gather of step k's result records to rank 0 overlaps the compute of step k+1" % (n_gpus, NB),
+            "MinCoverage": MIN_COV, "testMethod": "stouffer",
+            "tests": "KS test + weighted Stouffer combination per position (want_u = want_t = 0: the Mann-Whitney U "
+                     "and Welch t columns of the reference's table are NOT computed in this configuration; "
+                     "`variants.all_tests` is the run that fills them). Both arms do exactly this work.",
+            "want_u": False, "want_t": False,
+            "parallelism": ("1 GPU" if n_gpus == 1 else
+                            "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
+                            "sharded, per step each rank's ranking head (>= %d rows) is all-gathered over NCCL" % (n_gpus, HEAD_WANT)),
             "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -92,31 +107,54 @@ def host_sample_pileup(length: int, seed: int = SEED):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the scalar oracle (same scipy-level calls per position as myDetect.py:331-401)
+# CPU arm: the reference's own code (oracle/_ref), else the restated oracle
 # ---------------------------------------------------------------------------------------------
-def _oracle_run(args):
-    length, seed = args
-    from oracle import nanomod_oracle as o
+def _cpu_run(args):
+    """one bounded sample: returns (rows, seconds, kind)"""
+    length, seed, all_tests = args
+    import copy
     p = host_sample_pileup(length, seed)
     d0, d1 = p.to_dicts()
-    mo = o.default_moptions(MinCoverage=MIN_COV, neighborPvalues=NB, WeightsDif=WEIGHTS_DIF, testMethod="stouffer")
+    kw = dict(MinCoverage=MIN_COV, neighborPvalues=NB, WeightsDif=WEIGHTS_DIF, testMethod="stouffer")
+    from oracle import ref_loader as rl
+    if rl.available():
+        rl.set_tests(all_tests)
+        mo = rl.default_moptions(**kw)
+        mo["g0"], mo["g1"] = d0, d1
+        t0 = time.perf_counter()
+        rl.run_detect(mo)
+        return len(mo["sign_test"]), time.perf_counter() - t0, "reference"
+    from oracle import nanomod_oracle as o
+    mo = o.default_moptions(SaveTest=0, **kw)
     mo["ds2"] = ["g0", "g1"]
     mo["g0"], mo["g1"] = d0, d1
+    if not all_tests:
+        mo["_ks_only"] = 1
     t0 = time.perf_counter()
     o.mfilter_coverage(mo)
     o.mtest2(mo, strict=False)
-    return len(mo["sign_test"]), time.perf_counter() - t0
+    return len(mo["sign_test"]), time.perf_counter() - t0, "port"
 
 
-def cpu_baseline_one_core(sample: int = 20000):
-    rows, sec = _oracle_run((sample, SEED))
-    return {"value": rows / sec, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "first %d positions of the same synthetic workload (2x%dx), scalar oracle: "
-                      "mfilter_coverage + mtest2 (U, t, KS per position + Stouffer), %.1f s" % (sample, COV, sec)}
+def _cpu_what(kind: str) -> str:
+    return ("the reference's own bin/scripts/myDetect.py (oracle/_ref: Python-3 rendering, scipy-1.2.1 call semantics): "
+            "mfilter_coverage + mtest2" if kind == "reference" else
+            "oracle port of myDetect.py:301-462 (oracle/_ref not built): mfilter_coverage + mtest2")
+
+
+def cpu_baseline_one_core(sample: int):
+    rows, sec, kind = _cpu_run((sample, SEED, False))
+    rows_all, sec_all, _ = _cpu_run((max(sample // 4, 1000), SEED + 1, True))
+    return {"value": rows / sec, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "first %d positions of the same synthetic workload (2x%dx), %s, same tests as the GPU arm "
+                      "(KS + Stouffer; U / t calls switched off), %.1f s" % (sample, COV, _cpu_what(kind), sec),
+            "all_tests_value": rows_all / sec_all,
+            "all_tests_note": "the reference as it actually runs (mannwhitneyu + ttest_ind + ks_2samp per position), "
+                              "%d positions, %.1f s; compare with variants.all_tests" % (rows_all, sec_all)}
 
 
 def run_reference_arm(args):
-    """--impl reference: the oracle on every host core; each step = a bounded sample."""
+    """--impl reference: the reference's code on every host core; each step = a bounded sample."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -124,27 +162,36 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     per_core = 1500
     ctx = mp.get_context("fork")
-    times = []
-    rows_total = 0
+    times, rows_total, kind = [], 0, "reference"
     with ctx.Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_oracle_run, [(per_core, SEED + 17 * step + c) for c in range(cores)])
+            res = pool.map(_cpu_run, [(per_core, SEED + 17 * step + c, False) for c in range(cores)])
             dt = time.perf_counter() - t0
+            kind = res[0][2]
             if step >= args.warmup:
                 times.append(dt)
-                rows_total += sum(r for r, _ in res)
+                rows_total += sum(r for r, _, _ in res)
+        t0 = time.perf_counter()
+        res_all = pool.map(_cpu_run, [(per_core // 3, SEED + 991 + c, True) for c in range(cores)])
+        all_value = sum(r for r, _, _ in res_all) / (time.perf_counter() - t0)
     total = sum(times)
     value = rows_total / total
-    sample = "%d positions per step (%d per core x %d cores) of the 2x%dx workload" % (per_core * cores, per_core, cores, COV)
+    sample = "%d positions per step (%d per core x %d cores) of the 2x%dx workload; %s" % (
+        per_core * cores, per_core, cores, COV, _cpu_what(kind))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+            "ms_per_step_median": 1e3 * statistics.median(times), "ms_per_step_best": 1e3 * min(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "all_tests_value": all_value,
+                             "all_tests_note": "the same code with its mannwhitneyu + ttest_ind calls left on (what "
+                                               "NanoMod actually runs per position), all %d cores" % cores},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "reference = scalar CPU oracle (scipy-1.2.1 formulas); the Python-2 reference cannot run here"}
+            "note": "reference = NanoMod's own myDetect.py hot path executed from oracle/_ref on %d host cores "
+                    "(one process per core; the reference itself is single-threaded)" % cores}
     print(json.dumps(line), flush=True)
 
 
@@ -212,34 +259,96 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def lane_traffic():
-    """DRAM bytes per nm_lane_kernel launch on the bench workload, from the committed ncu
-    --set full capture (profiles/lane_kernel_traffic.json); None if no capture is recorded."""
+def lane_capture():
+    """the committed ncu --set full capture of the lane kernel on this workload
+    (profiles/lane_kernel_traffic.json): DRAM bytes per launch + what actually bounds the kernel"""
     try:
         with open(os.path.join(ROOT, "profiles", "lane_kernel_traffic.json")) as f:
-            d = json.load(f)
-        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
-    except Exception:
-        return None, None
-
-
-def lane_ncu_summary():
-    """What actually bounds the lane kernel, from the same committed ncu capture: the path is
-    HBM-bound by contract, but the kernel is limited by instruction issue on the half-rate integer
-    pipes -- reported next to the HBM roofline so that `frac` is read correctly."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "lane_kernel_traffic.json")) as f:
-            d = json.load(f)
-        return {k: d[k] for k in ("issue_active_pct", "alu_pipe_active_pct", "fmaheavy_pipe_active_pct",
-                                  "warp_instructions", "registers_per_thread", "warps_active_pct") if k in d}
+            return json.load(f)
     except Exception:
         return None
+
+
+def time_config(det, dev, opt, length, steps, warmup, nvals, bytes_out):
+    """a few steps of another configuration through the same device-resident call"""
+    import torch
+    import nanomod_b200 as nm
+    out = nm.alloc_device_table(opt, length, dev.vals0.device)
+    for _ in range(warmup):
+        det.detect_device(dev, opt, out)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    tms = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
+    ev[0].record()
+    for k in range(steps):
+        rows = det.detect_device(dev, opt, out)
+        for name, v in det.handle.last_timings().items():
+            tms[name] += v / steps
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+    ms = sum(per) / steps
+    alg = 4 * nvals + (16 + bytes_out) * length
+    peak, _ = hbm_peak()
+    main = max(tms["lane"], tms["deep"])
+    del out
+    return {"positions": length, "rows": rows, "steps": steps, "ms_per_step": ms, "ms_per_step_median": statistics.median(per),
+            "ms_per_step_best": min(per), "positions_per_s": length / (ms * 1e-3), "kernel_ms": tms,
+            "algorithmic_bytes": alg, "tests_kernel_frac_of_hbm_peak": alg / (main * 1e-3) / 1e9 / peak,
+            "whole_step_frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "path": det.handle.last_path()}
+
+
+def run_variants(det, device):
+    """the other BASELINE configs (parity-test cases, not bench lines), N = 1 only"""
+    import torch
+    import nanomod_b200 as nm
+    out = {}
+    ks_st = nm.DetectOptions(neighborPvalues=NB, testMethod="stouffer", want_u=False, want_t=False, MinCoverage=MIN_COV)
+    dev, _ = make_device_workload(GENOME, COV, COV, device)
+    allv = nm.DetectOptions(neighborPvalues=NB, both_combinations=True, want_u=True, want_t=True, MinCoverage=MIN_COV)
+    out["all_tests"] = time_config(det, dev, allv, GENOME, 5, 3, GENOME * 2 * COV, 76)
+    out["all_tests"]["what"] = ("BASELINE configs[2]: the same pileup, U + Welch t + KS per position, Fisher AND Stouffer: "
+                                "every column of the reference's table (892 algorithmic B/position)")
+    del dev
+    # Poisson coverage
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    lam = torch.full((GENOME,), float(COV), device=device)
+    c0 = torch.poisson(lam, generator=g).clamp_(5, 128).long()
+    c1 = torch.poisson(lam, generator=g).clamp_(5, 128).long()
+    from nanomod_b200._lib import padded_len
+    off0 = torch.zeros(GENOME + 1, dtype=torch.int64, device=device)
+    off1 = torch.zeros(GENOME + 1, dtype=torch.int64, device=device)
+    off0[1:] = torch.cumsum(c0, 0)
+    off1[1:] = torch.cumsum(c1, 0)
+    nv = int(off0[-1]) + int(off1[-1])
+    v0 = torch.empty(padded_len(int(off0[-1])), dtype=torch.float32, device=device).normal_(generator=g)
+    v1 = torch.empty(padded_len(int(off1[-1])), dtype=torch.float32, device=device).normal_(generator=g)
+    dev = nm.DevicePileup(v0, off0, v1, off1, torch.arange(GENOME, dtype=torch.int32, device=device),
+                          torch.zeros(GENOME, dtype=torch.int32, device=device), GENOME)
+    out["poisson_coverage"] = time_config(det, dev, ks_st, GENOME, 5, 3, nv, 28)
+    out["poisson_coverage"]["what"] = "E. coli scale, coverage ~ Poisson(100) clipped to [5, 128] per group, KS + Stouffer"
+    del dev, v0, v1, off0, off1, c0, c1, lam
+    dev, _ = make_device_workload(50_000, 2000, 2000, device)
+    out["deep_2x2000x"] = time_config(det, dev, ks_st, 50_000, 5, 2, 50_000 * 4000, 28)
+    out["deep_2x2000x"]["what"] = "BASELINE configs[4]: 50 kb plasmid, 2x2000x, KS + Stouffer (deep tier)"
+    del dev
+    torch.cuda.empty_cache()
+    L = 64_444_167
+    dev, _ = make_device_workload(L, 30, 30, device)
+    out["chr20_2x30x_1gpu"] = time_config(det, dev, ks_st, L, 3, 2, L * 60, 28)
+    out["chr20_2x30x_1gpu"]["what"] = ("BASELINE configs[3] on ONE GPU: human chr20, 64 444 167 positions, 2x30x, KS + Stouffer "
+                                       "(the sharded 2/4/8-GPU run of it: profiles/round2_cfg4_strong_scaling.json)")
+    del dev
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     import nanomod_b200 as nm
+    from nanomod_b200.sharded import ShardedDetector, shard_halo
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,64 +360,38 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     det = nm.Detector(local_rank)
+    sd = ShardedDetector(det)
     opt = nm.DetectOptions(MinCoverage=MIN_COV, neighborPvalues=NB, WeightsDif=WEIGHTS_DIF, testMethod="stouffer",
-                           want_u=False, want_t=False)
+                           want_u=False, want_t=False, SaveTest=0)
     L = args.positions
-    halo_lo = NB if rank > 0 else 0
-    halo_hi = NB if rank < world - 1 else 0
+    halo = shard_halo(opt) if world > 1 else 0
+    halo_lo = halo if rank > 0 else 0
+    halo_hi = halo if rank < world - 1 else 0
     n_local = L + halo_lo + halo_hi
     dev, _shift = make_device_workload(n_local, COV, COV, device, seed=SEED + rank, pos0=rank * L - halo_lo)
     out = nm.alloc_device_table(opt, n_local, device)
-    rec_cols = ["ks_dnum", "ks_p", "stouffer_stat", "stouffer_p"]  # the 28-byte result record
-    outs = [out]
-    gbufs = []
-    pending = [None, None]
-    if world > 1:
-        # Multi-GPU step: every rank computes its shard, then the 28-byte result records go to
-        # rank 0 over NCCL.  Outputs are double-buffered and the gather of step k runs on a side
-        # stream while step k+1 is computed; the lane kernel leaves a few SMs free for NCCL's
-        # copy kernels.  All gathers complete inside the timed region.
-        comm = torch.cuda.Stream(device=device)
-        det.handle.set_sm_limit(max(1, det.handle.sm_count - args.sm_reserve))
-        outs.append(nm.alloc_device_table(opt, n_local, device))
-        rec_w = [0, 4, 12, 20, 28]  # byte offsets of ks_dnum, ks_p, stouffer_stat, stouffer_p in a record
-        recs = [torch.empty((L, 28), dtype=torch.uint8, device=device) for _b in range(2)]
-        for _b in range(2):
-            gbufs.append([torch.empty((L, 28), dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None)
     step_tm = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
-    step_no = [0]
-
-    def drain(b):
-        if pending[b] is not None:
-            for w in pending[b]:
-                w.wait()
-            pending[b] = None
+    head_rows = [0]
 
     def step():
-        b = step_no[0] & 1 if world > 1 else 0
-        step_no[0] += 1
-        if world > 1:
-            drain(b)  # the buffer's previous gather (two steps ago) must have finished
-        rows = det.detect_device(dev, opt, outs[b])  # returns with the results complete on the device
+        if world == 1:
+            rows = det.detect_device(dev, opt, out)  # returns with the results complete on the device
+        else:
+            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, out)
+            rows = res.n_rows
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
         if world > 1:
-            # pack the four result columns into 28-byte records (one kernel), then ONE gather
-            det.pack_records(outs[b], halo_lo, L, opt, recs[b])
-            comm.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(comm):
-                pending[b] = [dist.gather(recs[b], gbufs[b], dst=0, async_op=True)]
+            m = sd.merged_head(res, HEAD_WANT)  # nm_rank_head_device + the NCCL all-gather of the heads
+            head_rows[0] = int(m.row.shape[0])
         return rows
 
     def fence():
-        if world > 1:
-            drain(0)
-            drain(1)
-            torch.cuda.synchronize()
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
-    launches0 = det.launch_count
     for _ in range(args.warmup):
         step()
     fence()
@@ -316,30 +399,29 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     lane_ms, comb_ms, plan_ms = [], [], []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches1 = det.launch_count
-    ev0.record()
+    evs[0].record()
     rows = 0
-    for _ in range(args.steps):
+    for k in range(args.steps):
         rows = step()
+        evs[k + 1].record()
         lane_ms.append(step_tm["lane"])
         comb_ms.append(step_tm["combine"])
         plan_ms.append(step_tm["plan"])
-    if world > 1:  # the last two gathers belong to the timed region
-        drain(0)
-        drain(1)
-    ev1.record()
     fence()
-    ms_total = ev0.elapsed_time(ev1)
+    per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    ms_total = evs[0].elapsed_time(evs[args.steps])
     launches = det.launch_count - launches1
+    path = det.handle.last_path()
     assert rows == n_local, (rows, n_local)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_total, statistics.median(per_step), min(per_step)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, ms_median, ms_best = (float(x) for x in t.tolist())
     value = world * L * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers through the public API (H2D + kernels + D2H every step)
+    # ---- e2e: host buffers through the host-facing API (H2D + kernels + D2H every step)
     e2e = None
     if not args.no_e2e:
         pin = lambda x: x.cpu().pin_memory().numpy()
@@ -351,12 +433,29 @@ def run_gpu_arm(args):
         tdt = {"int32": torch.int32, "int64": torch.int64, "float64": torch.float64, "uint8": torch.uint8}
         hout = {c: torch.empty(n_local, dtype=tdt[_lib.TABLE_DTYPES[c]]).pin_memory().numpy() for c in cols}
         e_steps = max(1, min(args.steps, args.e2e_steps))
-        det.detect(hp, opt, out=hout)  # warm-up (allocates the staging buffers)
+
+        hout_t = {c: torch.from_numpy(hout[c]) for c in cols}
+
+        def e2e_step():
+            if world == 1:
+                tbl = det.detect(hp, opt, out=hout)  # nm_detect_host: pinned host CSR in, result columns out
+                _ = float(tbl.stouffer_p[0])         # the result is on the host
+            else:
+                # the sharded product path from host buffers: H2D of the shard, detect_shard, heads
+                # all-gathered, this rank's rows back to (pinned) host memory
+                d = nm.DevicePileup.from_host(hp, device)
+                res = sd.detect_shard(d, halo_lo, halo_lo + L, rank * L - halo_lo, opt, out)
+                sd.merged_head(res, HEAD_WANT)
+                for c in cols:
+                    hout_t[c][:res.n_core].copy_(res.core(c), non_blocking=True)
+                torch.cuda.synchronize()
+                _ = float(hout["stouffer_p"][0])
+
+        e2e_step()  # warm-up (allocates the staging buffers)
         fence()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            tbl = det.detect(hp, opt, out=hout)
-            _ = float(tbl.stouffer_p[0])  # the result is on the host
+            e2e_step()
         fence()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=device)
@@ -365,31 +464,51 @@ def run_gpu_arm(args):
         h2d = int(4 * (hp.off0[-1] + hp.off1[-1]) + 8 * 2 * (n_local + 1) + 4 * 2 * n_local)
         d2h = int(sum(hout[c].itemsize for c in cols) * n_local)
         e2e = {"value": world * L * e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e_steps,
-               "api": "nanomod_b200.Detector.detect (nm_detect_host): pinned host CSR in, result columns out"}
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": 1e3 * float(tt.item()) / e_steps,
+               "pcie_GBps": (h2d + d2h) / (float(tt.item()) / e_steps) / 1e9,
+               "api": ("nanomod_b200.Detector.detect (nm_detect_host): pinned host CSR in, result columns out" if world == 1 else
+                       "DevicePileup.from_host (pinned) + ShardedDetector.detect_shard + merged_head (NCCL) + the rank's rows to pinned host")}
     clocks = sampler.stop() if rank == 0 else None
+    variants = None
+    if rank == 0 and world == 1 and not args.no_variants and L == GENOME:
+        del dev, out
+        torch.cuda.empty_cache()
+        variants = run_variants(det, device)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
         lane_avg = sum(lane_ms) / len(lane_ms)
         achieved = BYTES_PER_POS * n_local / (lane_avg * 1e-3) / 1e9
+        cap = lane_capture() if (world == 1 and L == GENOME) else None
+        kernel = "nm_lane_dense_kernel" if path in (1, 2, 3) else "nm_lane_kernel"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_step_median": ms_median,
+                "ms_per_step_best": ms_best, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys, i32 ranks, f64 tails",
                 "data": "synthetic", "config": workload_config(world),
-                "roofline": {"bound": "hbm", "kernel": "nm_lane_kernel", "achieved": achieved, "peak": peak,
+                "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": (lane_traffic()[0] if world == 1 and L == GENOME else None),
-                             "traffic_source": lane_traffic()[1], "algorithmic_bytes_per_launch": BYTES_PER_POS * n_local,
+                             "traffic": (float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])) if cap else None,
+                             "traffic_source": cap.get("source") if cap else None,
+                             "algorithmic_bytes_per_launch": BYTES_PER_POS * n_local,
                              "peak_source": peak_src,
                              "bytes_per_position": BYTES_PER_POS, "positions_per_launch": n_local,
-                             "kernel_ms": lane_avg, "other_kernels_ms": {"plan": sum(plan_ms) / len(plan_ms),
-                                                                         "combine": sum(comb_ms) / len(comb_ms)},
+                             "kernel_ms": lane_avg, "kernel_ms_median": statistics.median(lane_ms), "kernel_ms_best": min(lane_ms),
+                             "other_kernels_ms": {"plan": sum(plan_ms) / len(plan_ms), "combine": sum(comb_ms) / len(comb_ms)},
+                             "step_minus_kernel_ms": ms_total / args.steps - lane_avg,
                              "frac_of_nominal_8TBs": achieved / 8000.0,
-                             "practical_bound": "instruction issue on the ALU / FMA-heavy pipes (ncu, committed capture)",
-                             "ncu": (lane_ncu_summary() if world == 1 and L == GENOME else None)},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                             "practical_bound": "instruction issue on the half-rate ALU / FMA-heavy pipes (ncu, committed capture)",
+                             "ncu": ({k: cap[k] for k in ("issue_active_pct", "alu_pipe_active_pct", "fmaheavy_pipe_active_pct",
+                                                          "warp_instructions", "registers_per_thread", "warps_active_pct") if k in cap}
+                                     if cap else None)},
+                "e2e": e2e, "gpu_launches": launches, "code_path": {0: "general", 1: "dense", 2: "dense (speculative launch)",
+                                                                    3: "dense (re-run)", 4: "general (re-run)"}.get(path, str(path)),
+                "clocks": clocks,
                 "pct_hbm_peak_whole_step": 100.0 * (BYTES_PER_POS * value / world / 1e9) / peak}
+        if world > 1:
+            line["head_rows_exchanged"] = head_rows[0]
+        if variants is not None:
+            line["variants"] = variants
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_one_core(args.cpu_sample)
             line["cpu_baseline"]["host_cores_available"] = os.cpu_count()
@@ -408,9 +527,9 @@ def main():
     ap.add_argument("--positions", type=int, default=GENOME, help="positions per GPU (default: E. coli scale)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--sm-reserve", type=int, default=2, help="SMs left free for NCCL while computing (N > 1)")
-    ap.add_argument("--cpu-sample", type=int, default=60000)
+    ap.add_argument("--cpu-sample", type=int, default=40000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

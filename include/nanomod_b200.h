@@ -140,13 +140,32 @@ int nm_rank_host(nm_handle* h, const double* key_comb, const double* key_ks, con
 
 /* The first rows of that ranking without sorting all of them -- what the called-site rule
  * (mboxplot / plot1, myDetect.py:279-297, :153-164) needs, and all that has to leave a GPU when
- * the genome is sharded.  Keys are DEVICE columns as for nm_rank_device; rows_out is HOST memory
- * with room for `cap` indices.  On return rows_out[0 .. *n_head) are the leading rows of the
- * ranking in order, *n_head >= min(want, n_rows): every row whose primary key shares the cut's
- * exponent bin is included, so rows not returned rank strictly after every row returned. */
+ * the genome is sharded.  Keys are DEVICE columns as for nm_rank_device, over the n_rows rows to
+ * rank; rows_out is HOST memory with room for `cap` entries.  On return rows_out[0 .. *n_head)
+ * are the leading rows of the ranking in order, *n_head >= min(want, n_rows): every row whose
+ * primary key shares the cut's exponent bin is included, so rows not returned rank strictly
+ * after every row returned.  With `geometry` (device arrays) each entry also carries the row's
+ * segment / position and whether rows r-nearby .. r+nearby of the whole row list form one
+ * contiguous run (plot1's requirement, :156-164); the ranked rows are rows
+ * [row_offset, row_offset + n_rows) of that list (a shard's core rows inside core + halo). */
+typedef struct nm_head_geometry {
+  const int32_t* row_pos_index; /* row -> candidate, or NULL when rows are the candidates */
+  const int32_t* pos;           /* per candidate */
+  const int32_t* seg;
+  int64_t row_offset;
+  int64_t n_rows_total;
+  int32_t nearby;
+  int32_t reserved;
+} nm_head_geometry;
+typedef struct nm_head_row {
+  int64_t row;       /* index into the ranked rows */
+  int32_t seg, pos;  /* -1 without geometry */
+  int32_t full_nbhd;
+  int32_t reserved;
+} nm_head_row;
 int nm_rank_head_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
-                        int64_t n_rows, int reverse, int64_t want, int64_t* rows_out, int64_t cap,
-                        int64_t* n_head, void* cuda_stream);
+                        int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                        nm_head_row* rows_out, int64_t cap, int64_t* n_head, void* cuda_stream);
 
 /* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
  * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`

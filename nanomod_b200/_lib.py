@@ -61,6 +61,14 @@ TABLE_DTYPES = {"row_pos_index": "int32", "n0": "int32", "n1": "int32", "ks_dnum
 TABLE_WIDTH = {"moments": 4}  # columns that hold several values per row
 
 
+class nm_head_geometry(C.Structure):
+    _fields_ = [("row_pos_index", C.c_void_p), ("pos", C.c_void_p), ("seg", C.c_void_p), ("row_offset", C.c_int64),
+                ("n_rows_total", C.c_int64), ("nearby", C.c_int32), ("reserved", C.c_int32)]
+
+
+HEAD_ROW_DTYPE = [("row", "<i8"), ("seg", "<i4"), ("pos", "<i4"), ("full_nbhd", "<i4"), ("reserved", "<i4")]
+
+
 class nm_text_columns(C.Structure):
     _fields_ = [("seg_chrom", C.POINTER(C.c_char_p)), ("seg_strand", C.POINTER(C.c_char_p)), ("n_seg", C.c_int32),
                 ("reserved", C.c_int32), ("n_rows", C.c_int64)] + \
@@ -116,7 +124,8 @@ def load():
     lib.nm_rank_host.restype = C.c_int
     lib.nm_rank_head_device.restype = C.c_int
     lib.nm_rank_head_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
-                                        C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+                                        C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                        C.c_void_p]
     lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                  C.c_void_p]
     lib.nm_format_bound.restype = C.c_int64
@@ -209,11 +218,12 @@ class Handle:
                                              C.c_void_p(key_u or 0), int(n_rows), int(bool(reverse)),
                                              C.c_void_p(order), C.c_void_p(int(stream))))
 
-    def rank_head_device(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, want: int, rows_out, cap: int,
-                         stream: int = 0) -> int:
+    def rank_head_device(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, want: int, geometry, rows_out,
+                         cap: int, stream: int = 0) -> int:
         n_head = C.c_int64(0)
         self._check(self._lib.nm_rank_head_device(self._h, key_comb, key_ks, key_u, n_rows, 1 if reverse else 0, want,
-                                                  rows_out, cap, C.byref(n_head), C.c_void_p(stream)))
+                                                  None if geometry is None else C.byref(geometry), rows_out, cap,
+                                                  C.byref(n_head), C.c_void_p(stream)))
         return int(n_head.value)
 
     def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,

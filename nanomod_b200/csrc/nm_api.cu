@@ -57,7 +57,7 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
               int mincov, const int32_t* __restrict__ seg, int n_seg, int* __restrict__ block_count,
               nm_summary* __restrict__ sum) {
   const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
-  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0;
+  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0, max_deep_t = 0;
   bool bad = false;
 #pragma unroll
   for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
@@ -77,6 +77,8 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
           max_slack = max_slack > slack ? max_slack : slack;
         } else {
           ++n_deep;
+          const int64_t tt = n0 + n1;
+          max_deep_t = max_deep_t > (int)(tt < 0x7fffffff ? tt : 0x7fffffff) ? max_deep_t : (int)(tt < 0x7fffffff ? tt : 0x7fffffff);
           const int64_t cap = 1 << 24;
           const int p2 = nm_deep_p2((int)(n0 < cap ? n0 : cap)) + nm_deep_p2((int)(n1 < cap ? n1 : cap));
           max_deep = max_deep > p2 ? max_deep : p2;
@@ -95,28 +97,31 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
   max_lane = __reduce_max_sync(0xffffffffu, max_lane);
   max_slack = __reduce_max_sync(0xffffffffu, max_slack);
   max_deep = __reduce_max_sync(0xffffffffu, max_deep);
+  max_deep_t = __reduce_max_sync(0xffffffffu, max_deep_t);
   n_deep = __reduce_add_sync(0xffffffffu, n_deep);
   // one set of atomics per block, and only when it would change the summary (every warp hitting
   // the same address costs tens of microseconds at 4.6 M candidates)
-  __shared__ int red[4][NM_PLAN_THREADS / 32];
+  __shared__ int red[5][NM_PLAN_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
-    red[0][w] = max_lane; red[1][w] = max_slack; red[2][w] = max_deep; red[3][w] = n_deep;
+    red[0][w] = max_lane; red[1][w] = max_slack; red[2][w] = max_deep; red[3][w] = n_deep; red[4][w] = max_deep_t;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int ml = 0, ms = 0, md = 0, nd = 0;
+    int ml = 0, ms = 0, md = 0, nd = 0, mt = 0;
     for (int w = 0; w < NM_PLAN_THREADS / 32; ++w) {
       ml = ml > red[0][w] ? ml : red[0][w];
       ms = ms > red[1][w] ? ms : red[1][w];
       md = md > red[2][w] ? md : red[2][w];
       nd += red[3][w];
+      mt = mt > red[4][w] ? mt : red[4][w];
     }
     if (ml > *(volatile int*)&sum->max_lane_n) atomicMax(&sum->max_lane_n, ml);
     if (ms > *(volatile int*)&sum->max_lane_slack) atomicMax(&sum->max_lane_slack, ms);
     if (nd) {
       atomicAdd(&sum->n_deep, nd);
       atomicMax(&sum->max_deep_p2, md);
+      atomicMax(&sum->max_deep_t, mt);
     }
   }
   if (threadIdx.x == 0) block_count[blockIdx.x] = total;
@@ -341,6 +346,7 @@ struct nm_handle {
   cudaStream_t own_stream;
   nm_summary* d_sum;
   nm_summary* h_sum;  // pinned
+  void* h_head;       // pinned landing area of nm_rank_head_device
   nm_buf d_block_count, d_deep_rows, d_acc_r2, d_acc_tie, d_acc_mom;
   // staging for nm_detect_host
   nm_buf d_vals0, d_vals1, d_off0, d_off1, d_pos, d_seg, d_seg_cov;
@@ -350,12 +356,13 @@ struct nm_handle {
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
+  int no_deep2;        // NANOMOD_B200_NO_DEEP2=1: deep rows go straight to the sorting kernel (A/B experiments, tests)
   int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
   int dense_class;     // network class of the previous call when it had the dense shape (else 0): the next
                        // call is launched on that assumption without waiting for its plan summary
   int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 / 4 speculative launch refused and
                        // the call re-run dense with the right network class / on the general path
-  nm_buf d_comb_z, d_comb_ln;
+  nm_buf d_comb_z, d_comb_ln, d_deep_fallback;
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -443,6 +450,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
   {
     const char* g = getenv("NANOMOD_B200_NO_CLASS_SORT");
     h->no_class_sort = (g && g[0] == '1') ? 1 : 0;
+    const char* d2 = getenv("NANOMOD_B200_NO_DEEP2");
+    h->no_deep2 = (d2 && d2[0] == '1') ? 1 : 0;
     const char* d = getenv("NANOMOD_B200_NO_DENSE");
     h->no_dense = (d && d[0] == '1') ? 1 : 0;
   }
@@ -469,13 +478,14 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
     if (b.p) cudaFree(b.p);
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->h_sum) cudaFreeHost(h->h_sum);
+  if (h->h_head) cudaFreeHost(h->h_head);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (int k = 0; k < 5; ++k)
     if (h->ev[k]) cudaEventDestroy(h->ev[k]);
@@ -540,7 +550,20 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
-    const cudaError_t e = (cudaError_t)nm_launch_deep(ka, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
+    // binned kernel first; what it passes on (rows too long for its shared memory, rows whose values
+    // pile up in few bins) goes to the sorting kernel, whose grid is cut short by a device-side count
+    nm_kargs kd = ka;
+    if (!h->no_deep2) {
+      int rc = nm_reserve(h, &h->d_deep_fallback, sizeof(int32_t) * (size_t)n_deep);
+      if (rc != NM_OK) return rc;
+      cudaError_t e = (cudaError_t)nm_launch_deep2(ka, want_u, want_t, want_m, n_deep, sum.max_deep_t,
+                                                   (int32_t*)h->d_deep_fallback.p, &h->d_sum->deep_fallback_count, st);
+      if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_deep2_kernel launch failed: %s", cudaGetErrorString(e));
+      h->launches++;
+      kd.deep_rows = (const int32_t*)h->d_deep_fallback.p;
+      kd.deep_count_ptr = &h->d_sum->deep_fallback_count;
+    }
+    const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
     if (e != cudaSuccess)
       return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -1000,27 +1023,45 @@ extern "C" int nm_rank_host(nm_handle* h, const double* key_comb, const double* 
 // streaming passes over the primary key instead of a full sort (nm_rank.cu); the selected
 // records (a few thousand) are ordered on the host.
 extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
-                                   int64_t n_rows, int reverse, int64_t want, int64_t* rows_out, int64_t cap,
-                                   int64_t* n_head, void* cuda_stream) {
+                                   int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                                   nm_head_row* rows_out, int64_t cap, int64_t* n_head, void* cuda_stream) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
   if (!n_head || !rows_out || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "rows_out/n_head is NULL or cap <= 0");
   *n_head = 0;
   if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
   if (n_rows == 0 || want <= 0) return NM_OK;
   if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
+  nm_head_geo geo;
+  memset(&geo, 0, sizeof(geo));
+  if (geometry) {
+    if (!geometry->pos || !geometry->seg || geometry->row_offset < 0 || geometry->nearby < 0 ||
+        geometry->row_offset + n_rows > geometry->n_rows_total)
+      return nm_fail(h, NM_ERR_BAD_ARG, "head geometry: NULL pos/seg or a row range outside the row list");
+    geo.row_pos_index = geometry->row_pos_index; geo.pos = geometry->pos; geo.seg = geometry->seg;
+    geo.row_offset = geometry->row_offset; geo.n_rows_total = geometry->n_rows_total; geo.nearby = geometry->nearby;
+  }
   NM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int64_t dev_cap = cap < 65536 ? 65536 : cap;
-  unsigned info[4] = {0, 0, 0, 0};
+  int64_t dev_cap = cap < 16384 ? 16384 : cap;
+  const size_t head_off = (sizeof(unsigned) * (4096 + 4) + 255) & ~(size_t)255;
+  // pinned landing area: [4 info words][first records]; one stream sync covers both copies
+  const int64_t first = 8192;
+  if (!h->h_head) {
+    NM_CUDA(h, cudaMallocHost(&h->h_head, 64 + sizeof(nm_head_record) * (size_t)first));
+  }
+  unsigned* info = (unsigned*)h->h_head;
+  nm_head_record* first_recs = (nm_head_record*)((unsigned char*)h->h_head + 64);
   for (int attempt = 0; attempt < 2; ++attempt) {
     int rc = nm_reserve(h, &h->d_rank, nm_head_scratch_bytes(dev_cap));
     if (rc != NM_OK) return rc;
     int launches = 0;
-    const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want, dev_cap, h->d_rank.p,
+    const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want, dev_cap, geo, h->d_rank.p,
                                                    h->sm_count, &launches, st);
     h->launches += launches;
     if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
-    NM_CUDA(h, cudaMemcpyAsync(info, (const unsigned*)h->d_rank.p + 4096, sizeof(info), cudaMemcpyDeviceToHost, st));
+    NM_CUDA(h, cudaMemcpyAsync(info, (const unsigned*)h->d_rank.p + 4096, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    NM_CUDA(h, cudaMemcpyAsync(first_recs, (const unsigned char*)h->d_rank.p + head_off,
+                               sizeof(nm_head_record) * (size_t)(first < dev_cap ? first : dev_cap), cudaMemcpyDeviceToHost, st));
     NM_CUDA(h, cudaStreamSynchronize(st));
     if ((int64_t)info[1] <= dev_cap) break;
     dev_cap = (int64_t)info[1];  // the cut bin holds more rows than fit: once more with room for all of them
@@ -1030,14 +1071,19 @@ extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const d
   if (n_sel > cap)
     return nm_fail(h, NM_ERR_BAD_ARG, "the ranking head holds %lld rows (ties at the cut), rows_out has room for %lld",
                    (long long)n_sel, (long long)cap);
-  nm_head_record* recs = (nm_head_record*)malloc(sizeof(nm_head_record) * (size_t)(n_sel > 0 ? n_sel : 1));
-  if (!recs) return nm_fail(h, NM_ERR_OOM, "out of host memory");
-  const unsigned char* d_recs = (const unsigned char*)h->d_rank.p + ((sizeof(unsigned) * (4096 + 4) + 255) & ~(size_t)255);
-  cudaError_t e = cudaMemcpyAsync(recs, d_recs, sizeof(nm_head_record) * (size_t)n_sel, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) {
-    free(recs);
-    return nm_fail(h, NM_ERR_CUDA, "head readback failed: %s", cudaGetErrorString(e));
+  nm_head_record* recs = first_recs;
+  nm_head_record* heap = nullptr;
+  if (n_sel > first) {
+    heap = (nm_head_record*)malloc(sizeof(nm_head_record) * (size_t)n_sel);
+    if (!heap) return nm_fail(h, NM_ERR_OOM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(heap, (const unsigned char*)h->d_rank.p + head_off, sizeof(nm_head_record) * (size_t)n_sel,
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      free(heap);
+      return nm_fail(h, NM_ERR_CUDA, "head readback failed: %s", cudaGetErrorString(e));
+    }
+    recs = heap;
   }
   struct Less {
     int reverse;
@@ -1048,8 +1094,14 @@ extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const d
     }
   };
   std::sort(recs, recs + n_sel, Less{reverse});
-  for (int64_t i = 0; i < n_sel; ++i) rows_out[i] = recs[i].row;
-  free(recs);
+  for (int64_t i = 0; i < n_sel; ++i) {
+    rows_out[i].row = recs[i].row;
+    rows_out[i].seg = recs[i].seg;
+    rows_out[i].pos = recs[i].pos;
+    rows_out[i].full_nbhd = recs[i].full_nbhd;
+    rows_out[i].reserved = 0;
+  }
+  if (heap) free(heap);
   *n_head = n_sel;
   return NM_OK;
 }

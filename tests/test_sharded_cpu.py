@@ -14,7 +14,8 @@ import torch.multiprocessing as mp
 
 import nanomod_b200 as nm
 from nanomod_b200.detect import SignTestTable
-from nanomod_b200.sharded import ShardedDetector, pack_records, plan_shards, shard_with_halo, unpack_records
+from nanomod_b200.sharded import (ShardedDetector, greedy_sites, local_head_from_table, merge_heads, pack_records,
+                                  plan_shards, shard_halo, shard_with_halo, unpack_records)
 from oracle import nanomod_oracle_vec as ov
 
 
@@ -124,3 +125,67 @@ def test_gloo_world_gather(tmp_path, world):
     assert got["z"].tobytes() == full.stouffer_stat.tobytes() and got["fp"].tobytes() == full.fisher_p.tobytes()
     assert np.array_equal(got["pos"], full.pos) and np.array_equal(got["seg"], full.seg)
     assert list(got["sites"]) == [s[2] for s in full.called_sites()]
+
+
+# ---------------------------------------------------------------------------------------------
+# the table stays sharded: heads of the per-shard rankings, merged; called sites without a gather
+# ---------------------------------------------------------------------------------------------
+def _shard_tables(p, opt, world):
+    """every rank's host table over core + halo rows, with the core row range inside it"""
+    eng = OracleEngine()
+    out = []
+    for lo, hi in plan_shards(p.off0, p.off1, world):
+        sl, core_lo, core_hi = shard_with_halo(p, lo, hi, shard_halo(opt))
+        t = eng.detect(sl, opt)
+        r_lo = int(np.searchsorted(t.row_pos_index, core_lo))
+        r_hi = int(np.searchsorted(t.row_pos_index, core_hi))
+        out.append((t, r_lo, r_hi))
+    return out
+
+
+@pytest.mark.parametrize("rank_use,method", [("pv", "stouffer"), ("st", "stouffer"), ("pv", "ks"), ("st", "fisher")])
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_merged_heads_give_the_single_table_called_sites(world, rank_use, method):
+    p = nm.synthetic_pileup(6000, 10, 12, drop_frac1=0.01, two_strands=True, round_decimals=1)
+    opt = nm.DetectOptions(neighborPvalues=2, testMethod=method, rankUse=rank_use, topN=12)
+    full = OracleEngine().detect(p, opt)
+    want_sites = full.called_sites()
+    ranked = full.ranked()
+    shards = _shard_tables(p, opt, world)
+    for want in (5, 40, 400, 100000):
+        heads = [local_head_from_table(t, lo, hi, want) for t, lo, hi in shards]
+        m = merge_heads(heads, rank_use != "pv")
+        # the exact part of the merged head IS the head of the single-table ranking
+        assert np.array_equal(m.row[:m.n_exact], ranked[:m.n_exact])
+        assert m.n_exact >= min(want, len(full)) or m.complete
+        sites, final = greedy_sites(m, opt, p.seg_names)
+        assert sites == want_sites[:len(sites)]
+        if final:
+            assert sites == want_sites
+    assert final  # with every row in, the answer is final
+
+
+def _head_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = make_pileup()
+        opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", topN=9)
+        t, r_lo, r_hi = _shard_tables(p, opt, world)[rank]
+        # a deliberately short first request: the loop has to come back for longer heads
+        sites = ShardedDetector(OracleEngine()).called_sites_host(t, r_lo, r_hi, want=3)
+        np.save(os.path.join(out_dir, "sites%d.npy" % rank), np.array([s[2] for s in sites]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_called_sites_without_gather(tmp_path, world):
+    mp.spawn(_head_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    p = make_pileup()
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", topN=9)
+    want = [s[2] for s in OracleEngine().detect(p, opt).called_sites()]
+    assert len(want) > 0
+    for r in range(world):
+        assert list(np.load(os.path.join(str(tmp_path), "sites%d.npy" % r))) == want
