@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libnanomod_b200.so")
-UNITS = ["nm_api.cu", "nm_lane_kernel.cu", "nm_deep_kernel.cu", "nm_rank.cu", "nm_downsample.cu", "nm_format.cu"]
+UNITS = ["nm_api.cu", "nm_lane_kernel.cu", "nm_deep_kernel.cu", "nm_huge.cu", "nm_rank.cu", "nm_downsample.cu", "nm_format.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # Default configuration of the lane tier: float32 sort keys, compare-exchanges mixed 1:2 between

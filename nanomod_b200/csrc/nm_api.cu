@@ -19,6 +19,7 @@
 
 #include "nm_device.cuh"
 #include "nm_downsample.cuh"
+#include "nm_huge.cuh"
 #include "nm_rank.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -54,11 +55,11 @@ __device__ __forceinline__ int nm_block_excl_scan(int v, int* total) {
 
 __global__ void __launch_bounds__(NM_PLAN_THREADS)
 nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1, int64_t n_pos,
-              int mincov, const int32_t* __restrict__ seg, int n_seg, int* __restrict__ block_count,
-              nm_summary* __restrict__ sum) {
+              int mincov, const int32_t* __restrict__ seg, int n_seg, const int32_t* __restrict__ seg_cov,
+              int* __restrict__ block_count, nm_summary* __restrict__ sum) {
   const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
-  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0, max_deep_t = 0;
-  bool bad = false;
+  int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0, max_deep_t = 0, n_le64 = 0, n_le104 = 0;
+  bool bad = false, ds_deep = false;
 #pragma unroll
   for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
     const int64_t p = p0 + k;
@@ -70,8 +71,16 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
       if (n_seg > 0) bad |= (unsigned)seg[p] >= (unsigned)n_seg;  // per-segment arrays are indexed with it
       if (n0 >= mincov && n1 >= mincov) {
         ++cnt;
+        if (seg_cov && n_seg > 0 && (unsigned)seg[p] < (unsigned)n_seg) {
+          // a row the down-sampling branch will take, but too long for it: known before any test runs
+          const int cov = seg_cov[seg[p]];
+          if (cov > 0 && (n0 > cov || n1 > cov) && (n0 > NM_DS_MAX_READS || n1 > NM_DS_MAX_READS)) ds_deep = true;
+        }
         const int64_t m = n0 > n1 ? n0 : n1;
         if (m <= NM_LANE_TIER_MAX) {
+          const int cls = nm_lane_class((int)m);
+          n_le64 += cls <= 64 ? 1 : 0;
+          n_le104 += cls <= NM_LANE_FINE_MAX ? 1 : 0;
           max_lane = max_lane > (int)m ? max_lane : (int)m;
           const int slack = NM_LANE_TIER_MAX - (int)m;
           max_slack = max_slack > slack ? max_slack : slack;
@@ -81,41 +90,59 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
           max_deep_t = max_deep_t > (int)(tt < 0x7fffffff ? tt : 0x7fffffff) ? max_deep_t : (int)(tt < 0x7fffffff ? tt : 0x7fffffff);
           const int64_t cap = 1 << 24;
           const int p2 = nm_deep_p2((int)(n0 < cap ? n0 : cap)) + nm_deep_p2((int)(n1 < cap ? n1 : cap));
-          max_deep = max_deep > p2 ? max_deep : p2;
+          if (p2 > NM_DEEP_TIER_MAX_POOLED) {  // too long for shared memory: the global-memory path (nm_huge.cu)
+            atomicAdd(&sum->n_huge, 1);
+            atomicAdd(&sum->huge_v0, (unsigned long long)n0);
+            atomicAdd(&sum->huge_v1, (unsigned long long)n1);
+          } else {
+            max_deep = max_deep > p2 ? max_deep : p2;
+          }
         }
       }
     }
   }
-  int total;
-  (void)nm_block_excl_scan(cnt, &total);
-  if (__syncthreads_or(bad) && threadIdx.x == 0) sum->bad_input = 1;
-  {
-    int cand_total;
-    (void)nm_block_excl_scan(n_cand, &cand_total);
-    if (threadIdx.x == 0 && cand_total != total) atomicAdd(&sum->n_filtered, cand_total - total);
-  }
+  // block totals: warp reductions, one shared-memory hop, ONE set of atomics per block -- and only
+  // those that would change the summary (every block hitting the same addresses costs tens of
+  // microseconds at 4.6 M candidates)
+  unsigned flags = (bad ? 1u : 0u) | (ds_deep ? 2u : 0u);
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+  n_le64 = __reduce_add_sync(0xffffffffu, n_le64);
+  n_le104 = __reduce_add_sync(0xffffffffu, n_le104);
+  n_deep = __reduce_add_sync(0xffffffffu, n_deep);
   max_lane = __reduce_max_sync(0xffffffffu, max_lane);
   max_slack = __reduce_max_sync(0xffffffffu, max_slack);
   max_deep = __reduce_max_sync(0xffffffffu, max_deep);
   max_deep_t = __reduce_max_sync(0xffffffffu, max_deep_t);
-  n_deep = __reduce_add_sync(0xffffffffu, n_deep);
-  // one set of atomics per block, and only when it would change the summary (every warp hitting
-  // the same address costs tens of microseconds at 4.6 M candidates)
-  __shared__ int red[5][NM_PLAN_THREADS / 32];
+  __shared__ int red[10][NM_PLAN_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
     red[0][w] = max_lane; red[1][w] = max_slack; red[2][w] = max_deep; red[3][w] = n_deep; red[4][w] = max_deep_t;
+    red[5][w] = cnt; red[6][w] = n_cand; red[7][w] = n_le64; red[8][w] = n_le104; red[9][w] = (int)flags;
   }
   __syncthreads();
+  int total = 0;
   if (threadIdx.x == 0) {
-    int ml = 0, ms = 0, md = 0, nd = 0, mt = 0;
+    int ml = 0, ms = 0, md = 0, nd = 0, mt = 0, nc = 0, l64 = 0, l104 = 0, fl = 0;
     for (int w = 0; w < NM_PLAN_THREADS / 32; ++w) {
       ml = ml > red[0][w] ? ml : red[0][w];
       ms = ms > red[1][w] ? ms : red[1][w];
       md = md > red[2][w] ? md : red[2][w];
       nd += red[3][w];
       mt = mt > red[4][w] ? mt : red[4][w];
+      total += red[5][w];
+      nc += red[6][w];
+      l64 += red[7][w];
+      l104 += red[8][w];
+      fl |= red[9][w];
     }
+    if (fl & 1) sum->bad_input = 1;
+    if (fl & 2) sum->ds_too_deep = 1;
+    if (nc != total) atomicAdd(&sum->n_filtered, nc - total);
+    if (total) atomicAdd(&sum->n_cand_kept, total);
+    if (l64) atomicAdd(&sum->plan_le64, l64);
+    if (l104) atomicAdd(&sum->plan_le104, l104);
     if (ml > *(volatile int*)&sum->max_lane_n) atomicMax(&sum->max_lane_n, ml);
     if (ms > *(volatile int*)&sum->max_lane_slack) atomicMax(&sum->max_lane_slack, ms);
     if (nd) {
@@ -356,13 +383,18 @@ struct nm_handle {
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
-  int no_deep2;        // NANOMOD_B200_NO_DEEP2=1: deep rows go straight to the sorting kernel (A/B experiments, tests)
   int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
   int dense_class;     // network class of the previous call when it had the dense shape (else 0): the next
                        // call is launched on that assumption without waiting for its plan summary
   int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 / 4 speculative launch refused and
                        // the call re-run dense with the right network class / on the general path
   nm_buf d_comb_z, d_comb_ln, d_deep_fallback;
+  // pipelined nm_detect_host: two slots of staging (inputs + outputs), copy streams and events
+  nm_buf p_in[2][6];    // vals0, vals1, off0, off1, pos, seg of a slab
+  nm_buf p_out[2][17];  // the slab's table
+  cudaStream_t s_in, s_out;
+  cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+  int64_t slab;         // candidates per slab (NANOMOD_B200_SLAB; 0 = never pipeline)
   cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
@@ -450,8 +482,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
   {
     const char* g = getenv("NANOMOD_B200_NO_CLASS_SORT");
     h->no_class_sort = (g && g[0] == '1') ? 1 : 0;
-    const char* d2 = getenv("NANOMOD_B200_NO_DEEP2");
-    h->no_deep2 = (d2 && d2[0] == '1') ? 1 : 0;
+    const char* sl = getenv("NANOMOD_B200_SLAB");
+    h->slab = sl ? atoll(sl) : 262144;
     const char* d = getenv("NANOMOD_B200_NO_DENSE");
     h->no_dense = (d && d[0] == '1') ? 1 : 0;
   }
@@ -463,6 +495,12 @@ extern "C" int nm_create(int device, nm_handle** out) {
     if (cudaMallocHost(&h->h_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
     for (int k = 0; k < 5 && rc == NM_OK; ++k)
       if (cudaEventCreate(&h->ev[k]) != cudaSuccess) rc = NM_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) rc = NM_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) rc = NM_ERR_CUDA;
+    for (int k = 0; k < 2 && rc == NM_OK; ++k)
+      if (cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_cmp[k], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming) != cudaSuccess) rc = NM_ERR_CUDA;
   } while (0);
   if (rc != NM_OK) {
     nm_fail(nullptr, rc, "nm_create: CUDA set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -483,6 +521,17 @@ extern "C" void nm_destroy(nm_handle* h) {
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
     if (b.p) cudaFree(b.p);
+  for (int s = 0; s < 2; ++s) {
+    for (nm_buf& b : h->p_in[s])
+      if (b.p) cudaFree(b.p);
+    for (nm_buf& b : h->p_out[s])
+      if (b.p) cudaFree(b.p);
+    if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
+    if (h->ev_cmp[s]) cudaEventDestroy(h->ev_cmp[s]);
+    if (h->ev_out[s]) cudaEventDestroy(h->ev_out[s]);
+  }
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->d_sum) cudaFree(h->d_sum);
   if (h->h_sum) cudaFreeHost(h->h_sum);
   if (h->h_head) cudaFreeHost(h->h_head);
@@ -550,23 +599,22 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   }
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
-    // binned kernel first; what it passes on (rows too long for its shared memory, rows whose values
-    // pile up in few bins) goes to the sorting kernel, whose grid is cut short by a device-side count
     nm_kargs kd = ka;
-    if (!h->no_deep2) {
-      int rc = nm_reserve(h, &h->d_deep_fallback, sizeof(int32_t) * (size_t)n_deep);
-      if (rc != NM_OK) return rc;
-      cudaError_t e = (cudaError_t)nm_launch_deep2(ka, want_u, want_t, want_m, n_deep, sum.max_deep_t,
-                                                   (int32_t*)h->d_deep_fallback.p, &h->d_sum->deep_fallback_count, st);
-      if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_deep2_kernel launch failed: %s", cudaGetErrorString(e));
+    if (n_deep > sum.n_huge) {
+      const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
+      if (e != cudaSuccess)
+        return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
       h->launches++;
-      kd.deep_rows = (const int32_t*)h->d_deep_fallback.p;
-      kd.deep_count_ptr = &h->d_sum->deep_fallback_count;
     }
-    const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
-    if (e != cudaSuccess)
-      return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
-    h->launches++;
+    if (sum.n_huge > 0) {  // rows too long for the deep tier's shared memory (the reference has no depth limit)
+      int rc = nm_reserve(h, &h->d_deep_fallback, nm_huge_scratch_bytes(sum.n_huge, (long long)sum.huge_v0, (long long)sum.huge_v1));
+      if (rc != NM_OK) return rc;
+      int launches = 0;
+      const cudaError_t e = (cudaError_t)nm_huge_run(ka, want_u, want_t, want_m, sum.n_huge, (long long)sum.huge_v0,
+                                                     (long long)sum.huge_v1, h->d_deep_fallback.p, &launches, st);
+      h->launches += launches;
+      if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "huge-row path failed: %s", cudaGetErrorString(e));
+    }
   }
   if ((want_u || want_t) && n_rows > n_deep) {
     nm_tails_args ta;
@@ -585,10 +633,7 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
 }
 
 // the shape the dense lane kernel assumes (it re-checks the same conditions on the device)
-static bool nm_dense_shape(const nm_summary& s) {
-  return s.n_filtered == 0 && s.n_deep == 0 && s.bad_input == 0 && s.max_lane_n > 0 &&
-         nm_lane_group(NM_LANE_TIER_MAX - s.max_lane_slack) == nm_lane_group(s.max_lane_n);
-}
+static bool nm_dense_shape(const nm_summary& s) { return nm_dense_shape_ok(s); }
 
 static void nm_fill_comb_args(nm_comb_args* ca, const nm_pileup* pl, const nm_params& prm, const nm_table* tb,
                               int64_t n_rows, bool ds_on) {
@@ -727,7 +772,8 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   NM_CUDA(h, cudaEventRecord(h->ev[0], st));
   NM_CUDA(h, cudaMemsetAsync(h->d_sum, 0, sizeof(nm_summary), st));
   nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage, pl->seg,
-                                                  pl->n_seg > 0 ? pl->n_seg : 0, (int*)h->d_block_count.p, h->d_sum);
+                                                  pl->n_seg > 0 ? pl->n_seg : 0, ds_on ? pl->seg_cov : nullptr,
+                                                  (int*)h->d_block_count.p, h->d_sum);
   NM_CUDA(h, cudaGetLastError());
   h->launches += 1;
   NM_CUDA(h, cudaEventRecord(h->ev[1], st));
@@ -779,6 +825,10 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   if (!have_sum) return nm_fail(h, NM_ERR_CUDA, "internal: plan summary missing");
   if (sum.bad_input)
     return nm_fail(h, NM_ERR_BAD_ARG, "offsets are not non-decreasing, or a segment id is outside [0, n_seg)");
+  if (ds_on && sum.ds_too_deep)  // known from the plan pass: refuse before any test has run
+    return nm_fail(h, NM_ERR_TOO_DEEP,
+                   "--coverages: a position to be down-sampled has more than %d reads in a group; the down-sampling "
+                   "branch supports at most that many (run without --coverages, or thin the pileup first)", NM_DS_MAX_READS);
 
   // ---- plan, second pass: ordered compaction of the kept candidates into rows
   {
@@ -788,10 +838,6 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   const int64_t n_rows = n_pos - (int64_t)sum.n_filtered;
   *n_rows_out = n_rows;
   if (n_rows == 0) return NM_OK;
-  if (sum.n_deep > 0 && sum.max_deep_p2 > NM_DEEP_TIER_MAX_POOLED)
-    return nm_fail(h, NM_ERR_TOO_DEEP,
-                   "a position has pow2(n0)+pow2(n1) = %d > %d values; deeper pileups are not supported",
-                   sum.max_deep_p2, NM_DEEP_TIER_MAX_POOLED);
   nm_plan_scan<<<1, NM_PLAN_THREADS, 0, st>>>((int*)h->d_block_count.p, nblk, h->d_sum);
   nm_plan_scatter<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage,
                                                     (const int*)h->d_block_count.p, tb->row_pos_index,
@@ -898,6 +944,160 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   return NM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Pipelined host entry.  The pileup is cut into slabs of `slab` candidates (+ a halo of nb
+// candidates per side, recomputed: the same argument as for genome shards); while slab k is
+// tested, slab k+1 is on its way in (copy stream) and the rows of slab k-1 are on their way out
+// (second copy stream; PCIe is full duplex).  Host -> device traffic is 96 % of the bytes, so
+// the call runs at the H2D line rate with kernels and the D2H hidden behind it; device memory
+// holds two slabs instead of the whole pileup.
+// ------------------------------------------------------------------------------------------
+__global__ void nm_rebase_offsets(int64_t* off, int64_t n, int64_t base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] -= base;
+}
+
+__global__ void nm_rebase_rows(int32_t* row_pos_index, int64_t lo, int64_t hi, int32_t add) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi) row_pos_index[i] += add;
+}
+
+static int nm_detect_host_pipelined(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb,
+                                    int64_t* n_rows_out) {
+  const int64_t n = pl->n_pos, S = h->slab;
+  const int nb = (prm.combine != 0) ? prm.nb : 0;
+  const int64_t n_slabs = (n + S - 1) / S;
+  void* const host_ptrs[17] = {tb->row_pos_index, tb->n0, tb->n1, tb->ks_dnum, tb->ks_d, tb->ks_p,
+                               tb->two_u, tb->u_stat, tb->u_p, tb->t_stat, tb->t_p, tb->fisher_stat,
+                               tb->fisher_p, tb->stouffer_stat, tb->stouffer_p, tb->flags, tb->moments};
+  const size_t elem[17] = {4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 1, 32};
+  const bool live[17] = {true, true, true, true, true, true,
+                         prm.want_u != 0, prm.want_u != 0, prm.want_u != 0, prm.want_t != 0, prm.want_t != 0,
+                         (prm.combine & NM_COMBINE_FISHER) != 0, (prm.combine & NM_COMBINE_FISHER) != 0,
+                         (prm.combine & NM_COMBINE_STOUFFER) != 0, (prm.combine & NM_COMBINE_STOUFFER) != 0, true, true};
+  int rc;
+  // slab geometry and staging capacity
+  int64_t max_v0 = 0, max_v1 = 0;
+  for (int64_t k = 0; k < n_slabs; ++k) {
+    const int64_t lo = k * S, hi = lo + S < n ? lo + S : n;
+    const int64_t hlo = lo - nb > 0 ? lo - nb : 0, hhi = hi + nb < n ? hi + nb : n;
+    const int64_t v0 = pl->off0[hhi] - pl->off0[hlo], v1 = pl->off1[hhi] - pl->off1[hlo];
+    if (v0 < 0 || v1 < 0) return nm_fail(h, NM_ERR_BAD_ARG, "offsets must be non-decreasing");
+    max_v0 = v0 > max_v0 ? v0 : max_v0;
+    max_v1 = v1 > max_v1 ? v1 : max_v1;
+  }
+  const int64_t cap = S + 2 * nb;
+  for (int s = 0; s < 2; ++s) {
+    const size_t need[6] = {sizeof(float) * (size_t)nm_padded_len(max_v0), sizeof(float) * (size_t)nm_padded_len(max_v1),
+                            sizeof(int64_t) * (size_t)(cap + 1), sizeof(int64_t) * (size_t)(cap + 1),
+                            sizeof(int32_t) * (size_t)cap, sizeof(int32_t) * (size_t)cap};
+    for (int b = 0; b < 6; ++b)
+      if ((rc = nm_reserve(h, &h->p_in[s][b], need[b])) != NM_OK) return rc;
+    for (int c = 0; c < 17; ++c)
+      if (host_ptrs[c] && (rc = nm_reserve(h, &h->p_out[s][c], elem[c] * (size_t)cap)) != NM_OK) return rc;
+  }
+  const int32_t* d_seg_cov = nullptr;
+  if (pl->seg_cov && pl->n_seg > 0) {
+    if ((rc = nm_reserve(h, &h->d_seg_cov, sizeof(int32_t) * (size_t)pl->n_seg)) != NM_OK) return rc;
+    NM_CUDA(h, cudaMemcpyAsync(h->d_seg_cov.p, pl->seg_cov, sizeof(int32_t) * (size_t)pl->n_seg, cudaMemcpyHostToDevice, h->s_in));
+    d_seg_cov = (const int32_t*)h->d_seg_cov.p;
+  }
+  cudaStream_t st = h->own_stream;
+
+  auto stage_in = [&](int64_t k) -> int {
+    const int s = (int)(k & 1);
+    const int64_t lo = k * S, hi = lo + S < n ? lo + S : n;
+    const int64_t hlo = lo - nb > 0 ? lo - nb : 0, hhi = hi + nb < n ? hi + nb : n;
+    const int64_t m = hhi - hlo;
+    const int64_t b0 = pl->off0[hlo], b1 = pl->off1[hlo];
+    const int64_t v0 = pl->off0[hhi] - b0, v1 = pl->off1[hhi] - b1;
+    // the slot's inputs were last read by slab k-2's kernels, which have completed (the compute call is synchronous)
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][0].p, pl->vals0 + b0, sizeof(float) * (size_t)v0, cudaMemcpyHostToDevice, h->s_in));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][1].p, pl->vals1 + b1, sizeof(float) * (size_t)v1, cudaMemcpyHostToDevice, h->s_in));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][2].p, pl->off0 + hlo, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, h->s_in));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][3].p, pl->off1 + hlo, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, h->s_in));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][4].p, pl->pos + hlo, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, h->s_in));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][5].p, pl->seg + hlo, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, h->s_in));
+    const unsigned g = (unsigned)((m + 1 + 255) / 256);
+    nm_rebase_offsets<<<g, 256, 0, h->s_in>>>((int64_t*)h->p_in[s][2].p, m + 1, b0);
+    nm_rebase_offsets<<<g, 256, 0, h->s_in>>>((int64_t*)h->p_in[s][3].p, m + 1, b1);
+    NM_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    NM_CUDA(h, cudaEventRecord(h->ev_in[s], h->s_in));
+    return NM_OK;
+  };
+
+  int64_t row_base = 0;
+  double ms_acc[4] = {0, 0, 0, 0};
+  if ((rc = stage_in(0)) != NM_OK) return rc;
+  for (int64_t k = 0; k < n_slabs; ++k) {
+    const int s = (int)(k & 1);
+    const int64_t lo = k * S, hi = lo + S < n ? lo + S : n;
+    const int64_t hlo = lo - nb > 0 ? lo - nb : 0, hhi = hi + nb < n ? hi + nb : n;
+    const int64_t m = hhi - hlo;
+    if (k + 1 < n_slabs && (rc = stage_in(k + 1)) != NM_OK) return rc;  // on its way while slab k is tested
+    NM_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[s], 0));
+    if (k >= 2) NM_CUDA(h, cudaStreamWaitEvent(st, h->ev_out[s], 0));  // the slot's table has left (slab k-2)
+    nm_pileup dpl = {(const float*)h->p_in[s][0].p, (const int64_t*)h->p_in[s][2].p, (const float*)h->p_in[s][1].p,
+                     (const int64_t*)h->p_in[s][3].p, (const int32_t*)h->p_in[s][4].p, (const int32_t*)h->p_in[s][5].p, m,
+                     d_seg_cov, d_seg_cov ? pl->n_seg : 0};
+    void* dp[17];
+    for (int c = 0; c < 17; ++c) dp[c] = host_ptrs[c] ? h->p_out[s][c].p : nullptr;
+    nm_table dtb = {(int32_t*)dp[0], (int32_t*)dp[1], (int32_t*)dp[2], (int32_t*)dp[3], (double*)dp[4], (double*)dp[5],
+                    (int64_t*)dp[6], (double*)dp[7], (double*)dp[8], (double*)dp[9], (double*)dp[10], (double*)dp[11],
+                    (double*)dp[12], (double*)dp[13], (double*)dp[14], (uint8_t*)dp[15], (double*)dp[16]};
+    int64_t rows = 0;
+    rc = nm_detect_device(h, &dpl, &prm, &dtb, &rows, (void*)st);
+    if (rc != NM_OK) {
+      cudaStreamSynchronize(h->s_in);
+      cudaStreamSynchronize(h->s_out);
+      return rc;
+    }
+    for (int q = 0; q < 4; ++q) ms_acc[q] += h->last_ms[q];
+    // core rows of the slab: those whose candidate lies in [lo, hi)
+    int64_t r_lo = lo - hlo, r_hi = hi - hlo;
+    if (rows != m) {
+      if (rows > 0) {
+        int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)rows);
+        if (!tmp) return nm_fail(h, NM_ERR_OOM, "out of host memory");
+        cudaError_t e = cudaMemcpyAsync(tmp, dp[0], sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          free(tmp);
+          return nm_fail(h, NM_ERR_CUDA, "row index readback failed: %s", cudaGetErrorString(e));
+        }
+        r_lo = std::lower_bound(tmp, tmp + rows, (int32_t)(lo - hlo)) - tmp;
+        r_hi = std::lower_bound(tmp, tmp + rows, (int32_t)(hi - hlo)) - tmp;
+        free(tmp);
+      } else {
+        r_lo = r_hi = 0;
+      }
+    }
+    const int64_t core = r_hi - r_lo;
+    if (core > 0) {
+      if (hlo != 0) {  // row -> candidate index of the whole pileup
+        nm_rebase_rows<<<(unsigned)((core + 255) / 256), 256, 0, st>>>((int32_t*)dp[0], r_lo, r_hi, (int32_t)hlo);
+        NM_CUDA(h, cudaGetLastError());
+        h->launches++;
+      }
+      NM_CUDA(h, cudaEventRecord(h->ev_cmp[s], st));
+      NM_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_cmp[s], 0));
+      for (int c = 0; c < 17; ++c)
+        if (host_ptrs[c] && live[c])
+          NM_CUDA(h, cudaMemcpyAsync((unsigned char*)host_ptrs[c] + elem[c] * (size_t)row_base,
+                                     (const unsigned char*)dp[c] + elem[c] * (size_t)r_lo, elem[c] * (size_t)core,
+                                     cudaMemcpyDeviceToHost, h->s_out));
+    }
+    NM_CUDA(h, cudaEventRecord(h->ev_out[s], h->s_out));
+    row_base += core;
+  }
+  NM_CUDA(h, cudaStreamSynchronize(h->s_out));
+  NM_CUDA(h, cudaStreamSynchronize(h->s_in));
+  for (int q = 0; q < 4; ++q) h->last_ms[q] = ms_acc[q];
+  *n_rows_out = row_base;
+  return NM_OK;
+}
+
 extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params* params,
                               const nm_table* tb, int64_t* n_rows_out) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
@@ -916,6 +1116,9 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
   const int64_t nv0 = pl->off0[n], nv1 = pl->off1[n];
   if (nv0 < 0 || nv1 < 0 || pl->off0[0] != 0 || pl->off1[0] != 0)
     return nm_fail(h, NM_ERR_BAD_ARG, "offsets must start at 0 and be non-decreasing");
+  if (!tb->row_pos_index || !tb->n0 || !tb->n1 || !tb->ks_dnum || !tb->ks_p)
+    return nm_fail(h, NM_ERR_BAD_ARG, "table lacks a mandatory output (row_pos_index,n0,n1,ks_dnum,ks_p)");
+  if (h->slab > 0 && n >= 2 * h->slab) return nm_detect_host_pipelined(h, pl, prm, tb, n_rows_out);
   if ((rc = nm_reserve(h, &h->d_vals0, sizeof(float) * (size_t)nm_padded_len(nv0))) != NM_OK) return rc;
   if ((rc = nm_reserve(h, &h->d_vals1, sizeof(float) * (size_t)nm_padded_len(nv1))) != NM_OK) return rc;
   if ((rc = nm_reserve(h, &h->d_off0, sizeof(int64_t) * (size_t)(n + 1))) != NM_OK) return rc;

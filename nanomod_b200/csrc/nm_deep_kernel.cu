@@ -69,8 +69,13 @@ __device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
   for (int i = 0; i < E; ++i) x[i] = s[tid * E + i];
   nm_sortnet<E>::run(x);
   constexpr int P = E * NM_DEEP_THREADS;
+  // fully unrolled (8 merge levels, <= 8 cross-thread strides each): every stride, and with it the
+  // choice shuffle / shared memory and the keep-min / keep-max mask, is a compile-time constant --
+  // the rolled form spent 40 % of its instructions on that index arithmetic (profiles/round2_deep_experiments.md)
+#pragma unroll
   for (int k = 2 * E; k <= P; k <<= 1) {
     nm_deep_exchange<E>(x, s, tid, k / E - 1, true);
+#pragma unroll
     for (int j = k >> 2; j >= E; j >>= 1) nm_deep_exchange<E>(x, s, tid, j / E, false);
 #pragma unroll
     for (int j = E >> 1; j > 0; j >>= 1) {
@@ -144,6 +149,7 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
   const int n0 = a.row_n0[r], n1 = a.row_n1[r];
   const long long s0 = a.off0[src], s1 = a.off1[src];
   const int P0 = nm_deep_p2(n0), P1 = nm_deep_p2(n1);
+  if (P0 + P1 > NM_DEEP_TIER_MAX_POOLED) return;  // does not fit shared memory: nm_huge.cu takes the row
   const long long al0 = s0 & ~3LL, al1 = s1 & ~3LL;
   const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
   // [raw A: P0 + 8 floats][raw B: P1 + 8 floats]; the arrays start at the row's first value
@@ -251,275 +257,6 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Binned variant (the default for deep rows of up to NM_DEEP2_MAX_T pooled reads).
-//
-// No sort at all.  The KS numerator is max over pooled x of |#{a <= x} * n1 - #{b <= x} * n0|
-// (searchsorted(side='right') of scipy's ks_2samp), and the rank statistics need #{. < x} as
-// well -- COUNTS, not an order.  So: map every value to one of NB value bins by a monotone
-// function (clamped affine map of mean +- 4.5 sd), counting-sort both groups by bin in shared
-// memory (count, scan, scatter), and let every element compare itself with the members of its OWN
-// bin only; everything in lower bins is smaller, by monotonicity, and is covered by the bin's
-// prefix count.  With NB ~ T/2 bins a bin holds a handful of values, so the work per element is
-// a few dozen instructions where the bitonic network above spends several hundred, and ties,
-// which a sort-and-walk has to treat specially, need nothing: tied values get equal counts.
-// Rows whose values pile up in few bins (massive ties, all-identical pools) would make the
-// in-bin comparisons quadratic; the scan phase measures that (sum of squared bin sizes) and such
-// rows, like rows too long for shared memory, are passed on to nm_deep_kernel through a list.
-// ------------------------------------------------------------------------------------------
-#define NM_DEEP2_MAX_T 10240      // pooled reads per position that fit 2 CTAs/SM
-#define NM_DEEP2_MAX_BINS 2048
-#define NM_DEEP2_WORK_FACTOR 48   // accepted in-bin comparisons per element (average) before falling back
-
-struct nm_deep2_args {
-  nm_kargs k;
-  int nbins;           // power of two <= NM_DEEP2_MAX_BINS
-  int smem_floats;     // capacity of each of the raw / binned areas (floats)
-  int32_t* fallback;   // rows handed to nm_deep_kernel
-  int* fallback_count;
-};
-
-__device__ __forceinline__ int nm_deep2_bin(float x, float lo, float scale, int nbins) {
-  // monotone non-decreasing in x: affine map, clamp, truncate
-  float t = (x - lo) * scale;
-  t = fminf(fmaxf(t, 0.0f), (float)(nbins - 1));
-  return (int)t;
-}
-
-// order-preserving int image of a float (for the per-bin min / max)
-__device__ __forceinline__ int nm_deep2_key(float x) {
-  const int b = __float_as_int(x);
-  return b >= 0 ? b : b ^ 0x7fffffff;
-}
-
-__device__ __forceinline__ long long nm_block_reduce_ll(long long v, long long* red, bool is_max) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = is_max ? nm_warp_max_ll(v) : nm_warp_sum_ll(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  long long t = red[0];
-  for (int w = 1; w < NM_DEEP_THREADS / 32; ++w) t = is_max ? (red[w] > t ? red[w] : t) : t + red[w];
-  return t;
-}
-
-__global__ void __launch_bounds__(NM_DEEP_THREADS, 2)
-nm_deep2_kernel(const nm_deep2_args g, const int want_u, const int want_t, const int want_m) {
-  extern __shared__ __align__(128) unsigned char nm_smem[];
-  __shared__ double red_d[NM_DEEP_THREADS / 32];
-  __shared__ long long red_l[NM_DEEP_THREADS / 32];
-  __shared__ double bcast[2];
-  __shared__ float bc_f[2];
-  const nm_kargs& a = g.k;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(nm_smem);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int NB = g.nbins;
-
-  const int64_t r = a.deep_rows[blockIdx.x];
-  const int32_t src = a.row_pos_index[r];
-  const int n0 = a.row_n0[r], n1 = a.row_n1[r];
-  const int T = n0 + n1;
-  const long long s0 = a.off0[src], s1 = a.off1[src];
-  const long long al0 = s0 & ~3LL, al1 = s1 & ~3LL;
-  const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
-  const int len0 = (sh0 + n0 + 3) & ~3, len1 = (sh1 + n1 + 3) & ~3;
-  if (len0 + len1 > g.smem_floats) {  // does not fit this launch's shared memory: the sorting kernel takes it
-    if (tid == 0) g.fallback[atomicAdd(g.fallback_count, 1)] = (int32_t)r;
-    return;
-  }
-  // [bar 16 B][raw: smem_floats][binned: smem_floats][startA NB+1][startB NB+1][curA NB][curB NB][bmin NB][bmax NB]
-  float* raw = reinterpret_cast<float*>(nm_smem + 16);
-  float* binned = raw + g.smem_floats;
-  int* startA = reinterpret_cast<int*>(binned + g.smem_floats);
-  int* startB = startA + NB + 1;
-  int* curA = startB + NB + 1;
-  int* curB = curA + NB;
-  int* bmin = curB + NB;  // smallest / largest value of a bin (order-preserving int images): a bin whose
-  int* bmax = bmin + NB;  // values are all equal needs no comparisons at all
-  const float* sa = raw + sh0;
-  const float* sb = raw + len0 + sh1;
-  float* ba = binned;
-  float* bb = binned + n0;
-
-  if (tid == 0) {
-    nm_mbar_init(bar, 1);
-    nm_mbar_expect_tx(bar, (uint32_t)(len0 + len1) * 4u);
-    nm_bulk_g2s(raw, a.vals0 + al0, (uint32_t)len0 * 4u, bar);
-    nm_bulk_g2s(raw + len0, a.vals1 + al1, (uint32_t)len1 * 4u, bar);
-  }
-  for (int b = tid; b < NB; b += NM_DEEP_THREADS) {
-    curA[b] = 0;
-    curB[b] = 0;
-    bmin[b] = 0x7fffffff;
-    bmax[b] = (int)0x80000000;
-  }
-  __syncthreads();
-  nm_mbar_wait(bar, 0);
-
-  // ---- exact fp64 moments (Welch t / --mstd), as in nm_deep_kernel; also give the binning range
-  double mean[2] = {0.0, 0.0}, var[2] = {0.0, 0.0};
-  for (int grp = 0; grp < 2; ++grp) {
-    const float* s = grp ? sb : sa;
-    const int n = grp ? n1 : n0;
-    double part = 0.0;
-    for (int k = tid; k < n; k += NM_DEEP_THREADS) part += (double)s[k];
-    part = nm_warp_sum_d(part);
-    __syncthreads();
-    if (lane == 0) red_d[wid] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
-      bcast[0] = t / (double)n;
-    }
-    __syncthreads();
-    const double m = bcast[0];
-    part = 0.0;
-    for (int k = tid; k < n; k += NM_DEEP_THREADS) {
-      const double d = (double)s[k] - m;
-      part += d * d;
-    }
-    part = nm_warp_sum_d(part);
-    __syncthreads();
-    if (lane == 0) red_d[wid] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < NM_DEEP_THREADS / 32; ++w) t += red_d[w];
-      bcast[1] = t / (double)(n - 1);
-    }
-    __syncthreads();
-    mean[grp] = m;
-    var[grp] = bcast[1];
-  }
-  if (tid == 0) {
-    // pooled range: the two group means +- 4.5 of the larger sd (values outside fall into the edge bins)
-    const double sd = sqrt(var[0] > var[1] ? var[0] : var[1]);
-    const double lo = (mean[0] < mean[1] ? mean[0] : mean[1]) - 4.5 * sd;
-    const double hi = (mean[0] > mean[1] ? mean[0] : mean[1]) + 4.5 * sd;
-    const double w = hi - lo;
-    bc_f[0] = (float)lo;
-    bc_f[1] = (w > 0.0 && w < 1e30) ? (float)((double)NB / w) : 0.0f;  // 0: everything in bin 0 -> falls back
-  }
-  __syncthreads();
-  const float lo = bc_f[0], scale = bc_f[1];
-
-  // ---- counting sort by bin: count, scan, scatter
-  for (int k = tid; k < T; k += NM_DEEP_THREADS) {
-    const float x = k < n0 ? sa[k] : sb[k - n0];
-    const int b = nm_deep2_bin(x, lo, scale, NB);
-    atomicAdd(k < n0 ? &curA[b] : &curB[b], 1);
-    const int key = nm_deep2_key(x);
-    if (key < bmin[b]) atomicMin(&bmin[b], key);
-    if (key > bmax[b]) atomicMax(&bmax[b], key);
-  }
-  __syncthreads();
-  {
-    // exclusive scan of NB counts per group: NB / 256 consecutive bins per thread + block scan
-    const int per = NB / NM_DEEP_THREADS > 0 ? NB / NM_DEEP_THREADS : 1;
-    const int b0 = tid * per;
-    int sumA = 0, sumB = 0;
-    long long work = 0;
-    if (b0 < NB) {
-      for (int b = b0; b < b0 + per; ++b) {
-        const int ca = curA[b], cb = curB[b];
-        sumA += ca;
-        sumB += cb;
-        work += bmin[b] >= bmax[b] ? (long long)(ca + cb) : (long long)(ca + cb) * (ca + cb);
-      }
-    }
-    // block exclusive scan of (sumA, sumB) packed in one 64-bit value
-    long long packed = ((long long)sumA << 32) | (unsigned)sumB;
-    long long inc = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    __shared__ long long wtot[NM_DEEP_THREADS / 32];
-    if (lane == 31) wtot[wid] = inc;
-    __syncthreads();
-    long long base = 0;
-    for (int w = 0; w < wid; ++w) base += wtot[w];
-    const long long ex = base + inc - packed;
-    int accA = (int)(ex >> 32), accB = (int)(ex & 0xffffffffLL);
-    if (b0 < NB) {
-      for (int b = b0; b < b0 + per; ++b) {
-        const int ca = curA[b], cb = curB[b];
-        startA[b] = accA;
-        startB[b] = accB;
-        curA[b] = accA;
-        curB[b] = accB;
-        accA += ca;
-        accB += cb;
-      }
-    }
-    if (tid == NM_DEEP_THREADS - 1) {
-      startA[NB] = n0;
-      startB[NB] = n1;
-    }
-    const long long total_work = nm_block_reduce_ll(work, red_l, false);
-    if (total_work > (long long)NM_DEEP2_WORK_FACTOR * T) {  // values pile up in few bins: sort instead
-      if (tid == 0) g.fallback[atomicAdd(g.fallback_count, 1)] = (int32_t)r;
-      return;
-    }
-  }
-  __syncthreads();
-  for (int k = tid; k < n0; k += NM_DEEP_THREADS) {
-    const float x = sa[k];
-    ba[atomicAdd(&curA[nm_deep2_bin(x, lo, scale, NB)], 1)] = x;
-  }
-  for (int k = tid; k < n1; k += NM_DEEP_THREADS) {
-    const float x = sb[k];
-    bb[atomicAdd(&curB[nm_deep2_bin(x, lo, scale, NB)], 1)] = x;
-  }
-  __syncthreads();
-
-  // ---- every element against its own bin (binned order: a warp's lanes share bins, the loads broadcast)
-  long long dmax = 0, r2 = 0, tie = 0;
-  for (int e = tid; e < T; e += NM_DEEP_THREADS) {
-    const bool is_a = e < n0;
-    const float x = is_a ? ba[e] : bb[e - n0];
-    const int b = nm_deep2_bin(x, lo, scale, NB);
-    const int a_lo = startA[b], a_hi = startA[b + 1], b_lo = startB[b], b_hi = startB[b + 1];
-    int ua = a_hi, ub = b_hi, la = a_lo, lb = b_lo;  // a bin of equal values: everything in it ties with x
-    if (bmin[b] < bmax[b]) {
-      ua = a_lo;
-      ub = b_lo;
-      for (int k = a_lo; k < a_hi; ++k) {
-        const float v = ba[k];
-        ua += v <= x ? 1 : 0;
-        la += v < x ? 1 : 0;
-      }
-      for (int k = b_lo; k < b_hi; ++k) {
-        const float v = bb[k];
-        ub += v <= x ? 1 : 0;
-        lb += v < x ? 1 : 0;
-      }
-    }
-    long long d = (long long)ua * n1 - (long long)ub * n0;
-    d = d < 0 ? -d : d;
-    dmax = d > dmax ? d : dmax;
-    if (want_u) {
-      const long long lo_r = la + lb, hi_r = ua + ub, t = hi_r - lo_r;
-      tie += t * t - 1;
-      r2 += is_a ? (lo_r + hi_r + 1) : 0;
-    }
-  }
-  nm_deep_acc tot;
-  tot.dnum = nm_block_reduce_ll(dmax, red_l, true);
-  tot.r2 = want_u ? nm_block_reduce_ll(r2, red_l, false) : 0;
-  tot.tie = want_u ? nm_block_reduce_ll(tie, red_l, false) : 0;
-  if (tid == 0) {
-    nm_row_out o;
-    o.two_u = 0;
-    o.u_stat = o.u_p = o.t_stat = o.t_p = 0.0;
-    nm_deep_finish(tot, n0, n1, want_u != 0, want_t != 0, mean[0], var[0], mean[1], var[1], &o);
-    nm_store_row(a, r, o, want_u != 0, want_t != 0);
-    if (want_m && a.acc_mom) reinterpret_cast<double4*>(a.acc_mom)[r] = make_double4(mean[0], var[0], mean[1], var[1]);
-  }
-}
-
 template <int EMAX>
 static int nm_launch_deep_t(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int smem_bytes, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(nm_deep_kernel<EMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -534,22 +271,4 @@ int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, in
   // a group can be at most max_p2 - NM_DEEP_MIN_P long
   if (max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS) return nm_launch_deep_t<16>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
   return nm_launch_deep_t<128>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
-}
-
-int nm_launch_deep2(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_t, int32_t* fallback,
-                    int* fallback_count, cudaStream_t st) {
-  nm_deep2_args g;
-  g.k = ka;
-  const int t = max_t < NM_DEEP2_MAX_T ? max_t : NM_DEEP2_MAX_T;
-  int nb = 256;
-  while (nb < NM_DEEP2_MAX_BINS && nb < t / 4) nb <<= 1;  // ~4 values per bin
-  g.nbins = nb;
-  g.smem_floats = (t + 8 + 3) & ~3;  // two slices rounded out to 16-byte boundaries
-  g.fallback = fallback;
-  g.fallback_count = fallback_count;
-  const int smem_bytes = 16 + 2 * g.smem_floats * (int)sizeof(float) + (6 * nb + 2) * (int)sizeof(int);
-  cudaError_t e = cudaFuncSetAttribute(nm_deep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) return (int)e;
-  nm_deep2_kernel<<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(g, want_u ? 1 : 0, want_t ? 1 : 0, want_m ? 1 : 0);
-  return (int)cudaGetLastError();
 }

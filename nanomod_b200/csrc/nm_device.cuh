@@ -105,13 +105,33 @@ struct nm_summary {
   int max_lane_slack;   // max over lane-tier rows of NM_LANE_TIER_MAX - max(n0,n1)  (-> shortest row)
   int n_le64, n_le104;  // class-binned calls: lane-tier rows whose network class is <= 64 / <= 104
   int n_filtered;       // candidates dropped by the coverage filter (0 => rows == candidates)
+  int n_cand_kept;      // candidates kept (rows)
   int bad_input;        // a candidate with a negative read count (offsets not monotonic) / segment id out of range
   int dense_retry;      // set by nm_lane_dense_kernel: the call does not have the shape the launch assumed
   int dense_tile_cursor;
   int max_deep_t;          // max over deep rows of n0 + n1
-  int deep_fallback_count; // deep rows the binned kernel handed to the sorting kernel
-  int pad;
+  int deep_fallback_count; // (reserved: a device-side count for nm_deep_kernel's row list)
+  int plan_le64, plan_le104;  // lane-tier candidates whose network class is <= 64 / <= 104, counted by nm_plan_count
+  int n_huge;                 // deep rows beyond the shared-memory deep tier (nm_huge.cu takes them)
+  unsigned long long huge_v0, huge_v1;  // their values in group 0 / 1
 };
+
+// The shape the dense lane kernel takes: rows == candidates, nothing deep, and the general path
+// would not split the call into one launch per size group (it does when the groups are not all the
+// same and one that is not the longest holds >= 7/8 of the rows: outliers must not make everybody
+// pay for their network).  Host (launch decision) and device (validation of a speculative launch).
+__host__ __device__ __forceinline__ bool nm_dense_shape_ok(const nm_summary& s) {
+  if (s.n_filtered != 0 || s.n_deep != 0 || s.bad_input != 0 || s.max_lane_n <= 0) return false;
+  const int gmin = nm_lane_group(NM_LANE_TIER_MAX - s.max_lane_slack), gmax = nm_lane_group(s.max_lane_n);
+  if (gmin == gmax) return true;
+  const long long n = (long long)s.plan_le64 + 0;  // rows in group 0
+  const long long g0 = n, g1 = (long long)s.plan_le104 - s.plan_le64;
+  const long long total = (long long)s.n_cand_kept;
+  const long long g2 = total - s.plan_le104;
+  const long long biggest = g0 > g1 ? (g0 > g2 ? g0 : g2) : (g1 > g2 ? g1 : g2);
+  const long long of_gmax = gmax == 2 ? g2 : gmax == 1 ? g1 : g0;
+  return !(biggest * 8 >= total * 7 && biggest != of_gmax);
+}
 
 
 __device__ __forceinline__ int nm_pow2ceil(int n) {
@@ -246,9 +266,7 @@ __host__ __device__ __forceinline__ int nm_deep_p2(int n) {
 // host-side launcher of the deep tier (nm_deep_kernel.cu)
 int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
                    cudaStream_t st);
-// binned deep kernel over all deep rows; rows it cannot take go to fallback[0 .. *fallback_count) (device)
-int nm_launch_deep2(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_t, int32_t* fallback,
-                    int* fallback_count, cudaStream_t st);
+
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st);

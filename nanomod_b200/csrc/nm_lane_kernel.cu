@@ -601,9 +601,7 @@ nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   {  // the shape this launch was sized for must be the shape the plan found
     const nm_summary* S = a.sum;
-    const bool shape_ok = S->n_filtered == 0 && S->n_deep == 0 && S->bad_input == 0 &&
-                          nm_lane_class(S->max_lane_n) == a.class_n &&
-                          nm_lane_group(NM_LANE_TIER_MAX - S->max_lane_slack) == nm_lane_group(S->max_lane_n);
+    const bool shape_ok = nm_dense_shape_ok(*S) && nm_lane_class(S->max_lane_n) == a.class_n;
     if (!shape_ok) {
       if (blockIdx.x == 0 && threadIdx.x == 0) a.sum->dense_retry = 1;
       return;

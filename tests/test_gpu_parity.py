@@ -250,13 +250,34 @@ def test_error_codes(det):
             det.handle.detect_host(pl, prm, tb)
         assert e.value.code == code, (prm.min_coverage, prm.nb, e.value)
     assert det.handle.detect_host(pl, _lib.nm_params(5, 2, 2.0, 0, 0, 0, 0), tb) == 64
-    # too deep for the shared-memory tier
-    n = 40000
-    big = nm.Pileup.from_arrays(np.zeros(n, np.float32), np.array([0, n]), np.ones(n, np.float32), np.array([0, n]),
-                                np.zeros(1, np.int32))
-    with pytest.raises(nm.NmError) as e:
-        det.detect(big, nm.DetectOptions(testMethod="ks"))
-    assert e.value.code == 5
+
+
+def test_rows_beyond_the_shared_memory_deep_tier(det):
+    """The reference has no depth limit (getKStest takes any two lists, myDetect.py:327-343): rows
+    too long for the deep tier's shared memory go through the global-memory path (nm_huge.cu)
+    instead of failing the call -- here next to ordinary and deep rows, with ties."""
+    rng = np.random.default_rng(17)
+    c0 = np.array([30, 40000, 25, 3000, 70000, 30, 30], np.int64)
+    c1 = np.array([28, 30000, 25, 2500, 9000, 31, 20000], np.int64)
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0.02, 1, off1[-1]), 2).astype(np.float32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(len(c0), dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=2, both_combinations=True, mstd=True)
+    t = det.detect(p, opt)
+    assert len(t) == len(c0)
+    for r in range(len(c0)):
+        ref = o.per_position(p.group(0, r).astype(np.float64), p.group(1, r).astype(np.float64))
+        assert t.ks_dnum[r] == ref["dnum"] and t.two_u[r] == ref["twoU"], r
+        for got, want in ((t.ks_p[r], ref["pks"]), (t.u_p[r], ref["pu"]), (t.t_stat[r], ref["t"]), (t.t_p[r], ref["pt"]),
+                          (t.ks_d[r], ref["D"])):
+            assert got == want or abs(got - want) <= RTOL * abs(want), (r, got, want)
+        a = p.group(0, r).astype(np.float64)
+        assert abs(t.moments[r, 0] - a.mean()) <= 1e-9 and abs(t.moments[r, 1] - a.var(ddof=1)) <= 1e-9 * a.var(ddof=1)
+    res = vec(p, opt)
+    ok, i = close(t.stouffer_p, res["stouffer_p"])
+    assert ok, i
 
 
 def test_reference_seam_mirror(det):
@@ -706,3 +727,59 @@ def test_sharded_device_heads_and_text(det, method, rank_use, tmp_path):
     # one "rank" holding everything: the public entry point
     res = sd.detect_shard(nm.DevicePileup.from_host(p, "cuda:0"), 0, p.n_pos, 0, opt)
     assert sd.called_sites(res, p.seg_names) == full.called_sites()
+
+
+# ---------------------------------------------------------------------------------------------
+# pipelined host entry (slabs with halos, copies overlapped with compute) == the one-piece call
+# ---------------------------------------------------------------------------------------------
+def _detector_with_env(**env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return nm.Detector(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("slab", [257, 1000, 4096])
+def test_pipelined_host_entry_equals_one_piece(slab):
+    whole = _detector_with_env(NANOMOD_B200_SLAB=0)
+    piped = _detector_with_env(NANOMOD_B200_SLAB=slab)
+    cases = [
+        (nm.synthetic_pileup(9000, 30, 28, round_decimals=2), nm.DetectOptions(neighborPvalues=3, both_combinations=True)),
+        (nm.synthetic_pileup(9000, 12, 14, drop_frac1=0.03, two_strands=True, poisson=True, clip=(2, 60), round_decimals=3),
+         nm.DetectOptions(neighborPvalues=5, testMethod="fisher", mstd=True)),
+        (nm.synthetic_pileup(9000, 20, 20, drop_frac1=0.5), nm.DetectOptions(neighborPvalues=2, testMethod="ks", want_u=False, want_t=False)),
+        (nm.synthetic_pileup(9000, 40, 40), nm.DetectOptions(neighborPvalues=0, testMethod="stouffer")),
+    ]
+    for p, opt in cases:
+        a, b = whole.detect(p, opt), piped.detect(p, opt)
+        _tables_identical(a, b)
+        if opt.mstd:
+            assert np.array_equal(a.moments, b.moments)
+    # deep rows and the down-sampling branch inside slabs
+    rng = np.random.default_rng(3)
+    L = 3000
+    c0 = np.full(L, 20, np.int64)
+    c1 = np.full(L, 24, np.int64)
+    for i in (5, 256, 257, 1000, 1001, 2999):
+        c0[i], c1[i] = 700, 300
+    c0[1500], c1[1500] = 150, 180
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    p = nm.Pileup.from_arrays(np.round(rng.normal(0, 1, off0[-1]), 3), off0, np.round(rng.normal(0.1, 1, off1[-1]), 3), off1,
+                              np.arange(L, dtype=np.int32))
+    opt = nm.DetectOptions(neighborPvalues=3, both_combinations=True)
+    _tables_identical(whole.detect(p, opt), piped.detect(p, opt))
+    keep = np.ones(L, bool)
+    keep[[5, 256, 257, 1000, 1001, 2999]] = False
+    q = nm.Pileup.from_arrays(p.vals0[:off0[-1]][np.repeat(keep, c0)], np.concatenate([[0], np.cumsum(c0[keep])]),
+                              p.vals1[:off1[-1]][np.repeat(keep, c1)], np.concatenate([[0], np.cumsum(c1[keep])]),
+                              np.arange(L, dtype=np.int32)[keep])
+    ds = nm.DetectOptions(neighborPvalues=2, testMethod="stouffer", coverages="100-100", downsampling=64)
+    _tables_identical(whole.detect(q, ds), piped.detect(q, ds))
