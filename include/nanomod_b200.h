@@ -162,10 +162,23 @@ typedef struct nm_head_row {
   int32_t seg, pos;  /* -1 without geometry */
   int32_t full_nbhd;
   int32_t reserved;
+  uint64_t key[3];   /* sort images of the row's (combined, KS, U) keys, 0 where a key is absent: unsigned
+                        lexicographic order of (key[0], key[1], key[2]), then row ascending (descending when
+                        reverse), IS the ranking -- heads of several shards merge by them */
 } nm_head_row;
 int nm_rank_head_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
                         int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
                         nm_head_row* rows_out, int64_t cap, int64_t* n_head, void* cuda_stream);
+
+/* The same selection left on the DEVICE, unsorted, without waiting for anything: records_dev has
+ * room for cap + 1 entries; entry 0 is a header (row = entries that follow, key[0] = n_rows,
+ * key[1] = 1 when they are ALL the rows, key[2] = exponent bin of the cut), entries 1.. are every row
+ * of the bins up to the cut -- the cut is lowered, if need be, to the bins that fit `cap` entries
+ * (header row = 0 and key[1] = 0: not even the first occupied bin fits).  This is what a rank of a
+ * sharded run hands to the all-gather; sorting the gathered entries by (key, row) merges the heads. */
+int nm_rank_head_select_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                               int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                               nm_head_row* records_dev, int64_t cap, void* cuda_stream);
 
 /* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
  * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`

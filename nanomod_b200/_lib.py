@@ -26,7 +26,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_rank_head_device",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_rank_head_device", "nm_rank_head_select_device",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -66,7 +66,8 @@ class nm_head_geometry(C.Structure):
                 ("n_rows_total", C.c_int64), ("nearby", C.c_int32), ("reserved", C.c_int32)]
 
 
-HEAD_ROW_DTYPE = [("row", "<i8"), ("seg", "<i4"), ("pos", "<i4"), ("full_nbhd", "<i4"), ("reserved", "<i4")]
+HEAD_ROW_DTYPE = [("row", "<i8"), ("seg", "<i4"), ("pos", "<i4"), ("full_nbhd", "<i4"), ("reserved", "<i4"),
+                  ("key", "<u8", (3,))]
 
 
 class nm_text_columns(C.Structure):
@@ -126,6 +127,9 @@ def load():
     lib.nm_rank_head_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                         C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                         C.c_void_p]
+    lib.nm_rank_head_select_device.restype = C.c_int
+    lib.nm_rank_head_select_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
+                                               C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.c_void_p]
     lib.nm_rank_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                  C.c_void_p]
     lib.nm_format_bound.restype = C.c_int64
@@ -225,6 +229,12 @@ class Handle:
                                                   None if geometry is None else C.byref(geometry), rows_out, cap,
                                                   C.byref(n_head), C.c_void_p(stream)))
         return int(n_head.value)
+
+    def rank_head_select_device(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, want: int, geometry,
+                                records_dev: int, cap: int, stream: int = 0) -> None:
+        self._check(self._lib.nm_rank_head_select_device(self._h, key_comb, key_ks, key_u, n_rows, 1 if reverse else 0, want,
+                                                         None if geometry is None else C.byref(geometry), records_dev,
+                                                         cap, C.c_void_p(stream)))
 
     def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,
                             stream: int = 0) -> None:

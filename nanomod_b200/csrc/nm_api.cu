@@ -1259,7 +1259,7 @@ extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const d
     if (rc != NM_OK) return rc;
     int launches = 0;
     const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want, dev_cap, geo, h->d_rank.p,
-                                                   h->sm_count, &launches, st);
+                                                   nullptr, h->sm_count, &launches, st);
     h->launches += launches;
     if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
     NM_CUDA(h, cudaMemcpyAsync(info, (const unsigned*)h->d_rank.p + 4096, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -1303,9 +1303,45 @@ extern "C" int nm_rank_head_device(nm_handle* h, const double* key_comb, const d
     rows_out[i].pos = recs[i].pos;
     rows_out[i].full_nbhd = recs[i].full_nbhd;
     rows_out[i].reserved = 0;
+    for (int k = 0; k < 3; ++k) rows_out[i].key[k] = recs[i].key[k];
   }
   if (heap) free(heap);
   *n_head = n_sel;
+  return NM_OK;
+}
+
+// The same selection left ON THE DEVICE, unsorted, in the caller's record buffer: what a rank hands
+// to the all-gather of a sharded run.  Nothing is waited for -- three streaming kernels and a header.
+extern "C" int nm_rank_head_select_device(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                                          int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                                          nm_head_row* records_dev, int64_t cap, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!records_dev || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "records_dev is NULL or cap <= 0");
+  if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
+  if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
+  nm_head_geo geo;
+  memset(&geo, 0, sizeof(geo));
+  if (geometry) {
+    if (!geometry->pos || !geometry->seg || geometry->row_offset < 0 || geometry->nearby < 0 ||
+        geometry->row_offset + n_rows > geometry->n_rows_total)
+      return nm_fail(h, NM_ERR_BAD_ARG, "head geometry: NULL pos/seg or a row range outside the row list");
+    geo.row_pos_index = geometry->row_pos_index; geo.pos = geometry->pos; geo.seg = geometry->seg;
+    geo.row_offset = geometry->row_offset; geo.n_rows_total = geometry->n_rows_total; geo.nearby = geometry->nearby;
+  }
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int rc = nm_reserve(h, &h->d_rank, nm_head_scratch_bytes(1));
+  if (rc != NM_OK) return rc;
+  if (n_rows == 0) {
+    NM_CUDA(h, cudaMemsetAsync(records_dev, 0, sizeof(nm_head_row), st));
+    return NM_OK;
+  }
+  int launches = 0;
+  static_assert(sizeof(nm_head_record) == sizeof(nm_head_row), "device and ABI head records must have one layout");
+  const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want > 0 ? want : 1, cap, geo,
+                                                 h->d_rank.p, (nm_head_record*)records_dev, h->sm_count, &launches, st);
+  h->launches += launches;
+  if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
   return NM_OK;
 }
 

@@ -204,35 +204,75 @@ __global__ void __launch_bounds__(256) nm_head_hist(const double* __restrict__ k
     if (h[b]) atomicAdd(&hist[b], h[b]);
 }
 
+// largest bin b with cum(b) <= limit (-1 if none), smallest bin b with cum(b) >= want; by one thread
+// over the 256 partial sums and then inside one 16-bin chunk
+__device__ void nm_head_search(const unsigned* hist, const unsigned* part, unsigned want, unsigned limit, int* cut_want,
+                               unsigned* cum_want, int* cut_fit, unsigned* cum_fit) {
+  constexpr int per = NM_HEAD_BINS / 256;
+  unsigned cum = 0;
+  *cut_want = NM_HEAD_BINS - 1;
+  *cut_fit = -1;
+  *cum_fit = 0;
+  bool have_want = false;
+  for (int t = 0; t < 256; ++t) {
+    const unsigned nxt = cum + part[t];
+    const bool w_here = !have_want && nxt >= want;
+    const bool f_here = cum <= limit && nxt > limit;
+    if (w_here || f_here) {
+      unsigned c = cum;
+      for (int b = 0; b < per; ++b) {
+        c += hist[t * per + b];
+        if (!have_want && c >= want) {
+          *cut_want = t * per + b;
+          *cum_want = c;
+          have_want = true;
+        }
+        if (c <= limit) {
+          *cut_fit = t * per + b;
+          *cum_fit = c;
+        }
+      }
+    } else if (nxt <= limit) {
+      *cut_fit = t * per + per - 1;
+      *cum_fit = nxt;
+    }
+    cum = nxt;
+  }
+  if (!have_want) *cum_want = cum;
+}
+
 // hist[NM_HEAD_BINS] = cut bin, hist[NM_HEAD_BINS + 1] = rows in bins <= cut, [+2] = compaction cursor (0)
-__global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want) {
+__global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want, unsigned cap, int fit_cap) {
   __shared__ unsigned part[256];
   unsigned s = 0;
   for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned cum = 0;
-    int cut = NM_HEAD_BINS - 1;
-    bool found = false;
-    for (int t = 0; t < 256 && !found; ++t) {
-      if (cum + part[t] >= want) {
-        for (int b = 0; b < NM_HEAD_BINS / 256; ++b) {
-          cum += hist[t * (NM_HEAD_BINS / 256) + b];
-          if (cum >= want) {
-            cut = t * (NM_HEAD_BINS / 256) + b;
-            found = true;
-            break;
-          }
-        }
-      } else {
-        cum += part[t];
-      }
+    int cut_w, cut_f;
+    unsigned cum_w, cum_f;
+    nm_head_search(hist, part, want, cap, &cut_w, &cum_w, &cut_f, &cum_f);
+    int cut = cut_w;
+    unsigned cum = cum_w;
+    if (fit_cap && cum_w > cap) {  // the caller's buffer is fixed: stop at the last bin that still fits
+      cut = cut_f;
+      cum = cum_f;
     }
-    hist[NM_HEAD_BINS] = (unsigned)cut;
-    hist[NM_HEAD_BINS + 1] = cum;  // all rows when `want` exceeds them
+    hist[NM_HEAD_BINS] = (unsigned)cut;  // 0xffffffff: not even the first occupied bin fits
+    hist[NM_HEAD_BINS + 1] = cum;
     hist[NM_HEAD_BINS + 2] = 0;
   }
+}
+
+__global__ void nm_head_header(const unsigned* __restrict__ hist, nm_head_record* __restrict__ rec, long long n, unsigned cap) {
+  nm_head_record hdr;
+  const unsigned sel = hist[NM_HEAD_BINS + 1];
+  hdr.row = sel <= cap ? sel : 0;
+  hdr.seg = hdr.pos = hdr.full_nbhd = hdr.pad = 0;
+  hdr.key[0] = (unsigned long long)n;
+  hdr.key[1] = (sel == (unsigned)n && sel <= cap) ? 1ull : 0ull;
+  hdr.key[2] = hist[NM_HEAD_BINS];
+  rec[0] = hdr;
 }
 
 __global__ void __launch_bounds__(256)
@@ -240,6 +280,7 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
                 int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap,
                 const nm_head_geo geo) {
   const unsigned cut = hist[NM_HEAD_BINS];
+  if (cut == 0xffffffffu) return;
   for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256) {
     const unsigned long long i0 = nm_head_image(k0, r, reverse);
     if ((unsigned)(i0 >> 52) <= cut) {
@@ -248,8 +289,8 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
         nm_head_record rec;
         rec.row = (long long)r;
         rec.key[0] = i0;
-        rec.key[1] = nm_head_image(k1, r, reverse);
-        rec.key[2] = nm_head_image(k2, r, reverse);
+        rec.key[1] = k1 ? nm_head_image(k1, r, reverse) : 0ull;
+        rec.key[2] = k2 ? nm_head_image(k2, r, reverse) : 0ull;
         rec.seg = rec.pos = -1;
         rec.full_nbhd = 0;
         rec.pad = 0;
@@ -281,9 +322,10 @@ size_t nm_head_scratch_bytes(int64_t cap) {
 }
 
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                const nm_head_geo& geo, void* scratch, int sm_count, int* launches, cudaStream_t st) {
+                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st) {
   unsigned* hist = (unsigned*)scratch;
-  nm_head_record* recs = (nm_head_record*)((unsigned char*)scratch + nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)));
+  nm_head_record* recs = records ? records + 1
+                                 : (nm_head_record*)((unsigned char*)scratch + nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)));
   // primary key = the first present column, as in nm_rank_run (absent columns do not order)
   const double* cols[3] = {comb, ks, u};
   const double* k[3] = {nullptr, nullptr, nullptr};
@@ -295,8 +337,12 @@ int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * (int64_t)sm_count) blocks = 8 * (int64_t)sm_count;
   nm_head_hist<<<(unsigned)blocks, 256, 0, st>>>(k[0], n, reverse, hist);
-  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n));
+  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n), (unsigned)cap, records ? 1 : 0);
   nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap, geo);
   *launches += 3;
+  if (records) {
+    nm_head_header<<<1, 1, 0, st>>>(hist, records, (long long)n, (unsigned)cap);
+    *launches += 1;
+  }
   return (int)cudaGetLastError();
 }

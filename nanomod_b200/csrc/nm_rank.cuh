@@ -27,12 +27,12 @@ int nm_group_sort_run(int64_t n, int32_t* perm_a, int32_t* perm_b, const int32_t
 // lowest exponent bins that together hold >= want rows.  scratch (device): a 4096 + 4 word
 // histogram block followed by `cap` records; word [4096 + 1] = rows selected, [4096 + 2] = rows
 // the compaction met (== selected; more than cap => the records are truncated).
-struct nm_head_record {
+struct nm_head_record {  // same layout as nm_head_row (include/nanomod_b200.h)
   long long row;
-  unsigned long long key[3];  // order-preserving images of (combined, KS, U); 0 where absent
   int seg, pos;               // the row's segment id / position (-1 without geometry)
   int full_nbhd;              // plot1's neighbourhood test passed
   int pad;
+  unsigned long long key[3];  // sort images of (combined, KS, U); 0 where absent
 };
 // optional geometry for the records: the ranked rows are rows [row_offset, row_offset + n) of a row
 // list of n_rows_total rows (row -> candidate through row_pos_index, identity when NULL)
@@ -45,5 +45,8 @@ struct nm_head_geo {
   int nearby;
 };
 size_t nm_head_scratch_bytes(int64_t cap);
+// records == NULL: the records follow the histogram block inside scratch.  Otherwise records[0] becomes
+// a header (row = rows selected, key[0] = n, key[1] = 1 when the head holds every row, key[2] = cut bin)
+// and records[1 .. cap] the selection; the cut is lowered to the bins that fit `cap` records.
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                const nm_head_geo& geo, void* scratch, int sm_count, int* launches, cudaStream_t st);
+                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st);

@@ -535,6 +535,28 @@ class Detector:
                     raise
                 cap = min(n_rows, cap * 8)
 
+    def rank_head_select_device(self, out: Dict[str, "object"], n_rows: int, options: DetectOptions, want: int,
+                                records, cap: int, geometry=None, stream: Optional[int] = None) -> None:
+        """``rank_head_device`` without leaving the GPU and without waiting: fills ``records`` (uint8
+        CUDA tensor of (cap + 1) * 48 bytes, ``sharded.HEAD_REC`` entries; entry 0 is a header) with
+        the UNSORTED rows of the ranking's head -- what a rank hands to the all-gather."""
+        import torch
+        use_p = options.rankUse == "pv"
+        m = options.testMethod
+        comb = None if m == "ks" else out[("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat")]
+        ks = out["ks_p" if use_p else "ks_d"]
+        u = out.get("u_p" if use_p else "u_stat") if options.want_u else None
+        if stream is None:
+            stream = torch.cuda.current_stream(ks.device).cuda_stream
+        geo = None
+        if geometry is not None:
+            rpi, pos, seg, row_offset, n_total, nearby = geometry
+            geo = _lib.nm_head_geometry(None if rpi is None else rpi.data_ptr(), pos.data_ptr(), seg.data_ptr(),
+                                        int(row_offset), int(n_total), int(nearby), 0)
+        self.handle.rank_head_select_device(None if comb is None else comb.data_ptr(), ks.data_ptr(),
+                                            None if u is None else u.data_ptr(), n_rows, not use_p, want, geo,
+                                            records.data_ptr(), cap, stream)
+
     def pack_records(self, out: Dict[str, "object"], row_lo: int, n: int, options: DetectOptions, records,
                      stream: Optional[int] = None) -> None:
         """Device-resident table -> 28-byte records {ks_dnum, ks_p, comb stat, comb p} of rows

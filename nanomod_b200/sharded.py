@@ -29,6 +29,10 @@ from . import _lib
 from .detect import DetectOptions, SignTestTable
 from .pileup import Pileup
 
+HEAD_REC = np.dtype([("row", "<i8"), ("seg", "<i4"), ("pos", "<i4"), ("full_nbhd", "<i4"), ("reserved", "<i4"),
+                     ("key", "<u8", (3,))])  # == nm_head_row (48 bytes)
+HEAD_CAP = 16384   # records per rank in the exchange buffer (a longer head is cut: still a valid, incomplete head)
+
 
 def plan_shards(off0: np.ndarray, off1: np.ndarray, world: int) -> List[Tuple[int, int]]:
     """Contiguous candidate ranges [lo, hi), one per rank, balanced by the number of values
@@ -194,20 +198,48 @@ class ShardedDetector:
         rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
         rows = self.engine.rank_head_device(core, res.n_core, o, want,
                                             geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
-        import torch
-        idx = torch.from_numpy(np.ascontiguousarray(rows["row"])).to(res.dev.pos.device)
-        m = o.testMethod
-        names = [None if m == "ks" else ("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat"),
-                 "ks_p" if use_p else "ks_d", ("u_p" if use_p else "u_stat") if o.want_u else None]
-        keys = torch.zeros((idx.numel(), 3), dtype=torch.float64, device=idx.device)
-        for k, nme in enumerate(names):
-            if nme is not None:
-                keys[:, k] = core[nme][idx]
         return LocalHead(rows["row"].astype(np.int64), rows["seg"].astype(np.int32), rows["pos"].astype(np.int32),
-                         keys.cpu().numpy(), rows["full_nbhd"] != 0, res.n_core, len(rows) == res.n_core)
+                         np.ascontiguousarray(rows["key"]), rows["full_nbhd"] != 0, res.n_core, len(rows) == res.n_core)
+
+    def gather_heads(self, res: ShardResult, want: int, cap: int = HEAD_CAP):
+        """The multi-GPU exchange of a step, all on the device and without a host wait: three
+        streaming kernels select the head of this rank's ranking into a record buffer
+        (nm_rank_head_select_device) and ONE NCCL all-gather hands every rank all heads.  Returns the
+        gathered records as a CUDA tensor; ``heads_from_gathered`` parses it when the ranking is needed."""
+        import torch
+        import torch.distributed as dist
+        o = res.options
+        world, _ = self._world()
+        dev = res.dev.pos.device
+        key = (str(dev), cap, world)
+        if getattr(self, "_head_key", None) != key:
+            self._head_key = key
+            self._head_mine = torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev)
+            self._head_all = torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev)
+        core = {c: res.out[c][res.r_lo:res.r_hi] for c in ("ks_p", "ks_d", "u_p", "u_stat", "fisher_p", "fisher_stat",
+                                                           "stouffer_p", "stouffer_stat") if c in res.out}
+        rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
+        self.engine.rank_head_select_device(core, res.n_core, o, want, self._head_mine, cap,
+                                            geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
+        if world == 1:
+            return self._head_mine
+        dist.all_gather_into_tensor(self._head_all, self._head_mine, group=self.group)
+        return self._head_all
+
+    def heads_from_gathered(self, gathered, options: DetectOptions, cap: int = HEAD_CAP) -> List[LocalHead]:
+        """gathered device records -> every rank's head, each in its own ranking order"""
+        buf = gathered.cpu().numpy().view(HEAD_REC)
+        world = buf.shape[0] // (cap + 1)
+        heads = []
+        for h in unpack_heads(buf, world, cap):
+            order = np.lexsort((h.rows if options.rankUse == "pv" else -h.rows, h.keys[:, 2], h.keys[:, 1], h.keys[:, 0])) \
+                if h.rows.shape[0] else np.zeros(0, np.int64)
+            heads.append(LocalHead(h.rows[order], h.seg[order], h.pos[order], h.keys[order], h.full_nbhd[order],
+                                   h.n_core, h.complete))
+        return heads
 
     def merged_head(self, res: ShardResult, want: int) -> MergedHead:
-        heads = exchange_heads(self.local_head(res, want), self.group, res.dev.pos.device)
+        heads = self.heads_from_gathered(self.gather_heads(res, want), res.options)
         return merge_heads(heads, res.options.rankUse != "pv")
 
     def _called_sites(self, head_fn, options: DetectOptions, seg_names, device=None, want: Optional[int] = None):
@@ -223,7 +255,18 @@ class ShardedDetector:
 
     def called_sites(self, res: ShardResult, seg_names, want: Optional[int] = None) -> List[Tuple[str, str, int]]:
         """The reference's called-site list (same on every rank) from the sharded, device-resident table."""
-        return self._called_sites(lambda w: self.local_head(res, w), res.options, seg_names, res.dev.pos.device, want)
+        o = res.options
+        if o.RegionRankbyST != 0:
+            raise NotImplementedError("region ranking needs the whole table: use gather_tables / SignTestTable")
+        want = want or max(64 * o.topN, 1024)
+        cap = HEAD_CAP
+        while True:
+            m = merge_heads(self.heads_from_gathered(self.gather_heads(res, want, cap), o, cap), o.rankUse != "pv")
+            sites, final = greedy_sites(m, o, seg_names)
+            if final or m.complete:
+                return sites
+            want *= 8  # the walk ran past what the heads guarantee: longer heads (same decision on every rank)
+            cap = max(cap, 2 * want)
 
     def called_sites_host(self, t: SignTestTable, core_lo: int, core_hi: int, want: Optional[int] = None):
         """Same from a host table of this rank's rows (core rows [core_lo, core_hi) + halo rows)."""
@@ -299,7 +342,8 @@ class LocalHead:
     rows: np.ndarray       # int64: row index inside the rank's core rows
     seg: np.ndarray        # int32
     pos: np.ndarray        # int32
-    keys: np.ndarray       # float64 [K, 3]: (combined, KS, U) p-values or statistics; 0 where a key is absent
+    keys: np.ndarray       # uint64 [K, 3]: sort images of (combined, KS, U) -- ascending unsigned order is the ranking
+                           # (already complemented for rankUse='st'); 0 where a key is absent
     full_nbhd: np.ndarray  # bool: rows r-nearby .. r+nearby are one contiguous run (plot1's requirement)
     n_core: int            # core rows this rank holds in total
     complete: bool         # the head holds every core row
@@ -314,21 +358,19 @@ def local_head_from_table(t: SignTestTable, core_lo: int, core_hi: int, want: in
     cols = [None if comb is None else (comb[1] if use_p else comb[0]), t.ks_p if use_p else t.ks_d,
             None if t.u_p is None else (t.u_p if use_p else t.u_stat)]
     n = core_hi - core_lo
-    keys = np.zeros((n, 3))
-    for k, c in enumerate(cols):
-        if c is not None:
-            keys[:, k] = c[core_lo:core_hi]
-    img = [key_image(keys[:, k]) for k in range(3)]
-    order = np.lexsort((np.arange(n), img[2], img[1], img[0]))
-    if not use_p:
-        order = order[::-1]
+    img = []
+    for c in cols:
+        k = np.zeros(n, np.uint64) if c is None else key_image(c[core_lo:core_hi])
+        img.append(k if (use_p or c is None) else ~k)
+    order = np.lexsort((np.arange(n) if use_p else -np.arange(n), img[2], img[1], img[0]))
     k = min(n, max(want, 0))
     # keep whole groups of equal primary keys, as the device selection does (it keeps whole exponent bins)
     while 0 < k < n and img[0][order[k]] == img[0][order[k - 1]]:
         k += 1
     rows = order[:k].astype(np.int64)
+    keys = np.stack([i[rows] for i in img], axis=1) if k else np.zeros((0, 3), np.uint64)
     return LocalHead(rows, t.seg[core_lo:core_hi][rows].astype(np.int32), t.pos[core_lo:core_hi][rows].astype(np.int32),
-                     keys[rows], neighbourhood_flags(t.seg, t.pos, rows + core_lo, nearby_rows(o)), n, k == n)
+                     keys, neighbourhood_flags(t.seg, t.pos, rows + core_lo, nearby_rows(o)), n, k == n)
 
 
 def neighbourhood_flags(seg: np.ndarray, pos: np.ndarray, rows: np.ndarray, nearby: int) -> np.ndarray:
@@ -344,38 +386,47 @@ def neighbourhood_flags(seg: np.ndarray, pos: np.ndarray, rows: np.ndarray, near
     return okk & (seg[lo_c] == seg[hi_c]) & (pos[hi_c].astype(np.int64) - pos[lo_c].astype(np.int64) == 2 * nearby)
 
 
-_HEAD_WIDTH = 8  # row, seg, pos, k0, k1, k2, full_nbhd, rank-local ordinal
 
 
-def exchange_heads(local: LocalHead, group=None, device=None) -> List[LocalHead]:
-    """all-gather of every rank's head (fixed-capacity float64 records; two small collectives)"""
+def pack_head(local: LocalHead, cap: int = HEAD_CAP) -> np.ndarray:
+    """[cap + 1] records: a header record followed by the head (cut at `cap`)"""
+    k = min(local.rows.shape[0], cap)
+    buf = np.zeros(cap + 1, dtype=HEAD_REC)
+    buf["row"][0] = k
+    buf["key"][0, 0] = local.n_core
+    buf["key"][0, 1] = 1 if (local.complete and k == local.rows.shape[0]) else 0
+    buf["row"][1:k + 1], buf["seg"][1:k + 1], buf["pos"][1:k + 1] = local.rows[:k], local.seg[:k], local.pos[:k]
+    buf["full_nbhd"][1:k + 1] = local.full_nbhd[:k]
+    buf["key"][1:k + 1] = local.keys[:k]
+    return buf
+
+
+def unpack_heads(buf: np.ndarray, world: int, cap: int = HEAD_CAP) -> List[LocalHead]:
+    out = []
+    for r in range(world):
+        b = buf[r * (cap + 1):(r + 1) * (cap + 1)]
+        k = int(b["row"][0])
+        out.append(LocalHead(b["row"][1:k + 1].astype(np.int64), b["seg"][1:k + 1].copy(), b["pos"][1:k + 1].copy(),
+                             b["key"][1:k + 1].copy(), b["full_nbhd"][1:k + 1] != 0, int(b["key"][0, 0]), bool(b["key"][0, 1])))
+    return out
+
+
+def exchange_heads(local: LocalHead, group=None, device=None, cap: int = HEAD_CAP, parse: bool = True):
+    """all-gather of every rank's head: ONE collective of fixed-size records (NCCL over NVLink on
+    GPUs, gloo on the CPU).  Returns the list of heads (or the raw gathered record array with
+    ``parse=False``: the exchange is then complete and the host-side merge can happen later)."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return [local]
+        return [local] if parse else pack_head(local, cap)
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
     dev = torch.device("cpu") if backend == "gloo" else (device or torch.device("cuda", torch.cuda.current_device()))
-    k = local.rows.shape[0]
-    meta = torch.tensor([k, local.n_core, 1 if local.complete else 0], dtype=torch.int64, device=dev)
-    metas = [torch.empty_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    metas = [m.cpu().numpy() for m in metas]
-    cap = int(max(m[0] for m in metas))
-    rec = np.zeros((max(cap, 1), _HEAD_WIDTH))
-    rec[:k, 0], rec[:k, 1], rec[:k, 2] = local.rows, local.seg, local.pos
-    rec[:k, 3:6] = local.keys
-    rec[:k, 6] = local.full_nbhd
-    mine = torch.from_numpy(rec).to(dev)
-    bufs = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(bufs, mine, group=group)
-    out = []
-    for r in range(world):
-        kr = int(metas[r][0])
-        a = bufs[r][:kr].cpu().numpy()
-        out.append(LocalHead(a[:, 0].astype(np.int64), a[:, 1].astype(np.int32), a[:, 2].astype(np.int32),
-                             np.ascontiguousarray(a[:, 3:6]), a[:, 6] != 0, int(metas[r][1]), bool(metas[r][2])))
-    return out
+    mine = torch.from_numpy(pack_head(local, cap).view(np.uint8)).to(dev, non_blocking=True)
+    gathered = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    buf = gathered.cpu().numpy().view(HEAD_REC)
+    return unpack_heads(buf, world, cap) if parse else buf
 
 
 @dataclass
@@ -398,12 +449,8 @@ def merge_heads(heads: Sequence[LocalHead], reverse: bool) -> MergedHead:
     base = np.concatenate([[0], np.cumsum([h.n_core for h in heads])])
     rank = np.concatenate([np.full(h.rows.shape[0], r, np.int32) for r, h in enumerate(heads)])
     row = np.concatenate([h.rows + base[r] for r, h in enumerate(heads)]).astype(np.int64)
-    keys = np.concatenate([h.keys.reshape(-1, 3) for h in heads], axis=0)
-    img = [key_image(keys[:, k]) for k in range(3)]
-    if reverse:
-        order = np.lexsort((-row, ~img[2], ~img[1], ~img[0]))
-    else:
-        order = np.lexsort((row, img[2], img[1], img[0]))
+    keys = np.concatenate([h.keys.reshape(-1, 3) for h in heads], axis=0).astype(np.uint64)
+    order = np.lexsort((-row if reverse else row, keys[:, 2], keys[:, 1], keys[:, 0]))
     n_exact = order.shape[0]
     pos_in_order = np.empty(order.shape[0], np.int64)
     pos_in_order[order] = np.arange(order.shape[0])

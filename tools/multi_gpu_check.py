@@ -86,7 +86,7 @@ def chr20(det, rank, world, steps=10):
     # timing: the sharded step (detect on the shard + heads all-gathered), strong scaling
     for _ in range(3):
         res = sd.detect_shard(sl, lo - hlo, hi - hlo, hlo, opt, out_s)
-        sd.merged_head(res, 2048)
+        sd.gather_heads(res, 1024)
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -95,7 +95,7 @@ def chr20(det, rank, world, steps=10):
     for _ in range(steps):
         res = sd.detect_shard(sl, lo - hlo, hi - hlo, hlo, opt, out_s)
         lane += det.handle.last_timings()["lane"] / steps
-        sd.merged_head(res, 2048)
+        sd.gather_heads(res, 1024)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / steps, lane, float(bad)], dtype=torch.float64, device=device)
