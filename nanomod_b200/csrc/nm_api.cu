@@ -140,9 +140,10 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
     if (fl & 1) sum->bad_input = 1;
     if (fl & 2) sum->ds_too_deep = 1;
     if (nc != total) atomicAdd(&sum->n_filtered, nc - total);
-    if (total) atomicAdd(&sum->n_cand_kept, total);
-    if (l64) atomicAdd(&sum->plan_le64, l64);
-    if (l104) atomicAdd(&sum->plan_le104, l104);
+    int* sp = sum->spread[blockIdx.x & (NM_SPREAD - 1)];
+    if (total) atomicAdd(&sp[0], total);
+    if (l64) atomicAdd(&sp[1], l64);
+    if (l104) atomicAdd(&sp[2], l104);
     if (ml > *(volatile int*)&sum->max_lane_n) atomicMax(&sum->max_lane_n, ml);
     if (ms > *(volatile int*)&sum->max_lane_slack) atomicMax(&sum->max_lane_slack, ms);
     if (nd) {

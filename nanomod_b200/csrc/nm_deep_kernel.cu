@@ -65,8 +65,11 @@ __device__ __forceinline__ void nm_deep_exchange(float (&x)[E], float* stage, in
 template <int E>
 __device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
   float x[E];
+  // any E elements make a thread's initial run (the input order is arbitrary): take them strided,
+  // which is bank-conflict free (tid * E + i would be an E-way conflict)
 #pragma unroll
-  for (int i = 0; i < E; ++i) x[i] = s[tid * E + i];
+  for (int i = 0; i < E; ++i) x[i] = s[i * NM_DEEP_THREADS + tid];
+  __syncthreads();  // everybody has its elements before anybody stages into s
   nm_sortnet<E>::run(x);
   constexpr int P = E * NM_DEEP_THREADS;
   // fully unrolled (8 merge levels, <= 8 cross-thread strides each): every stride, and with it the
@@ -134,7 +137,7 @@ __device__ __forceinline__ int nm_deep_walk(const float* sa, int n0, const float
 // EMAX = largest per-thread chunk compiled in: 16 covers groups of up to 4096 reads at 3 CTAs/SM,
 // 128 (groups up to 32768 reads) needs most of the register file for one CTA.
 template <int EMAX>
-__global__ void __launch_bounds__(NM_DEEP_THREADS, EMAX <= 16 ? 3 : 1)
+__global__ void __launch_bounds__(NM_DEEP_THREADS, EMAX <= 16 ? 4 : 1)
 nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int want_m) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   __shared__ double red_d[NM_DEEP_THREADS / 32];

@@ -93,6 +93,7 @@ __device__ __forceinline__ double nm_warp_sum_d(double v) {
   return v;
 }
 
+#define NM_SPREAD 32
 struct nm_summary {
   unsigned long long n_rows;
   int max_lane_n;   // max over lane-tier rows of max(n0,n1)
@@ -105,13 +106,14 @@ struct nm_summary {
   int max_lane_slack;   // max over lane-tier rows of NM_LANE_TIER_MAX - max(n0,n1)  (-> shortest row)
   int n_le64, n_le104;  // class-binned calls: lane-tier rows whose network class is <= 64 / <= 104
   int n_filtered;       // candidates dropped by the coverage filter (0 => rows == candidates)
-  int n_cand_kept;      // candidates kept (rows)
   int bad_input;        // a candidate with a negative read count (offsets not monotonic) / segment id out of range
   int dense_retry;      // set by nm_lane_dense_kernel: the call does not have the shape the launch assumed
   int dense_tile_cursor;
   int max_deep_t;          // max over deep rows of n0 + n1
   int deep_fallback_count; // (reserved: a device-side count for nm_deep_kernel's row list)
-  int plan_le64, plan_le104;  // lane-tier candidates whose network class is <= 64 / <= 104, counted by nm_plan_count
+  // {kept candidates, lane-tier candidates of network class <= 64, <= 104, -} counted by nm_plan_count;
+  // every block adds to entry (blockIdx & 31): tens of thousands of atomics on ONE address serialise in L2
+  int spread[32][4];
   int n_huge;                 // deep rows beyond the shared-memory deep tier (nm_huge.cu takes them)
   unsigned long long huge_v0, huge_v1;  // their values in group 0 / 1
 };
@@ -124,10 +126,13 @@ __host__ __device__ __forceinline__ bool nm_dense_shape_ok(const nm_summary& s) 
   if (s.n_filtered != 0 || s.n_deep != 0 || s.bad_input != 0 || s.max_lane_n <= 0) return false;
   const int gmin = nm_lane_group(NM_LANE_TIER_MAX - s.max_lane_slack), gmax = nm_lane_group(s.max_lane_n);
   if (gmin == gmax) return true;
-  const long long n = (long long)s.plan_le64 + 0;  // rows in group 0
-  const long long g0 = n, g1 = (long long)s.plan_le104 - s.plan_le64;
-  const long long total = (long long)s.n_cand_kept;
-  const long long g2 = total - s.plan_le104;
+  long long total = 0, le64 = 0, le104 = 0;  // the counters are spread over 32 addresses (see nm_plan_count)
+  for (int k = 0; k < NM_SPREAD; ++k) {
+    total += s.spread[k][0];
+    le64 += s.spread[k][1];
+    le104 += s.spread[k][2];
+  }
+  const long long g0 = le64, g1 = le104 - le64, g2 = total - le104;
   const long long biggest = g0 > g1 ? (g0 > g2 ? g0 : g2) : (g1 > g2 ? g1 : g2);
   const long long of_gmax = gmax == 2 ? g2 : gmax == 1 ? g1 : g0;
   return !(biggest * 8 >= total * 7 && biggest != of_gmax);
