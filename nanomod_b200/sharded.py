@@ -201,11 +201,14 @@ class ShardedDetector:
         return LocalHead(rows["row"].astype(np.int64), rows["seg"].astype(np.int32), rows["pos"].astype(np.int32),
                          np.ascontiguousarray(rows["key"]), rows["full_nbhd"] != 0, res.n_core, len(rows) == res.n_core)
 
-    def gather_heads(self, res: ShardResult, want: int, cap: int = HEAD_CAP):
+    def gather_heads(self, res: ShardResult, want: int, cap: int = HEAD_CAP, slot: int = 0, async_op: bool = False):
         """The multi-GPU exchange of a step, all on the device and without a host wait: three
         streaming kernels select the head of this rank's ranking into a record buffer
         (nm_rank_head_select_device) and ONE NCCL all-gather hands every rank all heads.  Returns the
-        gathered records as a CUDA tensor; ``heads_from_gathered`` parses it when the ranking is needed."""
+        gathered records as a CUDA tensor; ``heads_from_gathered`` parses it when the ranking is needed.
+        ``async_op=True`` returns (tensor, work): the collective then runs beside whatever the caller
+        launches next (``slot`` selects one of two buffer pairs, so a step can overlap the exchange of
+        the previous one); ``work.wait()`` before the tensor is read."""
         import torch
         import torch.distributed as dist
         o = res.options
@@ -214,17 +217,18 @@ class ShardedDetector:
         key = (str(dev), cap, world)
         if getattr(self, "_head_key", None) != key:
             self._head_key = key
-            self._head_mine = torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev)
-            self._head_all = torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev)
+            self._head_mine = [torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._head_all = [torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+        mine, allv = self._head_mine[slot & 1], self._head_all[slot & 1]
         core = {c: res.out[c][res.r_lo:res.r_hi] for c in ("ks_p", "ks_d", "u_p", "u_stat", "fisher_p", "fisher_stat",
                                                            "stouffer_p", "stouffer_stat") if c in res.out}
         rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
-        self.engine.rank_head_select_device(core, res.n_core, o, want, self._head_mine, cap,
+        self.engine.rank_head_select_device(core, res.n_core, o, want, mine, cap,
                                             geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
         if world == 1:
-            return self._head_mine
-        dist.all_gather_into_tensor(self._head_all, self._head_mine, group=self.group)
-        return self._head_all
+            return (mine, None) if async_op else mine
+        work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=async_op)
+        return (allv, work) if async_op else allv
 
     def heads_from_gathered(self, gathered, options: DetectOptions, cap: int = HEAD_CAP) -> List[LocalHead]:
         """gathered device records -> every rank's head, each in its own ranking order"""
