@@ -53,6 +53,7 @@ SEED = 20190131
 BYTES_PER_POS = 4 * (COV + COV) + 16 + 28  # fp32 values + two int64 offsets + outputs
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 HEAD_WANT = 1024           # rows of each rank's ranking head exchanged per step at N > 1
+HEAD_CAP = 4096            # record capacity of the exchange buffer (48-byte records)
 
 
 def workload_config(n_gpus: int):
@@ -68,8 +69,7 @@ def workload_config(n_gpus: int):
                             "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
                             "sharded, per step each rank's ranking head (>= %d rows, selected on the device) is all-gathered "
                             "over NCCL; sorting the gathered heads into the global ranking is host-side ranking work and, like "
-                            "all ranking at N = 1, not part of the timed step; the exchange of step k overlaps the compute of step k+1 "
-                            "(2 SMs left to NCCL), all exchanges complete inside the timed region" % (n_gpus, HEAD_WANT)),
+                            "all ranking at N = 1, not part of the timed step" % (n_gpus, HEAD_WANT)),
             "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -375,41 +375,22 @@ def run_gpu_arm(args):
     out = nm.alloc_device_table(opt, n_local, device)
     step_tm = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
     gathered = [None]
-    pending = [None, None]
-    step_no = [0]
     outs = [out]
-    if world > 1:
-        # the exchange of step k (select kernels + NCCL all-gather, on torch's NCCL stream) runs beside the
-        # compute of step k+1: results are double-buffered and the persistent lane kernel leaves a few SMs
-        # free for NCCL's copy kernel.  Every exchange completes inside the timed region.
-        outs.append(nm.alloc_device_table(opt, n_local, device))
-        det.handle.set_sm_limit(max(1, det.handle.sm_count - args.sm_reserve))
-
-    def drain(b):
-        if pending[b] is not None:
-            pending[b][1].wait()
-            gathered[0] = pending[b][0]
-            pending[b] = None
 
     def step():
         if world == 1:
             rows = det.detect_device(dev, opt, out)  # returns with the results complete on the device
         else:
-            b = step_no[0] & 1
-            step_no[0] += 1
-            drain(b)  # this buffer pair's previous exchange (two steps ago)
-            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[b])
+            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, out)
             rows = res.n_rows
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
         if world > 1:
-            pending[b] = sd.gather_heads(res, HEAD_WANT, slot=b, async_op=True)
+            # head selection kernels + ONE NCCL all-gather, on the device, stream-ordered after the tests
+            gathered[0] = sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP)
         return rows
 
     def fence():
-        if world > 1:
-            drain(0)
-            drain(1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -432,10 +413,6 @@ def run_gpu_arm(args):
         lane_ms.append(step_tm["lane"])
         comb_ms.append(step_tm["combine"])
         plan_ms.append(step_tm["plan"])
-    if world > 1:  # the last two exchanges belong to the timed region
-        drain(0)
-        drain(1)
-        evs[args.steps].record()
     fence()
     per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     ms_total = evs[0].elapsed_time(evs[args.steps])
@@ -472,7 +449,7 @@ def run_gpu_arm(args):
                 # all-gathered, this rank's rows back to (pinned) host memory
                 d = nm.DevicePileup.from_host(hp, device)
                 res = sd.detect_shard(d, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[0])
-                sd.gather_heads(res, HEAD_WANT)
+                sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP)
                 for c in cols:
                     hout_t[c][:res.n_core].copy_(res.core(c), non_blocking=True)
                 torch.cuda.synchronize()
@@ -533,7 +510,7 @@ def run_gpu_arm(args):
                 "clocks": clocks,
                 "pct_hbm_peak_whole_step": 100.0 * (BYTES_PER_POS * value / world / 1e9) / peak}
         if world > 1:
-            heads = sd.heads_from_gathered(gathered[0], opt)
+            heads = sd.heads_from_gathered(gathered[0], opt, HEAD_CAP)
             line["head_rows_exchanged"] = [int(h.rows.shape[0]) for h in heads]
         if variants is not None:
             line["variants"] = variants
@@ -557,7 +534,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--sm-reserve", type=int, default=2, help="SMs left free for NCCL while computing (N > 1)")
     ap.add_argument("--cpu-sample", type=int, default=40000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

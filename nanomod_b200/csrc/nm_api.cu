@@ -872,7 +872,8 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     if ((rc = nm_reserve(h, &h->d_acc_mom, sizeof(double) * 4 * (size_t)n_rows)) != NM_OK) return rc;
     ka.acc_mom = (double*)h->d_acc_mom.p;
   }
-  const int deep_smem = 16 + (sum.max_deep_p2 + 16) * (int)sizeof(float);
+  // two groups, each stored skewed by one word per 32 after its sort (nm_deep_kernel.cu)
+  const int deep_smem = 16 + (sum.max_deep_p2 + (sum.max_deep_p2 >> 5) + 32) * (int)sizeof(float);
   // Mixed coverage.  The lane kernel runs ONE network size per launch (several sizes in flight
   // thrash the instruction cache), normally that of the call's longest row.  If the rows span
   // several size groups and one group holds nearly all of them, the others are outliers: split

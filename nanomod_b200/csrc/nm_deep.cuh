@@ -30,8 +30,21 @@ NM_HD void nm_deep_acc_merge(nm_deep_acc* a, const nm_deep_acc& b) {
   a->tie += b.tie;
 }
 
+// Views of a sorted array: plain, or skewed by one word per 32 (element i at i + i/32) -- the deep
+// kernel stores its sorted groups skewed so that threads whose indices are a multiple of 8 apart
+// (each holds 8 consecutive elements; each walks a piece of 16) hit 32 different banks.
+struct nm_view_plain {
+  const float* p;
+  NM_HD float operator[](int i) const { return p[i]; }
+};
+struct nm_view_skew {
+  const float* p;
+  NM_HD float operator[](int i) const { return p[i + (i >> 5)]; }
+};
+
 // number of elements of sorted s[0..n) that are <= x
-NM_HD int nm_count_le(const float* s, int n, float x) {
+template <class V>
+NM_HD int nm_count_le(const V& s, int n, float x) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -41,7 +54,8 @@ NM_HD int nm_count_le(const float* s, int n, float x) {
 }
 
 // number of elements of sorted s[0..n) that are < x
-NM_HD int nm_count_lt(const float* s, int n, float x) {
+template <class V>
+NM_HD int nm_count_lt(const V& s, int n, float x) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -51,8 +65,8 @@ NM_HD int nm_count_lt(const float* s, int n, float x) {
 }
 
 // Contribution of pooled element e (e < n0: group 0, else group 1).
-NM_HD void nm_deep_element(const float* sa, int n0, const float* sb, int n1, int e, bool want_u,
-                           nm_deep_acc* one) {
+template <class V>
+NM_HD void nm_deep_element(const V& sa, int n0, const V& sb, int n1, int e, bool want_u, nm_deep_acc* one) {
   const bool is_a = e < n0;
   const float x = is_a ? sa[e] : sb[e - n0];
   const long long ua = nm_count_le(sa, n0, x);
@@ -66,6 +80,9 @@ NM_HD void nm_deep_element(const float* sa, int n0, const float* sb, int n1, int
     one->tie = t * t - 1;
     one->r2 = is_a ? (lo + hi + 1) : 0;
   }
+}
+NM_HD void nm_deep_element(const float* sa, int n0, const float* sb, int n1, int e, bool want_u, nm_deep_acc* one) {
+  nm_deep_element(nm_view_plain{sa}, n0, nm_view_plain{sb}, n1, e, want_u, one);
 }
 
 NM_HD void nm_deep_finish(const nm_deep_acc& acc, int n0, int n1, bool want_u, bool want_t,

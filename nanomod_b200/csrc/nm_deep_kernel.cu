@@ -88,8 +88,14 @@ __device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
     }
   }
   __syncthreads();
+  // sorted order, stored SKEWED (element p at p + p/32; nm_view_skew): tid * E + i alone is an E-way
+  // bank conflict here and in every later access pattern with a stride of 8 or 16
 #pragma unroll
-  for (int i = 0; i < E; ++i) s[tid * E + i] = x[i];
+  for (int i = 0; i < E; ++i) {
+    const int p = tid * E + i;
+    s[p + (p >> 5)] = x[i];
+  }
+  if (tid == 0) s[P + (P >> 5)] = NM_INF;  // the sentinel one past the end
   __syncthreads();
 }
 
@@ -107,7 +113,7 @@ __device__ __forceinline__ void nm_deep_sort_p(float* s, int P, int tid) {
 }
 
 // KS numerator over this thread's piece [lo, hi) of the pooled order.  sa[n0] and sb[n1] are +inf.
-__device__ __forceinline__ int nm_deep_walk(const float* sa, int n0, const float* sb, int n1, int lo, int hi) {
+__device__ __forceinline__ int nm_deep_walk(const nm_view_skew sa, int n0, const nm_view_skew sb, int n1, int lo, int hi) {
   // merge-path split of diagonal lo under the rule "ties: group 0 first"
   int il = lo - n1 > 0 ? lo - n1 : 0, ih = lo < n0 ? lo : n0;
   while (il < ih) {
@@ -157,7 +163,7 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
   const int sh0 = (int)(s0 - al0), sh1 = (int)(s1 - al1);
   // [raw A: P0 + 8 floats][raw B: P1 + 8 floats]; the arrays start at the row's first value
   float* rawA = reinterpret_cast<float*>(nm_smem + 16);
-  float* rawB = rawA + P0 + 8;
+  float* rawB = rawA + ((P0 + (P0 >> 5) + 8 + 3) & ~3);  // room for the skewed sorted form of group 0
   float* sa = rawA + sh0;
   float* sb = rawB + sh1;
 
@@ -222,7 +228,7 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
     for (int e = tid; e < n0 + n1; e += NM_DEEP_THREADS) {
       nm_deep_acc one;
       nm_deep_acc_init(&one);
-      nm_deep_element(sa, n0, sb, n1, e, true, &one);
+      nm_deep_element(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, e, true, &one);
       nm_deep_acc_merge(&acc, one);
     }
   } else {
@@ -230,7 +236,7 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
     const int per = (T + NM_DEEP_THREADS - 1) / NM_DEEP_THREADS;
     const int lo = tid * per < T ? tid * per : T;
     const int hi = lo + per < T ? lo + per : T;
-    acc.dnum = nm_deep_walk(sa, n0, sb, n1, lo, hi);
+    acc.dnum = nm_deep_walk(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, lo, hi);
   }
   acc.dnum = nm_warp_max_ll(acc.dnum);
   acc.r2 = nm_warp_sum_ll(acc.r2);

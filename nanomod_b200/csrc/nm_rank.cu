@@ -242,7 +242,8 @@ __device__ void nm_head_search(const unsigned* hist, const unsigned* part, unsig
 }
 
 // hist[NM_HEAD_BINS] = cut bin, hist[NM_HEAD_BINS + 1] = rows in bins <= cut, [+2] = compaction cursor (0)
-__global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want, unsigned cap, int fit_cap) {
+__global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want, unsigned cap, int fit_cap,
+                                                   nm_head_record* __restrict__ header, long long n) {
   __shared__ unsigned part[256];
   unsigned s = 0;
   for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
@@ -261,18 +262,16 @@ __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, 
     hist[NM_HEAD_BINS] = (unsigned)cut;  // 0xffffffff: not even the first occupied bin fits
     hist[NM_HEAD_BINS + 1] = cum;
     hist[NM_HEAD_BINS + 2] = 0;
+    if (header) {  // entry 0 of the caller's record buffer
+      nm_head_record hdr;
+      hdr.row = cum <= cap ? cum : 0;
+      hdr.seg = hdr.pos = hdr.full_nbhd = hdr.pad = 0;
+      hdr.key[0] = (unsigned long long)n;
+      hdr.key[1] = (cum == (unsigned)n && cum <= cap) ? 1ull : 0ull;
+      hdr.key[2] = (unsigned)cut;
+      header[0] = hdr;
+    }
   }
-}
-
-__global__ void nm_head_header(const unsigned* __restrict__ hist, nm_head_record* __restrict__ rec, long long n, unsigned cap) {
-  nm_head_record hdr;
-  const unsigned sel = hist[NM_HEAD_BINS + 1];
-  hdr.row = sel <= cap ? sel : 0;
-  hdr.seg = hdr.pos = hdr.full_nbhd = hdr.pad = 0;
-  hdr.key[0] = (unsigned long long)n;
-  hdr.key[1] = (sel == (unsigned)n && sel <= cap) ? 1ull : 0ull;
-  hdr.key[2] = hist[NM_HEAD_BINS];
-  rec[0] = hdr;
 }
 
 __global__ void __launch_bounds__(256)
@@ -337,12 +336,8 @@ int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * (int64_t)sm_count) blocks = 8 * (int64_t)sm_count;
   nm_head_hist<<<(unsigned)blocks, 256, 0, st>>>(k[0], n, reverse, hist);
-  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n), (unsigned)cap, records ? 1 : 0);
+  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n), (unsigned)cap, records ? 1 : 0, records, (long long)n);
   nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap, geo);
   *launches += 3;
-  if (records) {
-    nm_head_header<<<1, 1, 0, st>>>(hist, records, (long long)n, (unsigned)cap);
-    *launches += 1;
-  }
   return (int)cudaGetLastError();
 }
