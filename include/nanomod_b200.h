@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define NM_VERSION 110 /* 0.1.1: nm_table.moments, nm_rank_*, down-sampling fields */
+#define NM_VERSION 120 /* 0.2.0: dense path, ranking heads, int16 transport format (nm_pileup grew), no depth limit */
 
 /* status codes (0 = ok).  nm_last_error(h) gives the text of the most recent failure. */
 enum {
@@ -77,6 +77,17 @@ typedef struct nm_pileup {
    * '+' else 1], myDetect.py:339); NULL or all <= 0 = no down-sampling */
   const int32_t* seg_cov; /* [n_seg] */
   int64_t n_seg;
+  /* optional 16-bit transport format: when vals0 / vals1 are NULL, the event means are
+   * vals*_i16[k] * i16_unit -- exactly the float32 nearest to that product, i.e. what casting the
+   * reference's 0.001-grid float64 values (norm_mean = round(x, 3), myRefBaseSignalAnnotation.py:1108)
+   * to float32 gives with i16_unit = 0.001.  Half the bytes over PCIe and in the staging copy; the
+   * library expands them on the GPU and everything downstream is unchanged.  Same offsets, same
+   * alignment / padding rule in elements (16-byte aligned, readable to the next multiple of 8). */
+  const int16_t* vals0_i16;
+  const int16_t* vals1_i16;
+  double i16_unit;
+  int64_t i16_total0; /* values per group (= off0[n_pos], off1[n_pos]); needed by the *_device entry, */
+  int64_t i16_total1; /* where the offsets cannot be read by the host                                */
 } nm_pileup;
 
 /* Per-row outputs (SoA), each with capacity n_pos.  Row r is the r-th candidate that passes

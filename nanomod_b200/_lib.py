@@ -47,7 +47,9 @@ class nm_params(C.Structure):
 class nm_pileup(C.Structure):
     _fields_ = [("vals0", C.c_void_p), ("off0", C.c_void_p), ("vals1", C.c_void_p),
                 ("off1", C.c_void_p), ("pos", C.c_void_p), ("seg", C.c_void_p),
-                ("n_pos", C.c_int64), ("seg_cov", C.c_void_p), ("n_seg", C.c_int64)]
+                ("n_pos", C.c_int64), ("seg_cov", C.c_void_p), ("n_seg", C.c_int64),
+                ("vals0_i16", C.c_void_p), ("vals1_i16", C.c_void_p), ("i16_unit", C.c_double),
+                ("i16_total0", C.c_int64), ("i16_total1", C.c_int64)]
 
 
 TABLE_FIELDS = ["row_pos_index", "n0", "n1", "ks_dnum", "ks_d", "ks_p", "two_u", "u_stat", "u_p",

@@ -389,9 +389,10 @@ struct nm_handle {
                        // call is launched on that assumption without waiting for its plan summary
   int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 / 4 speculative launch refused and
                        // the call re-run dense with the right network class / on the general path
-  nm_buf d_comb_z, d_comb_ln, d_deep_fallback;
+  nm_buf d_comb_z, d_comb_ln, d_deep_fallback, d_exp0, d_exp1;
   // pipelined nm_detect_host: two slots of staging (inputs + outputs), copy streams and events
   nm_buf p_in[2][6];    // vals0, vals1, off0, off1, pos, seg of a slab
+  nm_buf p_i16[2][2];   // the slab's int16 values (16-bit transport format), expanded into p_in[.][0..1]
   nm_buf p_out[2][17];  // the slab's table
   cudaStream_t s_in, s_out;
   cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
@@ -517,7 +518,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -526,6 +527,8 @@ extern "C" void nm_destroy(nm_handle* h) {
     for (nm_buf& b : h->p_in[s])
       if (b.p) cudaFree(b.p);
     for (nm_buf& b : h->p_out[s])
+      if (b.p) cudaFree(b.p);
+    for (nm_buf& b : h->p_i16[s])
       if (b.p) cudaFree(b.p);
     if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
     if (h->ev_cmp[s]) cudaEventDestroy(h->ev_cmp[s]);
@@ -630,6 +633,36 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[3], st));
+  return NM_OK;
+}
+
+// 16-bit transport format -> the float32 values every kernel works on: (float)((double)k * unit),
+// the float32 nearest to the decimal k * unit (a float64 product is within 1e-16 of it, and a decimal
+// with three places is never that close to a float32 rounding boundary)
+__global__ void __launch_bounds__(256) nm_expand_i16(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n,
+                                                     double unit) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const int4 w = *reinterpret_cast<const int4*>(in + i);
+    const int v[4] = {w.x, w.y, w.z, w.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = (float)((double)(short)(v[k] & 0xffff) * unit);
+      o[2 * k + 1] = (float)((double)(short)(v[k] >> 16) * unit);
+    }
+    *reinterpret_cast<float4*>(out + i) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = (float)((double)in[k] * unit);
+  }
+}
+
+static int nm_expand_i16_run(nm_handle* h, const int16_t* in, float* out, int64_t n, double unit, cudaStream_t st) {
+  if (n <= 0) return NM_OK;
+  nm_expand_i16<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(in, out, n, unit);
+  NM_CUDA(h, cudaGetLastError());
+  h->launches++;
   return NM_OK;
 }
 
@@ -749,6 +782,25 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     return nm_fail(h, NM_ERR_BAD_ARG, "n_pos (%lld) out of range", (long long)pl->n_pos);
   *n_rows_out = 0;
   if (pl->n_pos == 0) return NM_OK;
+  nm_pileup pl_f32;  // int16 transport format: expanded into the handle's float32 scratch first
+  if (!pl->vals0 && !pl->vals1 && pl->vals0_i16 && pl->vals1_i16 && pl->off0 && pl->off1) {
+    if (!(pl->i16_unit > 0.0)) return nm_fail(h, NM_ERR_BAD_ARG, "i16_unit must be positive");
+    if ((((uintptr_t)pl->vals0_i16) | ((uintptr_t)pl->vals1_i16)) & 15)
+      return nm_fail(h, NM_ERR_BAD_ARG, "vals0_i16/vals1_i16 must be 16-byte aligned");
+    if (pl->i16_total0 < 0 || pl->i16_total1 < 0)
+      return nm_fail(h, NM_ERR_BAD_ARG, "int16 pileups on the device need i16_total0 / i16_total1 (values per group)");
+    NM_CUDA(h, cudaSetDevice(h->device));
+    if ((rc = nm_reserve(h, &h->d_exp0, sizeof(float) * (size_t)nm_padded_len(pl->i16_total0))) != NM_OK) return rc;
+    if ((rc = nm_reserve(h, &h->d_exp1, sizeof(float) * (size_t)nm_padded_len(pl->i16_total1))) != NM_OK) return rc;
+    cudaStream_t st0 = (cudaStream_t)cuda_stream;
+    if ((rc = nm_expand_i16_run(h, pl->vals0_i16, (float*)h->d_exp0.p, pl->i16_total0, pl->i16_unit, st0)) != NM_OK) return rc;
+    if ((rc = nm_expand_i16_run(h, pl->vals1_i16, (float*)h->d_exp1.p, pl->i16_total1, pl->i16_unit, st0)) != NM_OK) return rc;
+    pl_f32 = *pl;
+    pl_f32.vals0 = (const float*)h->d_exp0.p;
+    pl_f32.vals1 = (const float*)h->d_exp1.p;
+    pl_f32.vals0_i16 = pl_f32.vals1_i16 = nullptr;
+    pl = &pl_f32;
+  }
   if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
     return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
   if ((((uintptr_t)pl->vals0) | ((uintptr_t)pl->vals1)) & 15)
@@ -967,6 +1019,7 @@ __global__ void nm_rebase_rows(int32_t* row_pos_index, int64_t lo, int64_t hi, i
 static int nm_detect_host_pipelined(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb,
                                     int64_t* n_rows_out) {
   const int64_t n = pl->n_pos, S = h->slab;
+  const bool i16 = !pl->vals0 && pl->vals0_i16 != nullptr;
   const int nb = (prm.combine != 0) ? prm.nb : 0;
   const int64_t n_slabs = (n + S - 1) / S;
   void* const host_ptrs[17] = {tb->row_pos_index, tb->n0, tb->n1, tb->ks_dnum, tb->ks_d, tb->ks_p,
@@ -995,6 +1048,10 @@ static int nm_detect_host_pipelined(nm_handle* h, const nm_pileup* pl, const nm_
                             sizeof(int32_t) * (size_t)cap, sizeof(int32_t) * (size_t)cap};
     for (int b = 0; b < 6; ++b)
       if ((rc = nm_reserve(h, &h->p_in[s][b], need[b])) != NM_OK) return rc;
+    if (i16) {
+      if ((rc = nm_reserve(h, &h->p_i16[s][0], sizeof(int16_t) * (size_t)(max_v0 + 8))) != NM_OK) return rc;
+      if ((rc = nm_reserve(h, &h->p_i16[s][1], sizeof(int16_t) * (size_t)(max_v1 + 8))) != NM_OK) return rc;
+    }
     for (int c = 0; c < 17; ++c)
       if (host_ptrs[c] && (rc = nm_reserve(h, &h->p_out[s][c], elem[c] * (size_t)cap)) != NM_OK) return rc;
   }
@@ -1014,8 +1071,17 @@ static int nm_detect_host_pipelined(nm_handle* h, const nm_pileup* pl, const nm_
     const int64_t b0 = pl->off0[hlo], b1 = pl->off1[hlo];
     const int64_t v0 = pl->off0[hhi] - b0, v1 = pl->off1[hhi] - b1;
     // the slot's inputs were last read by slab k-2's kernels, which have completed (the compute call is synchronous)
-    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][0].p, pl->vals0 + b0, sizeof(float) * (size_t)v0, cudaMemcpyHostToDevice, h->s_in));
-    NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][1].p, pl->vals1 + b1, sizeof(float) * (size_t)v1, cudaMemcpyHostToDevice, h->s_in));
+    if (i16) {
+      NM_CUDA(h, cudaMemcpyAsync(h->p_i16[s][0].p, pl->vals0_i16 + b0, sizeof(int16_t) * (size_t)v0, cudaMemcpyHostToDevice, h->s_in));
+      NM_CUDA(h, cudaMemcpyAsync(h->p_i16[s][1].p, pl->vals1_i16 + b1, sizeof(int16_t) * (size_t)v1, cudaMemcpyHostToDevice, h->s_in));
+      int rc2 = nm_expand_i16_run(h, (const int16_t*)h->p_i16[s][0].p, (float*)h->p_in[s][0].p, v0, pl->i16_unit, h->s_in);
+      if (rc2 != NM_OK) return rc2;
+      rc2 = nm_expand_i16_run(h, (const int16_t*)h->p_i16[s][1].p, (float*)h->p_in[s][1].p, v1, pl->i16_unit, h->s_in);
+      if (rc2 != NM_OK) return rc2;
+    } else {
+      NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][0].p, pl->vals0 + b0, sizeof(float) * (size_t)v0, cudaMemcpyHostToDevice, h->s_in));
+      NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][1].p, pl->vals1 + b1, sizeof(float) * (size_t)v1, cudaMemcpyHostToDevice, h->s_in));
+    }
     NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][2].p, pl->off0 + hlo, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, h->s_in));
     NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][3].p, pl->off1 + hlo, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyHostToDevice, h->s_in));
     NM_CUDA(h, cudaMemcpyAsync(h->p_in[s][4].p, pl->pos + hlo, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, h->s_in));
@@ -1110,7 +1176,9 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
   *n_rows_out = 0;
   if (pl->n_pos < 0) return nm_fail(h, NM_ERR_BAD_ARG, "n_pos is negative");
   if (pl->n_pos == 0) return NM_OK;
-  if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
+  const bool i16 = !pl->vals0 && !pl->vals1 && pl->vals0_i16 && pl->vals1_i16;
+  if (i16 && !(pl->i16_unit > 0.0)) return nm_fail(h, NM_ERR_BAD_ARG, "i16_unit must be positive");
+  if ((!i16 && (!pl->vals0 || !pl->vals1)) || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
     return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
   NM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->own_stream;
@@ -1127,8 +1195,17 @@ extern "C" int nm_detect_host(nm_handle* h, const nm_pileup* pl, const nm_params
   if ((rc = nm_reserve(h, &h->d_off1, sizeof(int64_t) * (size_t)(n + 1))) != NM_OK) return rc;
   if ((rc = nm_reserve(h, &h->d_pos, sizeof(int32_t) * (size_t)n)) != NM_OK) return rc;
   if ((rc = nm_reserve(h, &h->d_seg, sizeof(int32_t) * (size_t)n)) != NM_OK) return rc;
-  NM_CUDA(h, cudaMemcpyAsync(h->d_vals0.p, pl->vals0, sizeof(float) * (size_t)nv0, cudaMemcpyHostToDevice, st));
-  NM_CUDA(h, cudaMemcpyAsync(h->d_vals1.p, pl->vals1, sizeof(float) * (size_t)nv1, cudaMemcpyHostToDevice, st));
+  if (i16) {
+    if ((rc = nm_reserve(h, &h->p_i16[0][0], sizeof(int16_t) * (size_t)(nv0 + 8))) != NM_OK) return rc;
+    if ((rc = nm_reserve(h, &h->p_i16[0][1], sizeof(int16_t) * (size_t)(nv1 + 8))) != NM_OK) return rc;
+    NM_CUDA(h, cudaMemcpyAsync(h->p_i16[0][0].p, pl->vals0_i16, sizeof(int16_t) * (size_t)nv0, cudaMemcpyHostToDevice, st));
+    NM_CUDA(h, cudaMemcpyAsync(h->p_i16[0][1].p, pl->vals1_i16, sizeof(int16_t) * (size_t)nv1, cudaMemcpyHostToDevice, st));
+    if ((rc = nm_expand_i16_run(h, (const int16_t*)h->p_i16[0][0].p, (float*)h->d_vals0.p, nv0, pl->i16_unit, st)) != NM_OK) return rc;
+    if ((rc = nm_expand_i16_run(h, (const int16_t*)h->p_i16[0][1].p, (float*)h->d_vals1.p, nv1, pl->i16_unit, st)) != NM_OK) return rc;
+  } else {
+    NM_CUDA(h, cudaMemcpyAsync(h->d_vals0.p, pl->vals0, sizeof(float) * (size_t)nv0, cudaMemcpyHostToDevice, st));
+    NM_CUDA(h, cudaMemcpyAsync(h->d_vals1.p, pl->vals1, sizeof(float) * (size_t)nv1, cudaMemcpyHostToDevice, st));
+  }
   NM_CUDA(h, cudaMemcpyAsync(h->d_off0.p, pl->off0, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
   NM_CUDA(h, cudaMemcpyAsync(h->d_off1.p, pl->off1, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
   NM_CUDA(h, cudaMemcpyAsync(h->d_pos.p, pl->pos, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));

@@ -455,10 +455,14 @@ class Detector:
             out = {c: np.empty(_col_shape(c, n), dtype=_lib.TABLE_DTYPES[c]) for c in cols}
         tb = _lib.nm_table(**{c: out[c].ctypes.data for c in cols})
         seg_cov = opt.seg_cov(pileup.seg_names)
-        pl = _lib.nm_pileup(pileup.vals0.ctypes.data, pileup.off0.ctypes.data, pileup.vals1.ctypes.data,
+        i16 = pileup.vals0_i16 is not None and pileup.vals1_i16 is not None
+        pl = _lib.nm_pileup(None if i16 else pileup.vals0.ctypes.data, pileup.off0.ctypes.data,
+                            None if i16 else pileup.vals1.ctypes.data,
                             pileup.off1.ctypes.data, pileup.pos.ctypes.data, pileup.seg.ctypes.data, n,
                             None if seg_cov is None else seg_cov.ctypes.data,
-                            0 if seg_cov is None else len(seg_cov))
+                            0 if seg_cov is None else len(seg_cov),
+                            pileup.vals0_i16.ctypes.data if i16 else None, pileup.vals1_i16.ctypes.data if i16 else None,
+                            pileup.i16_unit if i16 else 0.0, int(pileup.off0[-1]), int(pileup.off1[-1]))
         n_rows = self.handle.detect_host(pl, opt.to_params(), tb)
         res = {c: out[c][:n_rows] for c in cols}
         if n_rows == n:  # nothing filtered: rows are the candidates themselves
@@ -578,10 +582,15 @@ class Detector:
         cols = _wanted_columns(options)
         tb = _lib.nm_table(**{c: out[c].data_ptr() for c in cols})
         seg_cov = getattr(dev, "seg_cov", None)
-        pl = _lib.nm_pileup(dev.vals0.data_ptr(), dev.off0.data_ptr(), dev.vals1.data_ptr(),
+        i16 = getattr(dev, "vals0_i16", None) is not None
+        pl = _lib.nm_pileup(None if i16 else dev.vals0.data_ptr(), dev.off0.data_ptr(),
+                            None if i16 else dev.vals1.data_ptr(),
                             dev.off1.data_ptr(), dev.pos.data_ptr(), dev.seg.data_ptr(), dev.n_pos,
                             None if seg_cov is None else seg_cov.data_ptr(),
-                            0 if seg_cov is None else int(seg_cov.numel()))
+                            0 if seg_cov is None else int(seg_cov.numel()),
+                            dev.vals0_i16.data_ptr() if i16 else None, dev.vals1_i16.data_ptr() if i16 else None,
+                            float(dev.i16_unit) if i16 else 0.0, int(dev.i16_total0) if i16 else 0,
+                            int(dev.i16_total1) if i16 else 0)
         if stream is None:
             stream = torch.cuda.current_stream(dev.vals0.device).cuda_stream
         return self.handle.detect_device(pl, options.to_params(), tb, stream)
@@ -598,6 +607,12 @@ class DevicePileup:
     seg: "object"
     n_pos: int
     seg_cov: "object" = None  # optional int32 CUDA tensor [n_seg]: down-sampling coverage per segment
+    # optional 16-bit transport format resident on the device (vals0 / vals1 may then be None)
+    vals0_i16: "object" = None
+    vals1_i16: "object" = None
+    i16_unit: float = 0.0
+    i16_total0: int = 0
+    i16_total1: int = 0
 
     @classmethod
     def from_host(cls, p: Pileup, device) -> "DevicePileup":

@@ -36,6 +36,10 @@ class Pileup:
     # positions whose recorded base differs between the groups: (segment key, pos, base of group 1,
     # base of group 0) -- what mtest2 reports as 'Error not equal' (myDetect.py:432-434)
     base_mismatch: List[Tuple[SegKey, int, str, str]] = field(default_factory=list)
+    # optional 16-bit transport format (see to_int16): value k stands for float32(k * i16_unit)
+    vals0_i16: Optional[np.ndarray] = None
+    vals1_i16: Optional[np.ndarray] = None
+    i16_unit: float = 0.0
 
     @property
     def n_pos(self) -> int:
@@ -155,6 +159,24 @@ class Pileup:
                 bs.setdefault(sk, {})[int(self.pos[i])] = chr(self.base[i])
             out.append({"norm_mean": nm, "base": bs})
         return out[0], out[1]
+
+    def to_int16(self, unit: float = 0.001) -> "Pileup":
+        """The same pileup with its values ALSO in the 16-bit transport format (half the bytes over
+        PCIe): every value must be exactly float32(k * unit) for an integer |k| <= 32767 -- true for
+        the reference's data (norm_mean = round(x, 3), myRefBaseSignalAnnotation.py:1108) cast to
+        float32 with unit = 0.001.  ``Detector.detect`` then ships the int16 arrays and the library
+        expands them on the GPU: results are bit-identical to the float32 pileup's."""
+        out = []
+        for vals, off in ((self.vals0, self.off0), (self.vals1, self.off1)):
+            n = int(off[-1])
+            k = np.rint(vals[:n].astype(np.float64) / unit)
+            if n and (np.abs(k).max() > 32767 or not np.array_equal((k * unit).astype(np.float32), vals[:n])):
+                raise ValueError("values are not on the %g grid within +-32767 units: no exact int16 form" % unit)
+            a = np.zeros((n + 15) // 8 * 8, dtype=np.int16)
+            a[:n] = k.astype(np.int16)
+            out.append(a)
+        return Pileup(self.vals0, self.off0, self.vals1, self.off1, self.pos, self.seg, self.base, self.seg_names,
+                      self.base_mismatch, out[0], out[1], float(unit))
 
     def save_npz(self, path: str) -> None:
         np.savez(path, vals0=self.vals0[:self.off0[-1]], off0=self.off0, vals1=self.vals1[:self.off1[-1]],

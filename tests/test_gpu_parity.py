@@ -783,3 +783,35 @@ def test_pipelined_host_entry_equals_one_piece(slab):
                               np.arange(L, dtype=np.int32)[keep])
     ds = nm.DetectOptions(neighborPvalues=2, testMethod="stouffer", coverages="100-100", downsampling=64)
     _tables_identical(whole.detect(q, ds), piped.detect(q, ds))
+
+
+# ---------------------------------------------------------------------------------------------
+# 16-bit transport format: half the bytes in, bit-identical tables out
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("slab", [0, 1500])
+def test_int16_transport_format(slab):
+    import torch
+    det = _detector_with_env(NANOMOD_B200_SLAB=slab)
+    p = nm.synthetic_pileup(7000, 35, 31, round_decimals=3, drop_frac1=0.01, two_strands=True)  # the reference's 0.001 grid
+    q = p.to_int16(0.001)
+    assert q.vals0_i16.dtype == np.int16 and q.vals0_i16.nbytes < p.vals0.nbytes * 0.52
+    for opt in (nm.DetectOptions(neighborPvalues=3, both_combinations=True, mstd=True),
+                nm.DetectOptions(neighborPvalues=2, testMethod="ks", want_u=False, want_t=False)):
+        a, b = det.detect(p, opt), det.detect(q, opt)
+        _tables_identical(a, b)
+        if opt.mstd:
+            assert np.array_equal(a.moments, b.moments)
+    # device-resident int16 pileup
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    dev16 = nm.DevicePileup(None, dev.off0, None, dev.off1, dev.pos, dev.seg, p.n_pos,
+                            vals0_i16=torch.from_numpy(q.vals0_i16).cuda(), vals1_i16=torch.from_numpy(q.vals1_i16).cuda(),
+                            i16_unit=0.001, i16_total0=int(p.off0[-1]), i16_total1=int(p.off1[-1]))
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer")
+    o1, o2 = nm.alloc_device_table(opt, p.n_pos, "cuda:0"), nm.alloc_device_table(opt, p.n_pos, "cuda:0")
+    n1, n2 = det.detect_device(dev, opt, o1), det.detect_device(dev16, opt, o2)
+    assert n1 == n2
+    for c in ("ks_dnum", "ks_p", "two_u", "t_stat", "stouffer_stat", "stouffer_p"):
+        assert torch.equal(o1[c][:n1].view(torch.uint8), o2[c][:n2].view(torch.uint8)), c
+    # values off the grid have no exact int16 form
+    with pytest.raises(ValueError):
+        nm.synthetic_pileup(100, 10, 10).to_int16(0.001)
