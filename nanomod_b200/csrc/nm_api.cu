@@ -303,12 +303,15 @@ struct nm_comb_win {
   }
 };
 
+// NB > 0: neighborPvalues known at compile time (window loops unrolled, weights indexed statically);
+// NB == 0: any value, read from the arguments.  Same operations in the same order either way.
+template <int NB>
 __global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_comb_args a) {
   __shared__ double z_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
   __shared__ double l_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
   __shared__ int pos_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
   __shared__ int seg_s[NM_COMB_THREADS + 2 * NM_MAX_NB];
-  const int nb = a.nb;
+  const int nb = NB > 0 ? NB : a.nb;
   const int64_t tile0 = (int64_t)blockIdx.x * NM_COMB_THREADS;
   for (int t = threadIdx.x; t < NM_COMB_THREADS + 2 * nb; t += NM_COMB_THREADS) {
     const int64_t r = tile0 - nb + t;
@@ -669,6 +672,18 @@ static int nm_expand_i16_run(nm_handle* h, const int16_t* in, float* out, int64_
 // the shape the dense lane kernel assumes (it re-checks the same conditions on the device)
 static bool nm_dense_shape(const nm_summary& s) { return nm_dense_shape_ok(s); }
 
+static void nm_launch_combine(const nm_comb_args& ca, int64_t n_rows, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n_rows + NM_COMB_THREADS - 1) / NM_COMB_THREADS);
+  switch (ca.nb) {
+    case 1: nm_combine_kernel<1><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+    case 2: nm_combine_kernel<2><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+    case 3: nm_combine_kernel<3><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+    case 4: nm_combine_kernel<4><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+    case 5: nm_combine_kernel<5><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+    default: nm_combine_kernel<0><<<grid, NM_COMB_THREADS, 0, st>>>(ca); break;
+  }
+}
+
 static void nm_fill_comb_args(nm_comb_args* ca, const nm_pileup* pl, const nm_params& prm, const nm_table* tb,
                               int64_t n_rows, bool ds_on) {
   memset(ca, 0, sizeof(*ca));
@@ -746,7 +761,7 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
     ca.row_pos_index = nullptr;  // row == candidate
     ca.z_pre = ka.comb_z;
     ca.ln_pre = ka.comb_ln;
-    nm_combine_kernel<<<(unsigned)((n + NM_COMB_THREADS - 1) / NM_COMB_THREADS), NM_COMB_THREADS, 0, st>>>(ca);
+    nm_launch_combine(ca, n, st);
     NM_CUDA(h, cudaGetLastError());
     h->launches++;
   }
@@ -978,8 +993,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   if (want_f || want_s) {
     nm_comb_args ca;
     nm_fill_comb_args(&ca, pl, prm, tb, n_rows, ds_on);
-    const unsigned grid = (unsigned)((n_rows + NM_COMB_THREADS - 1) / NM_COMB_THREADS);
-    nm_combine_kernel<<<grid, NM_COMB_THREADS, 0, st>>>(ca);
+    nm_launch_combine(ca, n_rows, st);
     NM_CUDA(h, cudaGetLastError());
     h->launches++;
   }

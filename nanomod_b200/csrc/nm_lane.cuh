@@ -318,6 +318,9 @@ NM_HD void nm_combine_row(int nb, const double* w, double wnorm, const WAcc& W, 
                           bool want_stouffer, double* f_stat, double* f_p, double* s_stat,
                           double* s_p) {
   double lnsum = 0.0, zsum = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (int k = -nb; k <= nb; ++k) {
     double z, lnp;
     W(k, &z, &lnp);

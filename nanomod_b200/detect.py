@@ -592,7 +592,7 @@ class Detector:
                             float(dev.i16_unit) if i16 else 0.0, int(dev.i16_total0) if i16 else 0,
                             int(dev.i16_total1) if i16 else 0)
         if stream is None:
-            stream = torch.cuda.current_stream(dev.vals0.device).cuda_stream
+            stream = torch.cuda.current_stream(dev.off0.device).cuda_stream
         return self.handle.detect_device(pl, options.to_params(), tb, stream)
 
 

@@ -179,7 +179,7 @@ class ShardedDetector:
         import torch
         from .detect import alloc_device_table
         if out is None:
-            out = alloc_device_table(options, dev.n_pos, dev.vals0.device)
+            out = alloc_device_table(options, dev.n_pos, dev.off0.device)
         n_rows = self.engine.detect_device(dev, options, out)
         if n_rows == dev.n_pos:  # nothing filtered: rows are the candidates
             r_lo, r_hi = core_lo, core_hi
