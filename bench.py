@@ -65,6 +65,11 @@ def workload_config(n_gpus: int):
                      "and Welch t columns of the reference's table are NOT computed in this configuration; "
                      "`variants.all_tests` is the run that fills them). Both arms do exactly this work.",
             "want_u": False, "want_t": False,
+            "values": ("Gaussian currents (+ shifted means at planted sites) rounded to three decimals, as the reference "
+                       "stores them (norm_mean = round(x, 3), myRefBaseSignalAnnotation.py:1108), float32 in HBM: the lane "
+                       "tier checks every value on the device and sorts such tiles as packed 16-bit keys "
+                       "(`grid_tiles`); `variants.off_grid_values` is the same run on raw float32 normals" if GRID else
+                       "raw float32 Gaussian currents (--off-grid): not the three-place decimals the reference stores"),
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
                             "sharded, per step each rank's ranking head (>= %d rows, selected on the device) is all-gathered "
@@ -81,7 +86,21 @@ def planted_shift_np(pos: np.ndarray) -> np.ndarray:
     return planted_shift(pos)
 
 
-def make_device_workload(length: int, n0: int, n1: int, device, seed: int = SEED, pos0: int = 0):
+GRID = True  # values as the reference stores them: three-place decimals (see to_grid_); --off-grid: raw float32 normals
+
+
+def to_grid_(v):
+    """In place: every value becomes float32(round(float64(x), 3)) -- what the reference's annotation stage
+    writes (norm_mean = round(x, 3), bin/scripts/myRefBaseSignalAnnotation.py:1108) and its packer casts."""
+    import torch
+    step = 1 << 26
+    for lo in range(0, v.numel(), step):
+        c = v[lo:lo + step]
+        c.copy_((torch.round(c.double() * 1000.0) / 1000.0).float())
+    return v
+
+
+def make_device_workload(length: int, n0: int, n1: int, device, seed: int = SEED, pos0: int = 0, grid=None):
     """Fixed-coverage synthetic pileup generated on the GPU (torch Philox generator).
     Returns (DevicePileup, per-position planted shift as a numpy array)."""
     import torch
@@ -97,6 +116,9 @@ def make_device_workload(length: int, n0: int, n1: int, device, seed: int = SEED
     v1.normal_(generator=g)
     sh = torch.from_numpy(shift.astype(np.float32)).to(device)
     v1[: length * n1].view(length, n1).add_(sh[:, None])
+    if GRID if grid is None else grid:
+        to_grid_(v0)
+        to_grid_(v1)
     off0 = torch.arange(length + 1, dtype=torch.int64, device=device) * n0
     off1 = torch.arange(length + 1, dtype=torch.int64, device=device) * n1
     posd = torch.from_numpy(pos.astype(np.int32)).to(device)
@@ -106,7 +128,7 @@ def make_device_workload(length: int, n0: int, n1: int, device, seed: int = SEED
 
 def host_sample_pileup(length: int, seed: int = SEED):
     import nanomod_b200 as nm
-    return nm.synthetic_pileup(length, COV, COV, seed=seed)
+    return nm.synthetic_pileup(length, COV, COV, seed=seed, round_decimals=3 if GRID else None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -262,12 +284,13 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def lane_capture():
+def lane_capture(kernel):
     """the committed ncu --set full capture of the lane kernel on this workload
-    (profiles/lane_kernel_traffic.json): DRAM bytes per launch + what actually bounds the kernel"""
+    (profiles/lane_kernel_traffic.json, one entry per kernel): DRAM bytes per launch + what actually
+    bounds the kernel"""
     try:
         with open(os.path.join(ROOT, "profiles", "lane_kernel_traffic.json")) as f:
-            return json.load(f)
+            return json.load(f).get(kernel)
     except Exception:
         return None
 
@@ -298,7 +321,8 @@ def time_config(det, dev, opt, length, steps, warmup, nvals, bytes_out):
     return {"positions": length, "rows": rows, "steps": steps, "ms_per_step": ms, "ms_per_step_median": statistics.median(per),
             "ms_per_step_best": min(per), "positions_per_s": length / (ms * 1e-3), "kernel_ms": tms,
             "algorithmic_bytes": alg, "tests_kernel_frac_of_hbm_peak": alg / (main * 1e-3) / 1e9 / peak,
-            "whole_step_frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "path": det.handle.last_path()}
+            "whole_step_frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "path": det.handle.last_path(),
+            "grid_tiles": det.handle.last_grid_tiles(), "tiles": (length + 31) // 32}
 
 
 def run_variants(det, device):
@@ -313,6 +337,12 @@ def run_variants(det, device):
     out["all_tests"]["what"] = ("BASELINE configs[2]: the same pileup, U + Welch t + KS per position, Fisher AND Stouffer: "
                                 "every column of the reference's table (892 algorithmic B/position)")
     del dev
+    if GRID:
+        dev, _ = make_device_workload(GENOME, COV, COV, device, grid=False)
+        out["off_grid_values"] = time_config(det, dev, ks_st, GENOME, 5, 3, GENOME * 2 * COV, 28)
+        out["off_grid_values"]["what"] = ("the headline workload with raw float32 normals instead of three-place decimals: "
+                                          "every warp's first tiles fail the grid check, the float32 sort does the work")
+        del dev
     # Poisson coverage
     g = torch.Generator(device=device)
     g.manual_seed(7)
@@ -327,6 +357,9 @@ def run_variants(det, device):
     nv = int(off0[-1]) + int(off1[-1])
     v0 = torch.empty(padded_len(int(off0[-1])), dtype=torch.float32, device=device).normal_(generator=g)
     v1 = torch.empty(padded_len(int(off1[-1])), dtype=torch.float32, device=device).normal_(generator=g)
+    if GRID:
+        to_grid_(v0)
+        to_grid_(v1)
     dev = nm.DevicePileup(v0, off0, v1, off1, torch.arange(GENOME, dtype=torch.int32, device=device),
                           torch.zeros(GENOME, dtype=torch.int32, device=device), GENOME)
     out["poisson_coverage"] = time_config(det, dev, ks_st, GENOME, 5, 3, nv, 28)
@@ -418,6 +451,7 @@ def run_gpu_arm(args):
     ms_total = evs[0].elapsed_time(evs[args.steps])
     launches = det.launch_count - launches1
     path = det.handle.last_path()
+    grid_tiles = det.handle.last_grid_tiles()
     assert rows == n_local, (rows, n_local)
     t = torch.tensor([ms_total, statistics.median(per_step), min(per_step)], dtype=torch.float64, device=device)
     if world > 1:
@@ -508,12 +542,14 @@ def run_gpu_arm(args):
         peak, peak_src = hbm_peak()
         lane_avg = sum(lane_ms) / len(lane_ms)
         achieved = BYTES_PER_POS * n_local / (lane_avg * 1e-3) / 1e9
-        cap = lane_capture() if (world == 1 and L == GENOME) else None
-        kernel = "nm_lane_dense_kernel" if path in (1, 2, 3) else "nm_lane_kernel"
+        kernel = ("nm_lane_grid_kernel" if grid_tiles > 0 else "nm_lane_dense_kernel") if path in (1, 2, 3) else "nm_lane_kernel"
+        cap = lane_capture(kernel) if (world == 1 and L == GENOME) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_step_median": ms_median,
                 "ms_per_step_best": ms_best, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 keys, i32 ranks, f64 tails",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": ("u16 keys (exact images of the float32 inputs, checked on the device), i32 ranks, f64 tails"
+                          if kernel == "nm_lane_grid_kernel" else "f32 keys, i32 ranks, f64 tails"),
                 "data": "synthetic", "config": workload_config(world),
                 "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
@@ -530,7 +566,7 @@ def run_gpu_arm(args):
                              "ncu": ({k: cap[k] for k in ("issue_active_pct", "alu_pipe_active_pct", "fmaheavy_pipe_active_pct",
                                                           "warp_instructions", "registers_per_thread", "warps_active_pct") if k in cap}
                                      if cap else None)},
-                "e2e": e2e, "gpu_launches": launches, "code_path": {0: "general", 1: "dense", 2: "dense (speculative launch)",
+                "e2e": e2e, "gpu_launches": launches, "grid_tiles": grid_tiles, "tiles": (n_local + 31) // 32, "code_path": {0: "general", 1: "dense", 2: "dense (speculative launch)",
                                                                     3: "dense (re-run)", 4: "general (re-run)"}.get(path, str(path)),
                 "clocks": clocks,
                 "pct_hbm_peak_whole_step": 100.0 * (BYTES_PER_POS * value / world / 1e9) / peak}
@@ -560,9 +596,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--off-grid", action="store_true",
+                    help="raw float32 normals instead of the reference's three-place decimals")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=40000)
     args = ap.parse_args()
+    global GRID
+    GRID = not args.off_grid
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

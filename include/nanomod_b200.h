@@ -248,6 +248,18 @@ int nm_last_timings(const nm_handle* h, double* ms4);
  * class, 4 refused and re-run on the general path. */
 int nm_last_path(const nm_handle* h);
 
+/* How many 32-position tiles of the most recent nm_detect_* call the lane tier sorted through its
+ * 16-bit grid-key path: values that are float32 images of decimals with three places (the
+ * reference's norm_mean = round(x, 3), myRefBaseSignalAnnotation.py:1108; |x| <= 32.766) are
+ * sorted as packed 16-bit keys, both groups in one network pass.  Every value is checked on the
+ * device; a tile with any other value takes the float32 path.  Results are identical either way. */
+int64_t nm_last_grid_tiles(const nm_handle* h);
+
+/* Self-test of the grid-key check on the device: evaluates it on all 2^32 float32 patterns.
+ * *passes = patterns accepted (65 534: the 65 533 grid points |k| <= 32766 and -0.0), *violations =
+ * accepted patterns that are not fl32(k / 1000) or whose key halves are not k + 32768 (must be 0). */
+int nm_grid_selftest(nm_handle* h, int64_t* violations, int64_t* passes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_rank_head_device", "nm_rank_head_select_device",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_last_grid_tiles", "nm_grid_selftest", "nm_rank_head_device", "nm_rank_head_select_device",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -113,6 +113,10 @@ def load():
     lib.nm_sm_count.argtypes = [C.c_void_p]
     lib.nm_last_path.restype = C.c_int
     lib.nm_last_path.argtypes = [C.c_void_p]
+    lib.nm_grid_selftest.restype = C.c_int
+    lib.nm_grid_selftest.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.nm_last_grid_tiles.restype = C.c_int64
+    lib.nm_last_grid_tiles.argtypes = [C.c_void_p]
     lib.nm_last_timings.restype = C.c_int
     lib.nm_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.nm_detect_device.restype = C.c_int
@@ -192,6 +196,16 @@ class Handle:
         """0 general, 1 dense, 2 dense (speculative launch), 3 / 4 speculative launch refused and the call re-run
         dense / on the general path"""
         return int(self._lib.nm_last_path(self._h))
+
+    def last_grid_tiles(self) -> int:
+        """32-position tiles of the last call that the lane tier sorted as packed 16-bit grid keys"""
+        return int(self._lib.nm_last_grid_tiles(self._h))
+
+    def grid_selftest(self):
+        """(violations, passes) of the grid-key check over all 2^32 float32 patterns, on the device"""
+        v, n = C.c_int64(), C.c_int64()
+        self._check(self._lib.nm_grid_selftest(self._h, C.byref(v), C.byref(n)))
+        return int(v.value), int(n.value)
 
     def last_timings(self):
         """Device ms of the last call: {'plan','lane','deep','combine'} (CUDA events)."""

@@ -22,7 +22,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # {FMNMX, FMNMX} (ALU pipe) and {FMNMX, a + b - min on the bit patterns as two IMADs} (FMA pipe).
 # No key conversion at all; measured 0.8 % faster than the int32-key form (-DNM_INT_KEYS) of
 # round 1 (profiles/round2_lane_variants.md).
-DEFAULT_DEFS = ("NM_FLOAT_IMAD",)
+# NM_WALK16_IMAD: the pointer bumps of the grid-key kernel's KS walk as IMADs (its ALU pipe is the busier one:
+# 1.565 -> 1.522 ms, profiles/round2_grid_keys.md).
+DEFAULT_DEFS = ("NM_FLOAT_IMAD", "NM_WALK16_IMAD")
 
 
 def _deps():

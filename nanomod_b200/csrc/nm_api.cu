@@ -387,9 +387,14 @@ struct nm_handle {
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
+  int grid_skip;       // calls left for which the grid-key launch is skipped (the last attempt found off-grid data)
+  nm_buf d_retry;      // retry list of the grid-key launch
+  int grid_u;          // NANOMOD_B200_GRID_U=1: take the grid-key kernel also when U is wanted (tests of that walk)
+  int no_grid;         // NANOMOD_B200_NO_GRID=1: never try the 16-bit grid-key sort of the lane tier (A/B experiments, tests)
   int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
   int dense_class;     // network class of the previous call when it had the dense shape (else 0): the next
                        // call is launched on that assumption without waiting for its plan summary
+  int last_grid_tiles; // lane-tier tiles of the last call that went through the grid-key sort
   int last_path;       // 0 general, 1 dense, 2 dense launched speculatively, 3 / 4 speculative launch refused and
                        // the call re-run dense with the right network class / on the general path
   nm_buf d_comb_z, d_comb_ln, d_deep_fallback, d_exp0, d_exp1;
@@ -462,6 +467,7 @@ extern "C" int nm_last_timings(const nm_handle* h, double* ms4) {
 }
 
 extern "C" int nm_last_path(const nm_handle* h) { return h ? h->last_path : -1; }
+extern "C" int64_t nm_last_grid_tiles(const nm_handle* h) { return h ? h->last_grid_tiles : -1; }
 
 extern "C" int nm_create(int device, nm_handle** out) {
   if (!out) return nm_fail(nullptr, NM_ERR_BAD_ARG, "nm_create: out is NULL");
@@ -491,6 +497,10 @@ extern "C" int nm_create(int device, nm_handle** out) {
     h->slab = sl ? atoll(sl) : 262144;
     const char* d = getenv("NANOMOD_B200_NO_DENSE");
     h->no_dense = (d && d[0] == '1') ? 1 : 0;
+    const char* gk = getenv("NANOMOD_B200_NO_GRID");
+    h->no_grid = (gk && gk[0] == '1') ? 1 : 0;
+    const char* gu = getenv("NANOMOD_B200_GRID_U");
+    h->grid_u = (gu && gu[0] == '1') ? 1 : 0;
   }
   int rc = NM_OK;
   do {
@@ -521,7 +531,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1, &h->d_retry};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -661,6 +671,53 @@ __global__ void __launch_bounds__(256) nm_expand_i16(const int16_t* __restrict__
   }
 }
 
+// nm_grid_selftest: the grid-key statement of nm_lane.cuh on every float32 pattern, on the device
+// (the arithmetic the lane kernel runs: FFMA / FADD / FSETP as compiled for sm_100a).
+__global__ void __launch_bounds__(256) nm_grid_selftest_kernel(unsigned long long* out /* [2]: violations, passes */) {
+  unsigned long long viol = 0, pass = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+    const float x = __uint_as_float((unsigned)b);
+    nm_grid_flag bad = NM_GRID_FLAG0, bad2 = NM_GRID_FLAG0;
+    const unsigned ta = nm_grid_bits(x, NM_GRID_MA, &bad);
+    const unsigned tb = nm_grid_bits(x, NM_GRID_MB, &bad2);
+    const bool ok = !nm_grid_failed(bad) && fabsf(x) <= NM_GRID_LIM, ok2 = !nm_grid_failed(bad2) && fabsf(x) <= NM_GRID_LIM;
+    if (ok != ok2) ++viol;
+    if (!ok) continue;
+    ++pass;
+    const int k = (int)(ta & 0xffffu) - 32768;
+    const float canon = (float)((double)k / 1000.0);
+    if (!(canon == x) || k < -32766 || k > 32766) ++viol;
+    if ((ta >> 16) != 0x4B40u) ++viol;
+    const unsigned packed = tb * 65536u + ta;
+    if ((packed >> 16) != (unsigned)(k + 32768) || (packed & 0xffffu) != (unsigned)(k + 32768)) ++viol;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    viol += __shfl_xor_sync(0xffffffffu, viol, o);
+    pass += __shfl_xor_sync(0xffffffffu, pass, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (viol | pass)) {
+    atomicAdd(out, viol);
+    atomicAdd(out + 1, pass);
+  }
+}
+
+extern "C" int nm_grid_selftest(nm_handle* h, int64_t* violations, int64_t* passes) {
+  if (!h || !violations || !passes) return NM_ERR_BAD_ARG;
+  unsigned long long* d = nullptr;
+  NM_CUDA(h, cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->own_stream);
+  nm_grid_selftest_kernel<<<h->sm_count * 8, 256, 0, h->own_stream>>>(d);
+  unsigned long long r[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(r, d, sizeof(r), cudaMemcpyDeviceToHost, h->own_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+  cudaFree(d);
+  NM_CUDA(h, e);
+  *violations = (int64_t)r[0];
+  *passes = (int64_t)r[1];
+  return NM_OK;
+}
+
 static int nm_expand_i16_run(nm_handle* h, const int16_t* in, float* out, int64_t n, double unit, cudaStream_t st) {
   if (n <= 0) return NM_OK;
   nm_expand_i16<<<(unsigned)((n + 2047) / 2048), 256, 0, st>>>(in, out, n, unit);
@@ -711,6 +768,7 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   ka.row_pos_index = tb->row_pos_index; ka.row_n0 = tb->n0; ka.row_n1 = tb->n1;
   ka.w_row_pos_index = tb->row_pos_index; ka.w_n0 = tb->n0; ka.w_n1 = tb->n1;
   ka.n_rows = n; ka.n_pos = n; ka.one = 1; ka.mone = -1;
+  ka.grid_tries = NM_GRID_TRIES;
   ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
@@ -738,7 +796,23 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
     ka.comb_ln = (double*)h->d_comb_ln.p;
   }
   const int sms = h->sm_limit > 0 ? h->sm_limit : h->sm_count;
-  cudaError_t e = (cudaError_t)nm_launch_lane_dense(ka, want_u, want_m, class_n, sms, st);
+  // Grid keys first (16-bit sort of three-place decimals, checked value by value on the device), then the
+  // float32 kernel over whatever that launch listed or left unclaimed -- normally nothing.  After a call
+  // whose data were not on the grid the attempt is skipped for a while.
+  // not for short rows (the check costs what the packed sort saves) and not with the rank statistics (their walk over
+  // 16-bit columns is slower than the float32 one by more than the sort gains: cfg3 2.65 -> 2.79 ms)
+  const bool try_grid = !h->no_grid && h->grid_skip == 0 && class_n > 64 && (!want_u || h->grid_u);
+  cudaError_t e;
+  if (try_grid) {
+    if ((rc = nm_reserve(h, &h->d_retry, sizeof(int32_t) * (size_t)((n + 31) / 32))) != NM_OK) return rc;
+    ka.retry_tiles = (int32_t*)h->d_retry.p;
+    e = (cudaError_t)nm_launch_lane_dense(ka, want_u, want_m, class_n, sms, true, st);
+    if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_lane_dense_kernel (grid keys) launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+    ka.retry_mode = 1;
+    ka.tile_cursor = &h->d_sum->retry_cursor;
+  }
+  e = (cudaError_t)nm_launch_lane_dense(ka, want_u, want_m, class_n, sms, false, st);
   if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_lane_dense_kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
@@ -769,9 +843,14 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
   *sum_out = *h->h_sum;
+  h->last_grid_tiles = sum_out->grid_tiles;
   *refused = sum_out->dense_retry != 0;
+  if (try_grid && !*refused)
+    h->grid_skip = sum_out->grid_giveup ? NM_GRID_SKIP_CALLS : 0;
+  else if (h->grid_skip > 0 && !*refused)
+    --h->grid_skip;
   if (*refused) {
-    h->launches -= 1 + ((want_u || want_t) ? 1 : 0) + ((want_f || want_s) ? 1 : 0);  // they did not compute
+    h->launches -= (try_grid ? 2 : 1) + ((want_u || want_t) ? 1 : 0) + ((want_f || want_s) ? 1 : 0);  // they did not compute
     // the refused kernels ran on an unvalidated shape: the tails / combine launches read rows the
     // lane kernel never wrote, which is harmless (every column is rewritten by the general path)
     return NM_OK;
@@ -879,7 +958,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     have_sum = true;  // nm_run_dense read the summary back
     h->last_path = 3;
     if (nm_dense_shape(sum)) {  // dense after all, only another network class: launch it again, sized right
-      NM_CUDA(h, cudaMemsetAsync(&h->d_sum->dense_retry, 0, 2 * sizeof(int), st));  // + dense_tile_cursor
+      NM_CUDA(h, cudaMemsetAsync(&h->d_sum->dense_retry, 0, 7 * sizeof(int), st));  // + the cursors and grid-key counters
       rc = nm_run_dense(h, pl, prm, tb, nm_lane_class(sum.max_lane_n), st, &sum, &refused);
       if (rc != NM_OK) return rc;
       if (refused) return nm_fail(h, NM_ERR_CUDA, "internal: dense launch refused after validation");
@@ -921,6 +1000,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
   ka.n_rows = n_rows;
   ka.one = 1;
   ka.mone = -1;
+  ka.sum = h->d_sum;
   ka.ks_dnum = tb->ks_dnum; ka.ks_d = tb->ks_d; ka.ks_p = tb->ks_p;
   ka.two_u = tb->two_u; ka.u_stat = tb->u_stat; ka.u_p = tb->u_p;
   ka.t_stat = tb->t_stat; ka.t_p = tb->t_p; ka.flags = tb->flags;
@@ -998,7 +1078,9 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[4], st));
+  NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
+  h->last_grid_tiles = h->h_sum->grid_tiles;
   if (ds_on && h->h_sum->ds_too_deep)
     return nm_fail(h, NM_ERR_TOO_DEEP, "down-sampling supports at most %d reads per group", NM_DS_MAX_READS);
   {

@@ -23,6 +23,11 @@ __device__ __forceinline__ void nm_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
                "r"(bytes)
                : "memory");
 }
+// raise the phase's pending byte count without arriving (a copy issued ahead of the phase's arrive)
+__device__ __forceinline__ void nm_mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(nm_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void nm_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t addr = nm_smem_u32(bar);
@@ -109,6 +114,12 @@ struct nm_summary {
   int bad_input;        // a candidate with a negative read count (offsets not monotonic) / segment id out of range
   int dense_retry;      // set by nm_lane_dense_kernel: the call does not have the shape the launch assumed
   int dense_tile_cursor;
+  // grid-key launch of the dense path (the seven ints from dense_retry on are zeroed together before a re-run)
+  int retry_cursor;     // work queue of the float32 launch that follows it
+  int retry_count;      // tiles on the retry list
+  int grid_giveup;      // a warp found nothing but off-grid tiles: everybody stops claiming
+  int grid_n_warps;     // warps of the grid-key launch: tiles >= grid_n_warps + dense_tile_cursor were never claimed
+  int grid_tiles;       // tiles the grid-key launch computed (nm_last_grid_tiles)
   int max_deep_t;          // max over deep rows of n0 + n1
   int deep_fallback_count; // (reserved: a device-side count for nm_deep_kernel's row list)
   // {kept candidates, lane-tier candidates of network class <= 64, <= 104, -} counted by nm_plan_count;
@@ -164,6 +175,11 @@ struct nm_kargs {
   int region_floats;  // floats per group region in shared memory (lane tier)
   int class_n;        // size class of the call's longest lane-tier row
   int one, mone;      // runtime 1 / -1: keeps the IMAD form of the integer compare-exchange
+  // dense path, grid keys (nm_lane.cuh): the grid-key launch lists the tiles it could not take in retry_tiles
+  // (count: sum->retry_count); the float32 launch after it (retry_mode = 1) works that list and the unclaimed tail
+  int grid_tries;        // tiles a warp may see fail the check, with none passing, before it raises sum->grid_giveup
+  int retry_mode;
+  int32_t* retry_tiles;  // [number of tiles of the call]
   int* tile_cursor;   // device counter, zero at launch
   // rank sums / moments of the lane tier; their fp64 tails (normal and Student-t
   // tails: a lot of cold fp64 code) run afterwards in nm_tails_kernel, not inside the sort loop
@@ -276,4 +292,5 @@ int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, in
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int
 int nm_launch_lane(const nm_kargs& ka, bool want_u, bool want_t, int max_n, int sm_count, cudaStream_t st);
 // dense variant: rows == candidates (nothing filtered, nothing deep); class_n = network class of the launch
-int nm_launch_lane_dense(const nm_kargs& ka, bool want_u, bool want_t, int class_n, int sm_count, cudaStream_t st);
+int nm_launch_lane_dense(const nm_kargs& ka, bool want_u, bool want_t, int class_n, int sm_count, bool grid_keys,
+                         cudaStream_t st);

@@ -67,6 +67,114 @@ NM_HD nm_key nm_make_key(float x, int) { return x; }
 #endif
 NM_HD float nm_min(float a, float b) { return fminf(a, b); }
 NM_HD float nm_max(float a, float b) { return fmaxf(a, b); }
+#ifndef NM_INT_KEYS
+NM_HD int nm_min(int a, int b) { return a < b ? a : b; }
+NM_HD int nm_max(int a, int b) { return a > b ? a : b; }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Grid keys.  The reference's event means are decimals with three places (norm_mean =
+// round(x, 3), bin/scripts/myRefBaseSignalAnnotation.py:1108), cast to float32 by the packer.
+// For such data k = round(1000 x) is an exact 16-bit image of the value: order and ties of the
+// keys are order and ties of the floats.  Two keys -- the e-th element of group 0 in the low
+// half, of group 1 in the high half -- share one register, and one compare-exchange network
+// pass made of packed 16-bit min/max (VIMNMX.U16x2) sorts BOTH groups: half the instructions
+// of the two float sorts.
+//
+// Nothing is assumed about the input.  Every value is checked while its key is made:
+//   t = fma(x, 1000, M)       M = 1.5*2^23 + bias: the low 16 bits of t's pattern are the key
+//   c = t - M                 = k, exactly
+//   r = fma(x, -1000, c)      = k - 1000 x, exactly (a few bits, far below 24)
+//   q = fma(r, 0.001f, x)     = RN(x + (k/1000 - x)): equals x iff x is the float nearest to k/1000
+// so x passes iff x == fl32(k/1000) -- then x is a function of its key and the key map is
+// injective on the values that pass -- and |x| <= 32.766 keeps k inside the 16 bits.  A tile with a
+// value that fails (off-grid data, a huge value, NaN) is sorted by the float path instead.
+// tests/host_emul checks this statement against ALL float32 values on the CPU (same source),
+// tests/test_gpu_grid.py on the device.
+// Key u = k + 32768 in [2, 65534]; 0 is the -inf sentinel, 0xffff the +inf padding.
+// ------------------------------------------------------------------------------------------
+#define NM_GRID_SCALE 1000.0f
+#define NM_GRID_RCP 0.001f
+#define NM_GRID_LIM 32.766f
+#define NM_GRID_MA 12615680.0f  // 1.5*2^23 + 32768: pattern of t = 0x4B408000 + k
+#define NM_GRID_MB 12596416.0f  // NM_GRID_MA - 0x4B40: (pattern of t) * 65536 + 0x4B40xxxx has u in the high half
+#define NM_GRID_PAD_A 0x4B40FFFFu
+#define NM_GRID_PAD_B 0x0000B4BFu
+#define NM_GRID_TRIES 2        // a warp whose first tiles all failed the check, this many of them, raises the give-up flag
+#define NM_GRID_SKIP_CALLS 15  // calls for which the grid-key launch is skipped after one that gave up
+#define NM_GRID_NINF 0u
+#define NM_GRID_PINF 0xffffffffu
+
+NM_HD unsigned nm_f2u(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(x);
+#else
+  unsigned k;
+  memcpy(&k, &x, sizeof(k));
+  return k;
+#endif
+}
+
+// Key-carrying pattern of x for the low (M = NM_GRID_MA) or high (NM_GRID_MB) half; *bad is raised
+// when x is not the float32 image of a grid point (the range test is the caller's: max |x|).
+// nm_grid_flag accumulates the outcome over the values of a row: a predicate (FSETP chain, ALU
+// pipe), or with -DNM_GRID_FSUM the sum of squares of q - x (FADD + FFMA, FMA pipes), which is
+// zero iff every q == x (-0.0 passes either way: it is 0 to every comparison of the path; NaN fails).
+#ifdef NM_GRID_FSUM
+typedef float nm_grid_flag;
+#define NM_GRID_FLAG0 0.0f
+NM_HD bool nm_grid_failed(float f) { return !(f == 0.0f); }
+#else
+typedef bool nm_grid_flag;
+#define NM_GRID_FLAG0 false
+NM_HD bool nm_grid_failed(bool f) { return f; }
+#endif
+NM_HD unsigned nm_grid_bits(float x, float M, nm_grid_flag* bad) {
+  const float t = fmaf(x, NM_GRID_SCALE, M);
+  const float c = t - M;
+  const float r = fmaf(x, -NM_GRID_SCALE, c);
+  const float q = fmaf(r, NM_GRID_RCP, x);
+#ifdef NM_GRID_FSUM
+  const float e = q - x;
+  *bad = fmaf(e, e, *bad);
+#else
+  *bad = *bad || (q != x);
+#endif
+  return nm_f2u(t);
+}
+
+// Two 16-bit keys in one register, compared half by half.
+struct nm_p16 {
+  unsigned v;
+};
+NM_HD nm_p16 nm_min(nm_p16 a, nm_p16 b) {
+  nm_p16 r;
+#if defined(__CUDA_ARCH__)
+  asm("min.u16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+#else
+  const unsigned al = a.v & 0xffffu, bl = b.v & 0xffffu, ah = a.v >> 16, bh = b.v >> 16;
+  r.v = (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+  return r;
+}
+NM_HD nm_p16 nm_max(nm_p16 a, nm_p16 b) {
+  nm_p16 r;
+#if defined(__CUDA_ARCH__)
+  asm("max.u16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+#else
+  const unsigned al = a.v & 0xffffu, bl = b.v & 0xffffu, ah = a.v >> 16, bh = b.v >> 16;
+  r.v = (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+#endif
+  return r;
+}
+// {min, a + b - min}: the sum of the two halves' maxima is a + b - min as ONE 32-bit integer
+// expression (per half min + max = a + b, so no borrow crosses the halves); two IMADs (FMA pipe)
+NM_HD void nm_ceb(nm_p16& a, nm_p16& b, int one, int mone) {
+  const nm_p16 lo = nm_min(a, b);
+  const unsigned t = a.v * (unsigned)one + b.v;
+  b.v = lo.v * (unsigned)mone + t;
+  a = lo;
+}
 // "B" flavour of the compare-exchange: for integers {min, a + b - min} with the two additions
 // written as multiply-adds by runtime +-1 (IMAD, FMA pipe); floats always use {min, max}
 NM_HD void nm_ceb(int& a, int& b, int one, int mone) {
@@ -117,7 +225,18 @@ NM_HD void nm_ceb(float& a, float& b, int, int) {
 #ifndef NM_CE_MIX
 #define NM_CE_MIX 3
 #endif
-#define NM_CEP(p, i, j) NM_CEP_SEL((p) % NM_CE_MIX == 0, i, j)
+// packed 16-bit pairs: their own mix (the grid-key kernel's walk and key check lean on the ALU pipe
+// harder than the float32 kernel's); 0 = every comparator in the IMAD flavour
+#ifndef NM_CE_MIX_P16
+#define NM_CE_MIX_P16 3
+#endif
+template <class T>
+NM_HD constexpr bool nm_ce_is_a(int p) { return p % NM_CE_MIX == 0; }
+template <>
+NM_HD constexpr bool nm_ce_is_a<nm_p16>(int p) {
+  return NM_CE_MIX_P16 > 0 && p % (NM_CE_MIX_P16 > 0 ? NM_CE_MIX_P16 : 1) == 0;
+}
+#define NM_CEP(p, i, j) NM_CEP_SEL(nm_ce_is_a<T>(p), i, j)
 #define NM_CEP_SEL(isA, i, j)        \
   if constexpr (isA) NM_CE(i, j) else { NM_CEB(i, j) }
 #include "nm_sortnet.inc"
@@ -203,16 +322,43 @@ NM_HD void nm_moments(const float* x, int n, double* mean_out, double* var_out) 
 // statistics each chain closes the tie groups that lie entirely on its side; the group that
 // straddles the split (if any) is closed once, after the loop.  iters >= ceil((n0+n1)/2) is the
 // warp-uniform trip count.
-template <bool WANT_U, int S>
-NM_HD void nm_merge_walk(const nm_key* colA, const nm_key* colB, int n0, int n1, int iters,
+// Column element type K -> the type its values are compared in (16-bit grid keys widen to int).
+template <class K>
+struct nm_walk_val {
+  typedef K type;
+};
+template <>
+struct nm_walk_val<unsigned short> {
+  typedef int type;
+};
+
+// Load of a column element.  A 16-bit key is widened to int behind an empty asm: told that the
+// values fit 16 bits, the compiler otherwise computes min / max with packed 16-bit operations and
+// re-masks every result (two extra instructions per step).
+template <class K>
+NM_HD typename nm_walk_val<K>::type nm_walk_load(const K* p) {
+  return *p;
+}
+template <>
+NM_HD int nm_walk_load<unsigned short>(const unsigned short* p) {
+  int v = *p;
+#if defined(__CUDA_ARCH__)
+  asm("" : "+r"(v));
+#endif
+  return v;
+}
+
+template <bool WANT_U, int S, class K>
+NM_HD void nm_merge_walk(const K* colA, const K* colB, int n0, int n1, int iters,
                          nm_lane_acc* acc) {
+  typedef typename nm_walk_val<K>::type V;
   const int T = n0 + n1, T1 = T >> 1, T2 = T - T1;
-  const nm_key* fa = colA + S;
-  const nm_key* fb = colB + S;
-  nm_key va = *fa, vb = *fb, v = nm_min(va, vb);
-  const nm_key* ba = colA + n0 * S;
-  const nm_key* bb = colB + n1 * S;
-  nm_key ea = *ba, eb = *bb, w = nm_max(ea, eb);
+  const K* fa = colA + S;
+  const K* fb = colB + S;
+  V va = nm_walk_load(fa), vb = nm_walk_load(fb), v = nm_min(va, vb);
+  const K* ba = colA + n0 * S;
+  const K* bb = colB + n1 * S;
+  V ea = nm_walk_load(ba), eb = nm_walk_load(bb), w = nm_max(ea, eb);
   int df = 0, db = 0, dmax = 0;
   int fi = 0, g = 0, ig = 0;    // forward: group-0 count, open group start (count, group-0 count)
   int bi = n0, h = T, ih = n0;  // backward: group-0 count below, open group end (count, group-0 count)
@@ -226,9 +372,9 @@ NM_HD void nm_merge_walk(const nm_key* colA, const nm_key* colB, int n0, int n1,
       fb += tb ? S : 0;
       df += ta ? n1 : 0;
       df -= tb ? n0 : 0;
-      va = *fa;
-      vb = *fb;
-      const nm_key vn = nm_min(va, vb);
+      va = nm_walk_load(fa);
+      vb = nm_walk_load(fb);
+      const V vn = nm_min(va, vb);
       const bool q = act && (vn > v);
       v = vn;
       const int ad = df < 0 ? -df : df;
@@ -252,9 +398,9 @@ NM_HD void nm_merge_walk(const nm_key* colA, const nm_key* colB, int n0, int n1,
       ba -= ta ? S : 0;
       db += tb ? n0 : 0;
       db -= ta ? n1 : 0;
-      ea = *ba;
-      eb = *bb;
-      const nm_key wn = nm_max(ea, eb);
+      ea = nm_walk_load(ba);
+      eb = nm_walk_load(bb);
+      const V wn = nm_max(ea, eb);
       const bool q = act && (wn < w);
       w = wn;
       const int ad = db < 0 ? -db : db;
@@ -359,19 +505,20 @@ NM_HD double nm_build_weights(int nb, double weights_dif, double* w /* [nb+1] */
 //   backward step: take the larger tail (ties: group 1), evaluate |i*T - r*n0| (i, r = group-0 /
 //                  all elements remaining) when the next pooled value below is smaller
 // ------------------------------------------------------------------------------------------
+template <class V>
 struct nm_chain {
-  int ia, ib;     // forward: heads (rows ia+1 / ib+1); backward: tails (rows ia / ib)
-  nm_key va, vb;  // their values
-  nm_key v;       // value of the element taken last (start: see nm_walk_ks4)
-  int m;          // forward: elements taken so far; backward: elements remaining
+  int ia, ib;  // forward: heads (rows ia+1 / ib+1); backward: tails (rows ia / ib)
+  V va, vb;    // their values
+  V v;         // value of the element taken last (start: see nm_walk_ks4)
+  int m;       // forward: elements taken so far; backward: elements remaining
 };
 
-template <int S>
-NM_HD void nm_chain_fwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int n0, int T, int* dmax) {
+template <int S, class K, class V>
+NM_HD void nm_chain_fwd(nm_chain<V>& c, const K* colA, const K* colB, int n0, int T, int* dmax) {
   const bool p = c.va <= c.vb;
   if (p) { ++c.ia; c.va = colA[(c.ia + 1) * S]; } else { ++c.ib; c.vb = colB[(c.ib + 1) * S]; }
   ++c.m;
-  const nm_key vn = nm_min(c.va, c.vb);
+  const V vn = nm_min(c.va, c.vb);
   const bool q = vn > c.v;
   c.v = vn;
   int d = c.ia * T - c.m * n0;
@@ -379,12 +526,12 @@ NM_HD void nm_chain_fwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int
   if (q && d > *dmax) *dmax = d;
 }
 
-template <int S>
-NM_HD void nm_chain_bwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int n0, int T, int* dmax) {
+template <int S, class K, class V>
+NM_HD void nm_chain_bwd(nm_chain<V>& c, const K* colA, const K* colB, int n0, int T, int* dmax) {
   const bool p = c.vb >= c.va;
   if (p) { --c.ib; c.vb = colB[c.ib * S]; } else { --c.ia; c.va = colA[c.ia * S]; }
   --c.m;
-  const nm_key wn = nm_max(c.va, c.vb);
+  const V wn = nm_max(c.va, c.vb);
   const bool q = wn < c.v;
   c.v = wn;
   int d = c.ia * T - c.m * n0;
@@ -393,11 +540,12 @@ NM_HD void nm_chain_bwd(nm_chain& c, const nm_key* colA, const nm_key* colB, int
 }
 
 // two chains meeting in the middle; iters >= ceil(T/2) and iters <= T
-template <int S>
-NM_HD int nm_walk_ks2(const nm_key* colA, const nm_key* colB, int n0, int n1, int iters) {
+template <int S, class K>
+NM_HD int nm_walk_ks2(const K* colA, const K* colB, int n0, int n1, int iters) {
+  typedef typename nm_walk_val<K>::type V;
   const int T = n0 + n1;
-  nm_chain f = {0, 0, colA[S], colB[S], nm_min(colA[S], colB[S]), 0};
-  nm_chain b = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max(colA[n0 * S], colB[n1 * S]), T};
+  nm_chain<V> f = {0, 0, colA[S], colB[S], nm_min((V)colA[S], (V)colB[S]), 0};
+  nm_chain<V> b = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max((V)colA[n0 * S], (V)colB[n1 * S]), T};
   int dmax = 0;
   for (int s = 0; s < iters; ++s) {
     nm_chain_fwd<S>(f, colA, colB, n0, T, &dmax);
@@ -408,8 +556,9 @@ NM_HD int nm_walk_ks2(const nm_key* colA, const nm_key* colB, int n0, int n1, in
 
 // four chains: merge-path split of the pooled order at h = T/2 (ties: group 0 first), a forward
 // and a backward chain per half; 2*it >= ceil(T/2), it <= T/2, 2^search_iters > max(n0, n1)
-template <int S>
-NM_HD int nm_walk_ks4(const nm_key* colA, const nm_key* colB, int n0, int n1, int it, int search_iters) {
+template <int S, class K>
+NM_HD int nm_walk_ks4(const K* colA, const K* colB, int n0, int n1, int it, int search_iters) {
+  typedef typename nm_walk_val<K>::type V;
   const int T = n0 + n1, h = T >> 1;
   int lo = h - n1 > 0 ? h - n1 : 0, hi = h < n0 ? h : n0;
   for (int k = 0; k < search_iters; ++k) {
@@ -419,10 +568,10 @@ NM_HD int nm_walk_ks4(const nm_key* colA, const nm_key* colB, int n0, int n1, in
     lo = P ? lo : mid + 1;
   }
   const int is = lo, js = h - lo;
-  nm_chain f1 = {0, 0, colA[S], colB[S], nm_min(colA[S], colB[S]), 0};
-  nm_chain b1 = {is, js, colA[is * S], colB[js * S], nm_max(colA[is * S], colB[js * S]), h};
-  nm_chain f2 = {is, js, colA[(is + 1) * S], colB[(js + 1) * S], nm_min(colA[(is + 1) * S], colB[(js + 1) * S]), h};
-  nm_chain b2 = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max(colA[n0 * S], colB[n1 * S]), T};
+  nm_chain<V> f1 = {0, 0, colA[S], colB[S], nm_min((V)colA[S], (V)colB[S]), 0};
+  nm_chain<V> b1 = {is, js, colA[is * S], colB[js * S], nm_max((V)colA[is * S], (V)colB[js * S]), h};
+  nm_chain<V> f2 = {is, js, colA[(is + 1) * S], colB[(js + 1) * S], nm_min((V)colA[(is + 1) * S], (V)colB[(js + 1) * S]), h};
+  nm_chain<V> b2 = {n0, n1, colA[n0 * S], colB[n1 * S], nm_max((V)colA[n0 * S], (V)colB[n1 * S]), T};
   int dmax = 0;
   {  // the boundary between pooled elements h-1 and h belongs to neither half's chains
     int dj = is * T - h * n0;

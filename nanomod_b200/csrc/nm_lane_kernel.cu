@@ -226,6 +226,116 @@ __device__ __forceinline__ int nm_walk_ks_fast4(const nm_key* colA, const nm_key
   return dmax >> 7;
 }
 
+// ---- the same two walks over 16-bit grid-key columns: a column is one half of the 32-bit words
+// of region A (row stride 128 bytes as before; group 1 lives 2 bytes above group 0), keys are
+// zero-extended into 32-bit registers and compared as unsigned integers.
+#ifdef NM_WALK16_IMAD  // pointer bump of a chain as a multiply-add by a runtime 1 (FMA pipe instead of ALU)
+#define NM_PTR_ADD16(pred, reg, imm) pred " mad.lo.s32 " reg ", %8, " imm ", " reg ";\n\t"
+#else
+#define NM_PTR_ADD16(pred, reg, imm) pred " add.s32 " reg ", " reg ", " imm ";\n\t"
+#endif
+#define NM_FWD_STEP16(fa, fb, va, vb, v, c, dmax, one)                                    \
+  asm volatile(                                                                      \
+      "{\n\t.reg .pred p, q;\n\t.reg .s32 d;\n\t.reg .u32 vn;\n\t"                    \
+      "setp.le.u32 p, %2, %3;\n\t"                                                   \
+      NM_PTR_ADD16("@p", "%0", "128") NM_PTR_ADD16("@!p", "%1", "128")                  \
+      "@p ld.shared.u16 %2, [%0];\n\t"                                               \
+      "@!p ld.shared.u16 %3, [%1];\n\t"                                              \
+      "min.u32 vn, %2, %3;\n\t"                                                      \
+      "setp.gt.u32 q, vn, %4;\n\t"                                                   \
+      "mov.u32 %4, vn;\n\t"                                                          \
+      "mad.lo.s32 d, %0, %6, %7;\n\t"                                                \
+      "abs.s32 d, d;\n\t"                                                            \
+      "@q max.s32 %5, %5, d;\n\t}"                                                   \
+      : "+r"(fa), "+r"(fb), "+r"(va), "+r"(vb), "+r"(v), "+r"(dmax)                  \
+      : "r"(T), "r"(c), "r"(one))
+
+#define NM_BWD_STEP16(ba, bb, ea, eb, w, c, dmax, one)                                    \
+  asm volatile(                                                                      \
+      "{\n\t.reg .pred p, q;\n\t.reg .s32 d;\n\t.reg .u32 wn;\n\t"                    \
+      "setp.ge.u32 p, %3, %2;\n\t"                                                   \
+      NM_PTR_ADD16("@p", "%1", "-128") NM_PTR_ADD16("@!p", "%0", "-128")                \
+      "@p ld.shared.u16 %3, [%1];\n\t"                                               \
+      "@!p ld.shared.u16 %2, [%0];\n\t"                                              \
+      "max.u32 wn, %2, %3;\n\t"                                                      \
+      "setp.lt.u32 q, wn, %4;\n\t"                                                   \
+      "mov.u32 %4, wn;\n\t"                                                          \
+      "mad.lo.s32 d, %0, %6, %7;\n\t"                                                \
+      "abs.s32 d, d;\n\t"                                                            \
+      "@q max.s32 %5, %5, d;\n\t}"                                                   \
+      : "+r"(ba), "+r"(bb), "+r"(ea), "+r"(eb), "+r"(w), "+r"(dmax)                  \
+      : "r"(T), "r"(c), "r"(one))
+
+__device__ __forceinline__ unsigned nm_umin(unsigned a, unsigned b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned nm_umax(unsigned a, unsigned b) { return a > b ? a : b; }
+
+// colA / colB: the lane's two 16-bit columns (element stride 64)
+__device__ __forceinline__ int nm_walk_ks_fast_g(const unsigned short* colA, const unsigned short* colB, int n0,
+                                                 int n1, int iters, int one) {
+  const int T = n0 + n1;
+  const unsigned A0 = nm_smem_u32(colA), B0 = nm_smem_u32(colB);
+  unsigned fa = A0 + 128u, fb = B0 + 128u;
+  unsigned ba = A0 + 128u * (unsigned)n0, bb = B0 + 128u * (unsigned)n1;
+  unsigned va = colA[64], vb = colB[64], v = nm_umin(va, vb);
+  unsigned ea = colA[n0 << 6], eb = colB[n1 << 6], w = nm_umax(ea, eb);
+  const int k0 = 128 * n0;
+  int cf = -(int)((A0 + 128u) * (unsigned)T) - k0;
+  int cb = -(int)(A0 * (unsigned)T) - k0 * (T - 1);
+  int dmax = 0;
+#pragma unroll 4
+  for (int s = 0; s < iters; ++s) {
+    NM_FWD_STEP16(fa, fb, va, vb, v, cf, dmax, one);
+    NM_BWD_STEP16(ba, bb, ea, eb, w, cb, dmax, one);
+    cf -= k0;
+    cb += k0;
+  }
+  return dmax >> 7;
+}
+
+__device__ __forceinline__ int nm_walk_ks_fast4_g(const unsigned short* colA, const unsigned short* colB, int n0,
+                                                  int n1, int it, int search_iters, int one) {
+  const int T = n0 + n1, h = T >> 1;
+  const unsigned A0 = nm_smem_u32(colA), B0 = nm_smem_u32(colB);
+  int lo = h - n1 > 0 ? h - n1 : 0, hi = h < n0 ? h : n0;
+#pragma unroll 1
+  for (int k = 0; k < search_iters; ++k) {
+    const int mid = (lo + hi) >> 1;
+    const bool P = colB[(h - mid) << 6] < colA[(mid + 1) << 6];
+    hi = P ? mid : hi;
+    lo = P ? lo : mid + 1;
+  }
+  const int is = lo, js = h - lo;
+  unsigned f1a = A0 + 128u, f1b = B0 + 128u;
+  unsigned b1a = A0 + 128u * (unsigned)is, b1b = B0 + 128u * (unsigned)js;
+  unsigned f2a = b1a + 128u, f2b = b1b + 128u;
+  unsigned b2a = A0 + 128u * (unsigned)n0, b2b = B0 + 128u * (unsigned)n1;
+  unsigned v1a = colA[64], v1b = colB[64], v1 = nm_umin(v1a, v1b);
+  unsigned e1a = colA[is << 6], e1b = colB[js << 6], w1 = nm_umax(e1a, e1b);
+  unsigned v2a = colA[(is + 1) << 6], v2b = colB[(js + 1) << 6], v2 = nm_umin(v2a, v2b);
+  unsigned e2a = colA[n0 << 6], e2b = colB[n1 << 6], w2 = nm_umax(e2a, e2b);
+  const int k0 = 128 * n0;
+  const int cF = -(int)((A0 + 128u) * (unsigned)T), cB = -(int)(A0 * (unsigned)T);
+  int cf1 = cF - k0, cb1 = cB - k0 * (h - 1), cf2 = cF - k0 * (h + 1), cb2 = cB - k0 * (T - 1);
+  int dmax = 0;
+  {
+    int dj = 128 * (is * T - h * n0);
+    dj = dj < 0 ? -dj : dj;
+    if (w1 < v2) dmax = dj;
+  }
+#pragma unroll 2
+  for (int s = 0; s < it; ++s) {
+    NM_FWD_STEP16(f1a, f1b, v1a, v1b, v1, cf1, dmax, one);
+    NM_BWD_STEP16(b1a, b1b, e1a, e1b, w1, cb1, dmax, one);
+    NM_FWD_STEP16(f2a, f2b, v2a, v2b, v2, cf2, dmax, one);
+    NM_BWD_STEP16(b2a, b2b, e2a, e2b, w2, cb2, dmax, one);
+    cf1 -= k0;
+    cb1 += k0;
+    cf2 -= k0;
+    cb2 += k0;
+  }
+  return dmax >> 7;
+}
+
 // Per-lane description of one row of a tile (tile = 32 rows of the launch's row list, one per lane).
 struct nm_tile_meta {
   int64_t r;        // row index
@@ -594,16 +704,18 @@ __device__ __forceinline__ void nm_dense_meta_load(const nm_kargs& a, int64_t ti
   nm_cp_async_commit();
 }
 
+// With a.retry_mode the kernel's work is what an nm_lane_grid_kernel launch before it left behind:
+// the tiles on the retry list, then every tile that launch never claimed.
 template <int NMAX>
 __global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, NMAX <= 64 ? 4 : 2)
 nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  nm_summary* S = a.sum;
   {  // the shape this launch was sized for must be the shape the plan found
-    const nm_summary* S = a.sum;
     const bool shape_ok = nm_dense_shape_ok(*S) && nm_lane_class(S->max_lane_n) == a.class_n;
     if (!shape_ok) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) a.sum->dense_retry = 1;
+      if (blockIdx.x == 0 && threadIdx.x == 0) S->dense_retry = 1;
       return;
     }
   }
@@ -618,22 +730,38 @@ nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
   const int warps_per_cta = blockDim.x >> 5;
   const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
 
-  int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
-  if (tile >= n_tiles) return;
+  // work items: tiles 0 .. n_tiles-1, or (retry mode) the retry list followed by the unclaimed tail
+  const bool retry = a.retry_mode != 0;
+  int64_t n_items = n_tiles, n_listed = 0, tail0 = 0;
+  if (retry) {
+    n_listed = S->retry_count;
+    tail0 = (int64_t)S->grid_n_warps + (int64_t)S->dense_tile_cursor;
+    tail0 = tail0 < n_tiles ? tail0 : n_tiles;
+    n_items = n_listed + (n_tiles - tail0);
+  }
+  auto item_tile = [&](int64_t i) -> int64_t {
+    if (i >= n_items) return -1;
+    if (!retry) return i;
+    return i < n_listed ? (int64_t)a.retry_tiles[i] : tail0 + (i - n_listed);
+  };
+
+  int64_t tile = item_tile((int64_t)blockIdx.x * warps_per_cta + wib);
+  if (tile < 0) return;
   if (lane == 0) nm_mbar_init(bar, 1);
   __syncwarp();
   unsigned parity = 0;
   int mb = 0;
   nm_dense_meta_load(a, tile, meta, lane);
-  long long claim = 0;
-  if (lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+  // lane 0 holds the next tile (claimed one tile ahead: the atomic and the list lookup get a whole tile of
+  // work to land)
+  long long claim = -1;
+  if (lane == 0) claim = item_tile((int64_t)atomicAdd(a.tile_cursor, 1) + n_warps);
   bool staged = false;
 
   while (true) {
-    const long long t = __shfl_sync(0xffffffffu, claim, 0);
-    const int64_t next = t < n_tiles ? t : -1;
+    const int64_t next = __shfl_sync(0xffffffffu, claim, 0);
     const bool done = next < 0;
-    if (!done && lane == 0) claim = (long long)atomicAdd(a.tile_cursor, 1) + n_warps;
+    if (!done && lane == 0) claim = item_tile((int64_t)atomicAdd(a.tile_cursor, 1) + n_warps);
 
     // ---- this tile's offsets (landed a tile ago), then the next tile's go on their way
     nm_cp_async_wait_all();
@@ -665,7 +793,7 @@ nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
     nm_lane_acc acc;
     acc.dnum = acc.r2 = acc.tie = 0;
     acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
-    if (want_t) {
+    if (want_t) {  // Welch moments from the raw rows, before the sort overwrites them
       nm_lane_moments(regA, base0, n0, &acc.mean0, &acc.var0);
       nm_lane_moments(regB, base1, n1, &acc.mean1, &acc.var1);
     }
@@ -749,6 +877,310 @@ nm_lane_dense_kernel(const nm_kargs a, const int want_u, const int want_t) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Grid-key variant of the dense kernel (nm_lane.cuh "Grid keys"): values that are three-place
+// decimals -- what the reference stores -- are sorted as 16-bit keys, the two groups of a position
+// packed into one register array and sorted by ONE network pass of VIMNMX.U16x2.  The sorted pairs
+// go back transposed into region A alone (row k+1 = k-th smallest of group 0 | group 1 << 16;
+// row 0 = 0 = -inf, row N+1 = all ones = +inf).
+//  * a tile with a value that is not on the grid is put on the retry list instead of being
+//    computed (nm_lane_dense_kernel with retry_mode runs afterwards); a warp whose first
+//    a.grid_tries tiles all failed raises `grid_giveup`, on which everybody hands back what has
+//    been claimed and stops: data that are not three-place decimals cost a few tiles' checks.
+//  * NM_GRID_LOCKSTEP: tiles are claimed per CTA (4 consecutive tiles, one per warp) and the four
+//    warps -- one per scheduler -- meet at a CTA barrier every round, so that they run through the
+//    ~120 KB of straight-line code of a tile together and share its instruction-cache fills; the
+//    two warps of a scheduler (different CTAs) still drift against each other.
+// A kernel of its own rather than a branch of nm_lane_dense_kernel: with both sorts in one function
+// both ran slower (float32 1.70 -> 2.25 ms; ncu stall no_instruction 0.45 -> 1.12 per issue).
+// ------------------------------------------------------------------------------------------
+#define NM_GRID_ELEM(v, valid, M, PAD, out)                         \
+  {                                                                 \
+    const float x_ = (valid) ? (v) : 0.0f;                          \
+    const unsigned b_ = nm_grid_bits(x_, M, &bad);                  \
+    vmax = fmaxf(vmax, fabsf(x_));                                  \
+    out = (valid) ? b_ : (PAD);                                     \
+  }
+
+template <int N>
+__device__ __forceinline__ bool nm_grid_tile(float* regA, float* regB, int base0, int base1, int n0, int n1,
+                                             int lane, int one, int mone) {
+  nm_p16 w[N];
+  const unsigned sh16 = (unsigned)one << 16;  // runtime 65536: keeps the pack an IMAD (FMA pipe)
+  const int shift0 = base0 & 3, shift1 = base1 & 3;
+  const float4* rawA = reinterpret_cast<const float4*>(regA + (base0 - shift0));
+  const float4* rawB = reinterpret_cast<const float4*>(regB + (base1 - shift1));
+  nm_grid_flag bad = NM_GRID_FLAG0;
+  float vmax = 0.0f;
+  const bool full = __all_sync(0xffffffffu, ((shift0 | shift1) == 0) && (n0 == N) && (n1 == N));
+  if (__builtin_expect(full, 1)) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 a4 = rawA[q], b4 = rawB[q];
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned ta = nm_grid_bits(av[j], NM_GRID_MA, &bad);
+        const unsigned tb = nm_grid_bits(bv[j], NM_GRID_MB, &bad);
+        vmax = fmaxf(vmax, fmaxf(fabsf(av[j]), fabsf(bv[j])));
+        w[4 * q + j].v = tb * sh16 + ta;
+      }
+      if ((q & 3) == 3) asm volatile("" ::: "memory");
+    }
+  } else {
+    // window slot e holds row element e - shift; the (up to 3) elements of a long shifted row that
+    // lie in slots N..N+2 take the slots 0..shift-1, which are free exactly then
+    const float4 wa4 = rawA[N / 4], wb4 = rawB[N / 4];
+    const float wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 a4 = rawA[q], b4 = rawB[q];
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = 4 * q + j;
+        bool va = (unsigned)(e - shift0) < (unsigned)n0, vb = (unsigned)(e - shift1) < (unsigned)n1;
+        float xa = av[j], xb = bv[j];
+        if (e < 3) {
+          const bool wra = (unsigned)(N + e - shift0) < (unsigned)n0, wrb = (unsigned)(N + e - shift1) < (unsigned)n1;
+          xa = wra ? wa[e] : xa;
+          xb = wrb ? wb[e] : xb;
+          va = va || wra;
+          vb = vb || wrb;
+        }
+        unsigned ta, tb;
+        NM_GRID_ELEM(xa, va, NM_GRID_MA, NM_GRID_PAD_A, ta)
+        NM_GRID_ELEM(xb, vb, NM_GRID_MB, NM_GRID_PAD_B, tb)
+        w[e].v = tb * sh16 + ta;
+      }
+      if ((q & 3) == 3) asm volatile("" ::: "memory");
+    }
+  }
+  if (__any_sync(0xffffffffu, nm_grid_failed(bad) || !(vmax <= NM_GRID_LIM))) return false;
+  nm_sorter<N>::run(w, one, mone);
+  __syncwarp();  // every lane has consumed its raw rows; region A may now be overwritten
+  unsigned* col = reinterpret_cast<unsigned*>(regA) + lane;
+  col[0] = NM_GRID_NINF;
+#pragma unroll
+  for (int k = 0; k < N; ++k) col[(k + 1) << 5] = w[nm_sorter<N>::order(k)].v;
+  col[(N + 1) << 5] = NM_GRID_PINF;
+  __syncwarp();
+  return true;
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(32 * NM_LANE_MAX_WARPS, 2)
+nm_lane_grid_kernel(const nm_kargs a, const int want_u, const int want_t) {
+  extern __shared__ __align__(128) unsigned char nm_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  nm_summary* S = a.sum;
+  {  // the shape this launch was sized for must be the shape the plan found
+    const bool shape_ok = nm_dense_shape_ok(*S) && nm_lane_class(S->max_lane_n) == a.class_n;
+    if (!shape_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) S->dense_retry = 1;
+      return;
+    }
+  }
+  const size_t per_warp = 16 + NM_DENSE_META_I64 * sizeof(long long) + 2 * (size_t)a.region_floats * sizeof(float);
+  unsigned char* my = nm_smem + (size_t)wib * per_warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(my);
+  long long* meta = reinterpret_cast<long long*>(my + 16);
+  float* regA = reinterpret_cast<float*>(my + 16 + NM_DENSE_META_I64 * sizeof(long long));
+  float* regB = regA + a.region_floats;
+  const int64_t n_rows = a.n_pos;
+  const int64_t n_tiles = (n_rows + 31) >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
+  if (blockIdx.x == 0 && threadIdx.x == 0) S->grid_n_warps = (int)n_warps;
+  // tiles >= n_tiles are empty rounds of a warp (offsets clamped: n0 = n1 = 0, nothing staged or written)
+#ifdef NM_GRID_LOCKSTEP
+  __shared__ long long s_claim[2];
+  __shared__ int s_gu[2];
+  const int claimer = threadIdx.x == 0;
+  const int claim_n = warps_per_cta;
+  if ((int64_t)blockIdx.x * warps_per_cta >= n_tiles) return;
+#else
+  const int claimer = lane == 0;
+  const int claim_n = 1;
+  if ((int64_t)blockIdx.x * warps_per_cta + wib >= n_tiles) return;
+#endif
+  int64_t tile = (int64_t)blockIdx.x * warps_per_cta + wib;
+  if (lane == 0) nm_mbar_init(bar, 1);
+  __syncwarp();
+  unsigned parity = 0;
+  int mb = 0;
+  nm_dense_meta_load(a, tile < n_tiles ? tile : n_tiles, meta, lane);
+  // the claimer holds the next claim and the give-up flag, both fetched one tile ahead
+  long long claim = 0;
+  int gu = 0;
+  if (claimer) {
+    claim = (long long)atomicAdd(a.tile_cursor, claim_n) + n_warps;
+    gu = *(volatile int*)&S->grid_giveup;
+  }
+  bool staged = false;
+  int grid_fail = 0, grid_done = 0, round = 0;
+
+  while (true) {
+#ifdef NM_GRID_LOCKSTEP
+    if (claimer) {
+      s_claim[round & 1] = claim;
+      s_gu[round & 1] = gu;
+    }
+    __syncthreads();
+    const long long t0 = s_claim[round & 1];
+    const bool giveup = s_gu[round & 1] != 0;
+    bool done = t0 >= n_tiles;  // CTA-uniform
+    int64_t next = t0 + wib;
+#else
+    const long long t0 = __shfl_sync(0xffffffffu, claim, 0);
+    const bool giveup = __shfl_sync(0xffffffffu, gu, 0) != 0 || (grid_done == 0 && grid_fail >= a.grid_tries);
+    bool done = t0 >= n_tiles;
+    int64_t next = t0;
+#endif
+    if (giveup && !done) {  // hand the claimed tile back, claim no more
+      if (lane == 0 && next < n_tiles) a.retry_tiles[atomicAdd(&S->retry_count, 1)] = (int32_t)next;
+      done = true;
+    }
+    if (!done && claimer) {
+      claim = (long long)atomicAdd(a.tile_cursor, claim_n) + n_warps;
+      gu = *(volatile int*)&S->grid_giveup;
+    }
+    ++round;
+    const bool have = tile < n_tiles, have_next = !done && next < n_tiles;
+
+    // ---- this tile's offsets (landed a tile ago), then the next tile's go on their way
+    nm_cp_async_wait_all();
+    __syncwarp();
+    const long long* m0 = meta + mb * 66;
+    const long long* m1 = m0 + 33;
+    const long long o0 = m0[lane], o1 = m1[lane];
+    const int n0 = (int)(m0[lane + 1] - o0), n1 = (int)(m1[lane + 1] - o1);
+    const long long al0 = m0[0] & ~3LL, al1 = m1[0] & ~3LL;
+    const unsigned bytes0 = (unsigned)((m0[32] - al0 + 3) & ~3LL) * 4u, bytes1 = (unsigned)((m1[32] - al1 + 3) & ~3LL) * 4u;
+    const int64_t r = tile * 32 + lane;
+    const bool ok = r < n_rows;
+    const int base0 = ok ? (int)(o0 - al0) : 0, base1 = ok ? (int)(o1 - al1) : 0;
+    if (have_next) nm_dense_meta_load(a, next, meta + (mb ^ 1) * 66, lane);
+
+    bool computed = false;
+    nm_lane_acc acc;
+    acc.dnum = acc.r2 = acc.tie = 0;
+    acc.mean0 = acc.var0 = acc.mean1 = acc.var1 = 0.0;
+    int nmax = 0, tmax = 0;
+    if (have) {
+      if (!staged && lane == 0) {
+        nm_mbar_expect_tx(bar, bytes0 + bytes1);
+        nm_bulk_g2s(regA, a.vals0 + al0, bytes0, bar);
+        nm_bulk_g2s(regB, a.vals1 + al1, bytes1, bar);
+      }
+      nm_mbar_wait(bar, parity);
+      parity ^= 1u;
+      __syncwarp();
+
+      nmax = __reduce_max_sync(0xffffffffu, n0 > n1 ? n0 : n1);
+      tmax = __reduce_max_sync(0xffffffffu, n0 + n1);
+      int nsel = nm_lane_class(nmax);
+      if (2 * nmax > a.class_n) nsel = a.class_n;
+      if (want_t) {  // Welch moments from the raw rows, before the sort overwrites them
+        nm_lane_moments(regA, base0, n0, &acc.mean0, &acc.var0);
+        nm_lane_moments(regB, base1, n1, &acc.mean1, &acc.var1);
+      }
+#define NM_CALL(NN)                                                                          \
+  if (NN <= NMAX)                                                                            \
+    computed = nm_grid_tile<(NN <= NMAX ? NN : NMAX)>(regA, regB, base0, base1, n0, n1, lane, a.one, a.mone)
+      NM_DISPATCH_N(nsel, NM_CALL)
+#undef NM_CALL
+      if (computed) {
+        ++grid_done;
+      } else {
+        ++grid_fail;
+        if (lane == 0) {
+          a.retry_tiles[atomicAdd(&S->retry_count, 1)] = (int32_t)tile;
+          if (grid_done == 0 && grid_fail >= a.grid_tries) S->grid_giveup = 1;
+        }
+      }
+    }
+
+    // ---- the next tile's span: known from its offsets (in shared memory by now); pull it into L2
+    long long nal0 = 0, nal1 = 0;
+    unsigned nbytes0 = 0, nbytes1 = 0;
+    if (have_next) {
+      nm_cp_async_wait_all();
+      __syncwarp();
+      const long long* q0 = meta + (mb ^ 1) * 66;
+      const long long* q1 = q0 + 33;
+      nal0 = q0[0] & ~3LL;
+      nal1 = q1[0] & ~3LL;
+      nbytes0 = (unsigned)((q0[32] - nal0 + 3) & ~3LL) * 4u;
+      nbytes1 = (unsigned)((q1[32] - nal1 + 3) & ~3LL) * 4u;
+      if (lane == 0) {
+        // region B has been free since the key pairs were made (the sorted pairs live in region A): the next
+        // tile's group-1 slice starts now, under the sort's shadow; group 0's follows when the walk is done
+        nm_prefetch_l2(a.vals0 + nal0, nbytes0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nm_mbar_expect_tx_only(bar, nbytes1);
+        nm_bulk_g2s(regB, a.vals1 + nal1, nbytes1, bar);
+      }
+    }
+
+    if (computed) {
+      const unsigned short* gA = reinterpret_cast<const unsigned short*>(regA) + 2 * lane;
+      const unsigned short* gB = gA + 1;
+      const int iters = (tmax + 1) >> 1;
+      const int it4 = (tmax + 3) >> 2;
+      constexpr bool kFour = NMAX > 64;
+      const bool fast = kFour ? __all_sync(0xffffffffu, ((n0 + n1) >> 1) >= it4)
+                              : __all_sync(0xffffffffu, n0 + n1 >= iters);
+      if (want_u)
+        nm_merge_walk<true, 64>(gA, gB, n0, n1, iters, &acc);
+      else if (fast && kFour)
+        acc.dnum = nm_walk_ks_fast4_g(gA, gB, n0, n1, it4, 32 - __clz(nmax), a.one);
+      else if (fast)
+        acc.dnum = nm_walk_ks_fast_g(gA, gB, n0, n1, iters, a.one);
+      else
+        nm_merge_walk<false, 64>(gA, gB, n0, n1, iters, &acc);
+    }
+
+    // ---- the regions are free again: the next tile's copies overlap the fp64 tails
+    __syncwarp();
+    staged = false;
+    if (have_next) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nm_mbar_expect_tx(bar, nbytes0);
+        nm_bulk_g2s(regA, a.vals0 + nal0, nbytes0, bar);
+      }
+      staged = true;
+    }
+
+    if (ok && computed) {
+      double d, pv;
+      nm_ks_tail(acc.dnum, n0, n1, &d, &pv);
+      a.w_row_pos_index[r] = (int32_t)r;
+      a.w_n0[r] = n0;
+      a.w_n1[r] = n1;
+      a.ks_dnum[r] = acc.dnum;
+      if (a.ks_d) a.ks_d[r] = d;
+      a.ks_p[r] = pv;
+      if (a.comb_z) a.comb_z[r] = nm_norm_isf(pv);
+      if (a.comb_ln) a.comb_ln[r] = log(pv);
+      if (want_u) {
+        a.acc_r2[r] = acc.r2;
+        a.acc_tie[r] = acc.tie;
+      }
+      if (want_t) {
+        double4* mom = reinterpret_cast<double4*>(a.acc_mom) + r;
+        *mom = make_double4(acc.mean0, acc.var0, acc.mean1, acc.var1);
+      }
+      if (a.flags && !want_u) a.flags[r] = 0;
+    }
+    if (done) break;
+    tile = next;
+    mb ^= 1;
+  }
+  if (lane == 0 && grid_done) atomicAdd(&S->grid_tiles, grid_done);
+}
+
 static int nm_lane_warp_smem(int region_floats) { return 16 + 2 * region_floats * (int)sizeof(float); }
 
 template <int NMAX>
@@ -819,16 +1251,15 @@ int nm_launch_lane(const nm_kargs& ka_in, bool want_u, bool want_t, int max_n, i
   return nm_launch_lane_t<128>(ka, want_u, want_t, sm_count, st);
 }
 
-template <int NMAX>
-static int nm_launch_lane_dense_t(const nm_kargs& ka, bool want_u, bool want_t, int sm_count, cudaStream_t st) {
-  const int per_warp = 16 + NM_DENSE_META_I64 * (int)sizeof(long long) + 2 * ka.region_floats * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(nm_lane_dense_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       NM_LANE_MAX_WARPS * per_warp);
+template <class K>
+static int nm_launch_dense_any(K kernel, const nm_kargs& ka, int per_warp, bool want_u, bool want_t, int sm_count,
+                               cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NM_LANE_MAX_WARPS * per_warp);
   if (e != cudaSuccess) return (int)e;
   int best_w = 1, best_blocks = 0, best_warps = 0;
   for (int w = NM_LANE_MAX_WARPS; w >= 1; --w) {
     int blocks = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, nm_lane_dense_kernel<NMAX>, 32 * w, (size_t)w * per_warp);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32 * w, (size_t)w * per_warp);
     if (e != cudaSuccess) return (int)e;
     if (blocks * w > best_warps) {
       best_warps = blocks * w;
@@ -841,15 +1272,21 @@ static int nm_launch_lane_dense_t(const nm_kargs& ka, bool want_u, bool want_t, 
   int64_t grid = (tiles + best_w - 1) / best_w;
   const int64_t resident = (int64_t)best_blocks * sm_count;
   if (grid > resident) grid = resident;
-  nm_lane_dense_kernel<NMAX><<<(unsigned)grid, 32 * best_w, (size_t)best_w * per_warp, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
+  kernel<<<(unsigned)grid, 32 * best_w, (size_t)best_w * per_warp, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0);
   return (int)cudaGetLastError();
 }
 
-int nm_launch_lane_dense(const nm_kargs& ka_in, bool want_u, bool want_t, int class_n, int sm_count, cudaStream_t st) {
+// grid_keys: launch nm_lane_grid_kernel (ka.retry_tiles / ka.grid_tries set; classes > 64 only) instead of the
+// float32 kernel
+int nm_launch_lane_dense(const nm_kargs& ka_in, bool want_u, bool want_t, int class_n, int sm_count, bool grid_keys,
+                         cudaStream_t st) {
   nm_kargs ka = ka_in;
   if (ka.n_pos <= 0) return (int)cudaSuccess;
   ka.region_floats = 32 * (class_n + 2);
   ka.class_n = class_n;
-  if (class_n <= 64) return nm_launch_lane_dense_t<64>(ka, want_u, want_t, sm_count, st);
-  return nm_launch_lane_dense_t<128>(ka, want_u, want_t, sm_count, st);
+  const int meta = 16 + NM_DENSE_META_I64 * (int)sizeof(long long);
+  const int per_warp = meta + 2 * ka.region_floats * (int)sizeof(float);
+  if (grid_keys) return nm_launch_dense_any(nm_lane_grid_kernel<128>, ka, per_warp, want_u, want_t, sm_count, st);
+  if (class_n <= 64) return nm_launch_dense_any(nm_lane_dense_kernel<64>, ka, per_warp, want_u, want_t, sm_count, st);
+  return nm_launch_dense_any(nm_lane_dense_kernel<128>, ka, per_warp, want_u, want_t, sm_count, st);
 }

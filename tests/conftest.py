@@ -35,7 +35,14 @@ def emul(request):
                     for f in ("nm_math.cuh", "nm_lane.cuh", "nm_deep.cuh", "nm_sortnet.inc", "nm_sortloop.inc")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         defs = {"int_keys": ["-DNM_INT_KEYS"], "float_imad": ["-DNM_FLOAT_IMAD"], "float_keys": []}[request.param]
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + defs + ["-x", "c++", src, "-o", lib])
+        # hardware FMA for fmaf() where the host has it (the exhaustive grid-key test makes 3e10 of them);
+        # no contraction of a*b+c anywhere else: results do not depend on the flag
+        try:
+            fma = ["-mfma", "-ffp-contract=off"] if " fma " in open("/proc/cpuinfo").read() else []
+        except OSError:
+            fma = []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + fma + defs +
+                              ["-x", "c++", src, "-o", lib])
     L = ctypes.CDLL(lib)
     assert L.emul_sizeof_row_out() == ctypes.sizeof(RowOut)
     dbl = ctypes.c_double
@@ -45,6 +52,12 @@ def emul(request):
         getattr(L, name).restype = dbl
         getattr(L, name).argtypes = args
     L.emul_combine.restype = None
+    L.emul_grid_exhaustive.restype = ctypes.c_longlong
+    L.emul_grid_exhaustive.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    L.emul_lane_position_grid.restype = ctypes.c_int
+    L.emul_lane_position_grid.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.variant = request.param
     return L
 
 

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../nanomod_b200/csrc/nm_lane.cuh"
@@ -129,6 +131,107 @@ void emul_combine(const double* ks_p, const int32_t* pos, const int32_t* seg, in
     if (want_fisher) { f_stat[i] = fs; f_p[i] = fp; }
     if (want_stouffer) { s_stat[i] = ss; s_p[i] = sp; }
   }
+}
+
+// The grid-key statement of nm_lane.cuh against EVERY float32 pattern: a value passes
+// nm_grid_bits + the range test iff it is fl32(fl64(k / 1000)) for an integer |k| <= 32766 (what
+// numpy's cast of the reference's round(x, 3) gives), and then both key patterns carry k + 32768.
+// Returns the number of violations; *n_pass = patterns that pass (65 533 grid points and -0.0).
+long long emul_grid_exhaustive(long long* n_pass, int n_threads) {
+  std::atomic<long long> viol(0), pass(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t)
+    th.emplace_back([&, t]() {
+      long long v = 0, p = 0;
+      const unsigned long long lo = (1ull << 32) * t / n_threads, hi = (1ull << 32) * (t + 1) / n_threads;
+      for (unsigned long long b = lo; b < hi; ++b) {
+        const unsigned bits = (unsigned)b;
+        float x;
+        memcpy(&x, &bits, 4);
+        nm_grid_flag bad = NM_GRID_FLAG0, bad2 = NM_GRID_FLAG0;
+        const unsigned ta = nm_grid_bits(x, NM_GRID_MA, &bad);
+        const unsigned tb = nm_grid_bits(x, NM_GRID_MB, &bad2);
+        const bool ok = !nm_grid_failed(bad) && fabsf(x) <= NM_GRID_LIM, ok2 = !nm_grid_failed(bad2) && fabsf(x) <= NM_GRID_LIM;
+        if (ok != ok2) ++v;
+        if (!ok) continue;
+        ++p;
+        const int k = (int)(ta & 0xffffu) - 32768;
+        const float canon = (float)((double)k / 1000.0);
+        if (!(canon == x) || k < -32766 || k > 32766) ++v;
+        if ((ta >> 16) != 0x4B40u) ++v;
+        const unsigned packed = tb * 65536u + ta;
+        if ((packed >> 16) != (unsigned)(k + 32768) || (packed & 0xffffu) != (unsigned)(k + 32768)) ++v;
+      }
+      viol += v;
+      pass += p;
+    });
+  for (auto& x : th) x.join();
+  *n_pass = pass.load();
+  return viol.load();
+}
+
+// Lane tier through the packed grid-key path (both groups sorted by one network pass over 16-bit
+// key pairs, walks on the 16-bit columns).  Returns 2 when a value fails the grid test (the kernel
+// then takes the float path), else fills *out like emul_lane_position.
+}  // extern "C"
+namespace {
+template <int N>
+int lane_position_grid(const float* a, int n0, const float* b, int n1, bool want_u, bool want_t, int walk,
+                       nm_row_out* out) {
+  nm_lane_acc acc;
+  memset(&acc, 0, sizeof(acc));
+  nm_p16 w[N];
+  nm_grid_flag bad = NM_GRID_FLAG0;
+  float m = 0.0f;
+  for (int k = 0; k < N; ++k) {
+    const unsigned ta = k < n0 ? nm_grid_bits(a[k], NM_GRID_MA, &bad) : NM_GRID_PAD_A;
+    const unsigned tb = k < n1 ? nm_grid_bits(b[k], NM_GRID_MB, &bad) : NM_GRID_PAD_B;
+    if (k < n0) m = fmaxf(m, fabsf(a[k]));
+    if (k < n1) m = fmaxf(m, fabsf(b[k]));
+    w[k].v = tb * 65536u + ta;
+  }
+  if (nm_grid_failed(bad) || !(m <= NM_GRID_LIM)) return 2;
+  if (want_t) {
+    nm_moments(a, n0, &acc.mean0, &acc.var0);
+    nm_moments(b, n1, &acc.mean1, &acc.var1);
+  }
+  nm_sorter<N>::run(w, g_one, g_mone);
+  std::vector<unsigned> col(N + 2 + 4, NM_GRID_PINF);
+  col[0] = NM_GRID_NINF;
+  for (int k = 0; k < N; ++k) col[k + 1] = w[nm_sorter<N>::order(k)].v;
+  const unsigned short* ca = reinterpret_cast<const unsigned short*>(col.data());  // little endian: low half first
+  const unsigned short* cb = ca + 1;
+  const int T = n0 + n1, nmax = n0 > n1 ? n0 : n1;
+  if (want_u || walk == 0) {
+    const int iters = (T + 1) / 2 + 3;
+    if (want_u)
+      nm_merge_walk<true, 2>(ca, cb, n0, n1, iters, &acc);
+    else
+      nm_merge_walk<false, 2>(ca, cb, n0, n1, iters, &acc);
+  } else if (walk == 2) {
+    acc.dnum = nm_walk_ks2<2>(ca, cb, n0, n1, (T + 1) >> 1);
+  } else {
+    int bits = 0;
+    while ((1 << bits) <= nmax) ++bits;
+    if ((T >> 1) < ((T + 3) >> 2)) return 3;
+    acc.dnum = nm_walk_ks4<2>(ca, cb, n0, n1, (T + 3) >> 2, bits);
+  }
+  nm_lane_finish(acc, n0, n1, want_u, want_t, out);
+  return 0;
+}
+}  // namespace
+extern "C" {
+int emul_lane_position_grid(const float* a, int n0, const float* b, int n1, int want_u, int want_t, int walk,
+                            nm_row_out* out) {
+  const int nmax = n0 > n1 ? n0 : n1;
+  if (nmax > NM_LANE_MAX_N || n0 < 2 || n1 < 2) return 1;
+  const int nsel = nm_lane_class(nmax);
+  memset(out, 0, sizeof(*out));
+  int rc = 0;
+#define CALL(NN) rc = lane_position_grid<NN>(a, n0, b, n1, want_u != 0, want_t != 0, walk, out)
+  NM_DISPATCH_N(nsel, CALL)
+#undef CALL
+  return rc;
 }
 
 double emul_kolmogorov_sf(double x) { return nm_kolmogorov_sf(x); }

@@ -174,3 +174,68 @@ def test_fast_walks_match_oracle(emul, chains):
         want = o.per_position(a.astype(np.float64), b.astype(np.float64))["dnum"]
         assert got == want, (case, n0, n1, tmax, got, want)
     assert ran > 1000
+
+
+# ---------------------------------------------------------------------------------------------
+# grid keys (nm_lane.cuh): the 16-bit image of three-place decimals and the packed sort
+# ---------------------------------------------------------------------------------------------
+def test_grid_key_statement_on_every_float32(emul):
+    """nm_grid_bits against ALL 2^32 float32 patterns: a value passes the check iff it is
+    fl32(fl64(k / 1000)) with |k| <= 32766 (numpy's cast of the reference's round(x, 3)) or -0.0, and
+    then both key patterns carry k + 32768.  Hence the key map is injective and monotone on whatever
+    passes: order and ties of the keys are order and ties of the values."""
+    if emul.variant != "float_imad":
+        pytest.skip("same source in every build; checked once")
+    n = ctypes.c_longlong()
+    viol = emul.emul_grid_exhaustive(ctypes.byref(n), os.cpu_count() or 4)
+    assert viol == 0 and n.value == 65534
+
+
+def _run_grid(emul, a, b, want_u, want_t, walk):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    r = RowOut()
+    rc = emul.emul_lane_position_grid(a.ctypes.data_as(FP), len(a), b.ctypes.data_as(FP), len(b), want_u, want_t, walk,
+                                      ctypes.byref(r))
+    return rc, r
+
+
+def test_grid_lane_matches_oracle(emul):
+    """The packed path -- one network pass over (group 0 | group 1 << 16) key pairs, walks over the 16-bit
+    columns -- against the oracle: every network size boundary, unequal n, heavy ties, both signs."""
+    rng = np.random.default_rng(23)
+    sizes = list(range(3, 18)) + [23, 24, 25, 31, 32, 33, 63, 64, 65, 96, 97, 100, 101, 104, 105, 112, 120, 121, 127, 128]
+    for trial in range(500):
+        n0 = int(rng.choice(sizes)) if trial % 2 else int(rng.integers(3, 129))
+        n1 = int(rng.choice([n0, 3, int(rng.integers(3, 129))]))
+        dec = [3, 3, 1, 2, 0][trial % 5]
+        a = np.round(rng.normal(0, [1, 3, 8][trial % 3], n0), dec)
+        b = np.round(rng.normal(rng.choice([0, 0.5, 1, 3, -9]), 1, n1), dec)
+        if trial % 11 == 0:
+            b[:] = a[rng.integers(0, n0, n1)]
+        a, b = np.clip(a, -32.766, 32.766).astype(np.float32), np.clip(b, -32.766, 32.766).astype(np.float32)
+        ref = o.per_position(a.astype(np.float64), b.astype(np.float64))
+        rc, r = _run_grid(emul, a, b, 1, 1, 0)
+        assert rc == 0
+        check(r, ref)
+        for walk in (2, 4):
+            rc, r = _run_grid(emul, a, b, 0, 0, walk)
+            if rc == 0:
+                assert r.dnum == ref["dnum"], (trial, n0, n1, walk)
+
+
+def test_grid_lane_refuses_values_off_the_grid(emul):
+    a = np.round(np.random.default_rng(1).normal(0, 1, 40), 3).astype(np.float32)
+    b = a.copy()
+    assert _run_grid(emul, a, b, 1, 1, 0)[0] == 0
+    for bad in (np.nextafter(np.float32(0.417), np.float32(1)), np.float32(0.4175), np.float32(32.767), np.float32(-40.0),
+                np.float32(1e10), np.float32(np.nan), np.float32(np.inf), np.float32(1e-30)):
+        for grp in (0, 1):
+            x, y = a.copy(), b.copy()
+            (x if grp == 0 else y)[17] = bad
+            assert _run_grid(emul, x, y, 1, 1, 0)[0] == 2, bad
+    x = a.copy()
+    x[3], x[4], x[5] = -0.0, 32.766, -32.766   # grid values all three
+    rc, r = _run_grid(emul, x, b, 1, 1, 0)
+    assert rc == 0
+    check(r, o.per_position(x.astype(np.float64), b.astype(np.float64)))

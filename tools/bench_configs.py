@@ -16,7 +16,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nanomod_b200 as nm
-from bench import make_device_workload, hbm_peak
+import bench
+from bench import make_device_workload, hbm_peak, to_grid_
+
+if os.environ.get("NM_OFF_GRID") == "1":  # raw float32 normals instead of the reference's three-place decimals
+    bench.GRID = False
 
 
 def poisson_workload(length, mean, device, lo=5, hi=128, seed=7):
@@ -40,6 +44,9 @@ def workload_from_counts(c0, c1, device, g=None):
     off1[1:] = torch.cumsum(c1, 0)
     v0 = torch.empty(padded_len(int(off0[-1])), dtype=torch.float32, device=device).normal_(generator=g)
     v1 = torch.empty(padded_len(int(off1[-1])), dtype=torch.float32, device=device).normal_(generator=g)
+    if bench.GRID:
+        to_grid_(v0)
+        to_grid_(v1)
     pos = torch.arange(length, dtype=torch.int32, device=device)
     seg = torch.zeros(length, dtype=torch.int32, device=device)
     return nm.DevicePileup(v0, off0, v1, off1, pos, seg, length), int(off0[-1]) + int(off1[-1])
