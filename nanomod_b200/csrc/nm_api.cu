@@ -617,6 +617,12 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
   NM_CUDA(h, cudaEventRecord(h->ev[2], st));
   if (n_deep > 0) {
     nm_kargs kd = ka;
+    if (!h->no_grid) {  // positions whose values are three-place decimals sort 16-bit key pairs; the others are listed
+      const int rc_r = nm_reserve(h, &h->d_retry, sizeof(int32_t) * (size_t)n_deep);
+      if (rc_r != NM_OK) return rc_r;
+      kd.deep_retry_rows = (int32_t*)h->d_retry.p;
+      kd.deep_retry_count = &h->d_sum->deep_fallback_count;
+    }
     if (n_deep > sum.n_huge) {
       const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
       if (e != cudaSuccess)

@@ -42,9 +42,17 @@ struct nm_view_skew {
   NM_HD float operator[](int i) const { return p[i + (i >> 5)]; }
 };
 
+// 16-bit grid keys (nm_lane.cuh): group 0 in the low halves, group 1 in the high halves of ONE sorted
+// array of key pairs (skewed like nm_view_skew); a view picks a half.  0xffff is the +inf padding.
+struct nm_view_skew16 {
+  const unsigned* p;
+  int sh;  // 0: group 0, 16: group 1
+  NM_HD int operator[](int i) const { return (int)((p[i + (i >> 5)] >> sh) & 0xffffu); }
+};
+
 // number of elements of sorted s[0..n) that are <= x
-template <class V>
-NM_HD int nm_count_le(const V& s, int n, float x) {
+template <class V, class X>
+NM_HD int nm_count_le(const V& s, int n, X x) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -54,8 +62,8 @@ NM_HD int nm_count_le(const V& s, int n, float x) {
 }
 
 // number of elements of sorted s[0..n) that are < x
-template <class V>
-NM_HD int nm_count_lt(const V& s, int n, float x) {
+template <class V, class X>
+NM_HD int nm_count_lt(const V& s, int n, X x) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -68,7 +76,7 @@ NM_HD int nm_count_lt(const V& s, int n, float x) {
 template <class V>
 NM_HD void nm_deep_element(const V& sa, int n0, const V& sb, int n1, int e, bool want_u, nm_deep_acc* one) {
   const bool is_a = e < n0;
-  const float x = is_a ? sa[e] : sb[e - n0];
+  const auto x = is_a ? sa[e] : sb[e - n0];
   const long long ua = nm_count_le(sa, n0, x);
   const long long ub = nm_count_le(sb, n1, x);
   long long d = ua * (long long)n1 - ub * (long long)n0;

@@ -12,18 +12,39 @@
 //           split by binary search) and walks it, evaluating c0*n1 - c1*n0 at tie-group ends;
 //           with the rank statistics: per-element counts by binary search (nm_deep.cuh)
 //   tails   thread 0, fp64
+//   grid keys  when every value of the position is a three-place decimal (nm_lane.cuh "Grid keys": checked
+//           value by value, block-wide) the two groups are packed into ONE array of 16-bit key pairs and
+//           sorted by one pass of the same network with packed min / max: half the sort.  Any other
+//           position takes the float32 sorts.
 #include "nm_device.cuh"
 
-__device__ __forceinline__ void nm_ce_up(float& a, float& b) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
+template <class T>
+__device__ __forceinline__ void nm_ce_up(T& a, T& b) {
+  const T lo = nm_min(a, b), hi = nm_max(a, b);
   a = lo;
   b = hi;
+}
+__device__ __forceinline__ float nm_shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ nm_p16 nm_shfl_xor(nm_p16 v, int m) {
+  nm_p16 r;
+  r.v = __shfl_xor_sync(0xffffffffu, v.v, m);
+  return r;
+}
+template <class T>
+__device__ __forceinline__ T nm_deep_pinf();
+template <>
+__device__ __forceinline__ float nm_deep_pinf<float>() { return NM_INF; }
+template <>
+__device__ __forceinline__ nm_p16 nm_deep_pinf<nm_p16>() {
+  nm_p16 r;
+  r.v = NM_GRID_PINF;
+  return r;
 }
 
 // exchange step of the normalised bitonic network across threads: partner thread tid ^ M,
 // partner element i (same) or E-1-i (reversed: the "flip" first step of a merge)
-template <int E>
-__device__ __forceinline__ void nm_deep_exchange(float (&x)[E], float* stage, int tid, int M, bool reversed) {
+template <int E, class T>
+__device__ __forceinline__ void nm_deep_exchange(T (&x)[E], T* stage, int tid, int M, bool reversed) {
   int hb = M;  // highest set bit of M decides who keeps the minimum
   hb |= hb >> 1; hb |= hb >> 2; hb |= hb >> 4; hb |= hb >> 8;
   hb = (hb + 1) >> 1;
@@ -33,16 +54,16 @@ __device__ __forceinline__ void nm_deep_exchange(float (&x)[E], float* stage, in
 #pragma unroll
       for (int i = 0; i < (E + 1) / 2; ++i) {
         const int r = E - 1 - i;
-        const float o1 = __shfl_xor_sync(0xffffffffu, x[r], M);  // partner's counterpart of my x[i]
-        const float o2 = __shfl_xor_sync(0xffffffffu, x[i], M);  // partner's counterpart of my x[r]
-        x[i] = lower ? fminf(x[i], o1) : fmaxf(x[i], o1);
-        if (r != i) x[r] = lower ? fminf(x[r], o2) : fmaxf(x[r], o2);
+        const T o1 = nm_shfl_xor(x[r], M);  // partner's counterpart of my x[i]
+        const T o2 = nm_shfl_xor(x[i], M);  // partner's counterpart of my x[r]
+        x[i] = lower ? nm_min(x[i], o1) : nm_max(x[i], o1);
+        if (r != i) x[r] = lower ? nm_min(x[r], o2) : nm_max(x[r], o2);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < E; ++i) {
-        const float o = __shfl_xor_sync(0xffffffffu, x[i], M);
-        x[i] = lower ? fminf(x[i], o) : fmaxf(x[i], o);
+        const T o = nm_shfl_xor(x[i], M);
+        x[i] = lower ? nm_min(x[i], o) : nm_max(x[i], o);
       }
     }
   } else {
@@ -55,16 +76,16 @@ __device__ __forceinline__ void nm_deep_exchange(float (&x)[E], float* stage, in
     const int pt = tid ^ M;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      const float o = stage[(reversed ? E - 1 - i : i) * NM_DEEP_THREADS + pt];
-      x[i] = lower ? fminf(x[i], o) : fmaxf(x[i], o);
+      const T o = stage[(reversed ? E - 1 - i : i) * NM_DEEP_THREADS + pt];
+      x[i] = lower ? nm_min(x[i], o) : nm_max(x[i], o);
     }
   }
 }
 
 // sort s[0 .. E*256) ascending in place (s is also used as the staging area)
-template <int E>
-__device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
-  float x[E];
+template <int E, class T>
+__device__ __forceinline__ void nm_deep_sort(T* s, int tid) {
+  T x[E];
   // any E elements make a thread's initial run (the input order is arbitrary): take them strided,
   // which is bank-conflict free (tid * E + i would be an E-way conflict)
 #pragma unroll
@@ -77,9 +98,9 @@ __device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
   // the rolled form spent 40 % of its instructions on that index arithmetic (profiles/round2_deep_experiments.md)
 #pragma unroll
   for (int k = 2 * E; k <= P; k <<= 1) {
-    nm_deep_exchange<E>(x, s, tid, k / E - 1, true);
+    nm_deep_exchange<E, T>(x, s, tid, k / E - 1, true);
 #pragma unroll
-    for (int j = k >> 2; j >= E; j >>= 1) nm_deep_exchange<E>(x, s, tid, j / E, false);
+    for (int j = k >> 2; j >= E; j >>= 1) nm_deep_exchange<E, T>(x, s, tid, j / E, false);
 #pragma unroll
     for (int j = E >> 1; j > 0; j >>= 1) {
 #pragma unroll
@@ -95,25 +116,26 @@ __device__ __forceinline__ void nm_deep_sort(float* s, int tid) {
     const int p = tid * E + i;
     s[p + (p >> 5)] = x[i];
   }
-  if (tid == 0) s[P + (P >> 5)] = NM_INF;  // the sentinel one past the end
+  if (tid == 0) s[P + (P >> 5)] = nm_deep_pinf<T>();  // the sentinel one past the end
   __syncthreads();
 }
 
-template <int EMAX>
-__device__ __forceinline__ void nm_deep_sort_p(float* s, int P, int tid) {
+template <int EMAX, class T>
+__device__ __forceinline__ void nm_deep_sort_p(T* s, int P, int tid) {
   switch (P / NM_DEEP_THREADS) {
-    case 2: nm_deep_sort<2>(s, tid); break;
-    case 4: nm_deep_sort<4>(s, tid); break;
-    case 8: nm_deep_sort<8>(s, tid); break;
-    case 16: nm_deep_sort<16>(s, tid); break;
-    case 32: if (EMAX >= 32) nm_deep_sort<(EMAX >= 32 ? 32 : 2)>(s, tid); break;
-    case 64: if (EMAX >= 64) nm_deep_sort<(EMAX >= 64 ? 64 : 2)>(s, tid); break;
-    default: if (EMAX >= 128) nm_deep_sort<(EMAX >= 128 ? 128 : 2)>(s, tid); break;
+    case 2: nm_deep_sort<2, T>(s, tid); break;
+    case 4: nm_deep_sort<4, T>(s, tid); break;
+    case 8: nm_deep_sort<8, T>(s, tid); break;
+    case 16: nm_deep_sort<16, T>(s, tid); break;
+    case 32: if (EMAX >= 32) nm_deep_sort<(EMAX >= 32 ? 32 : 2), T>(s, tid); break;
+    case 64: if (EMAX >= 64) nm_deep_sort<(EMAX >= 64 ? 64 : 2), T>(s, tid); break;
+    default: if (EMAX >= 128) nm_deep_sort<(EMAX >= 128 ? 128 : 2), T>(s, tid); break;
   }
 }
 
 // KS numerator over this thread's piece [lo, hi) of the pooled order.  sa[n0] and sb[n1] are +inf.
-__device__ __forceinline__ int nm_deep_walk(const nm_view_skew sa, int n0, const nm_view_skew sb, int n1, int lo, int hi) {
+template <class V>
+__device__ __forceinline__ int nm_deep_walk(const V sa, int n0, const V sb, int n1, int lo, int hi) {
   // merge-path split of diagonal lo under the rule "ties: group 0 first"
   int il = lo - n1 > 0 ? lo - n1 : 0, ih = lo < n0 ? lo : n0;
   while (il < ih) {
@@ -121,8 +143,8 @@ __device__ __forceinline__ int nm_deep_walk(const nm_view_skew sa, int n0, const
     if (sa[mid] <= sb[lo - mid - 1]) il = mid + 1; else ih = mid;
   }
   int i = il, j = lo - il;
-  float va = sa[i], vb = sb[j];
-  float v = fminf(va, vb);
+  auto va = sa[i], vb = sb[j];
+  auto v = nm_min(va, vb);
   int dmax = 0;
   for (int s = lo; s < hi; ++s) {
     const bool le = va <= vb;
@@ -130,7 +152,7 @@ __device__ __forceinline__ int nm_deep_walk(const nm_view_skew sa, int n0, const
     j += le ? 0 : 1;
     va = sa[i];
     vb = sb[j];
-    const float vn = fminf(va, vb);
+    const auto vn = nm_min(va, vb);
     const bool q = vn > v;
     v = vn;
     int d = i * n1 - j * n0;
@@ -142,7 +164,10 @@ __device__ __forceinline__ int nm_deep_walk(const nm_view_skew sa, int n0, const
 
 // EMAX = largest per-thread chunk compiled in: 16 covers groups of up to 4096 reads at 3 CTAs/SM,
 // 128 (groups up to 32768 reads) needs most of the register file for one CTA.
-template <int EMAX>
+// GRID: the 16-bit key-pair sort; a position with a value that is not a three-place decimal is put on
+// a.deep_retry_rows instead of being computed, and the float32 instantiation (launched afterwards over that list)
+// takes it.  Two instantiations rather than a branch: with both sorts in one kernel the float32 one ran 23 % slower.
+template <int EMAX, bool GRID>
 __global__ void __launch_bounds__(NM_DEEP_THREADS, EMAX <= 16 ? 4 : 1)
 nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int want_m) {
   extern __shared__ __align__(128) unsigned char nm_smem[];
@@ -219,24 +244,62 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
     }
   }
   __syncthreads();
-  nm_deep_sort_p<EMAX>(sa, P0, tid);
-  nm_deep_sort_p<EMAX>(sb, P1, tid);
-
+  // ---- grid keys?  every value of both groups must be a three-place decimal within the 16-bit range
+  const int Pm = P0 > P1 ? P0 : P1;
+  if (GRID) {
+    nm_grid_flag bad = NM_GRID_FLAG0;
+    float vmax = 0.0f;
+    for (int k = tid; k < Pm; k += NM_DEEP_THREADS) {
+      const float xa = k < n0 ? sa[k] : 0.0f, xb = k < n1 ? sb[k] : 0.0f;
+      (void)nm_grid_bits(xa, NM_GRID_MA, &bad);
+      (void)nm_grid_bits(xb, NM_GRID_MB, &bad);
+      vmax = fmaxf(vmax, fmaxf(fabsf(xa), fabsf(xb)));
+    }
+    if (__syncthreads_or(nm_grid_failed(bad) || !(vmax <= NM_GRID_LIM))) {
+      if (tid == 0) a.deep_retry_rows[atomicAdd(a.deep_retry_count, 1)] = (int32_t)r;
+      return;
+    }
+  }
   nm_deep_acc acc;
   nm_deep_acc_init(&acc);
-  if (want_u) {
-    for (int e = tid; e < n0 + n1; e += NM_DEEP_THREADS) {
-      nm_deep_acc one;
-      nm_deep_acc_init(&one);
-      nm_deep_element(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, e, true, &one);
-      nm_deep_acc_merge(&acc, one);
+  const int T = n0 + n1;
+  const int per = (T + NM_DEEP_THREADS - 1) / NM_DEEP_THREADS;
+  const int wlo = tid * per < T ? tid * per : T;
+  const int whi = wlo + per < T ? wlo + per : T;
+  if (GRID) {
+    // key pairs in place over the longer group's array (index k is read and written by the same thread)
+    nm_p16* pk = reinterpret_cast<nm_p16*>(P0 >= P1 ? sa : sb);
+    for (int k = tid; k < Pm; k += NM_DEEP_THREADS) {
+      const unsigned ta = k < n0 ? nm_f2u(fmaf(sa[k], NM_GRID_SCALE, NM_GRID_MA)) : NM_GRID_PAD_A;
+      const unsigned tb = k < n1 ? nm_f2u(fmaf(sb[k], NM_GRID_SCALE, NM_GRID_MB)) : NM_GRID_PAD_B;
+      pk[k].v = tb * 65536u + ta;
+    }
+    __syncthreads();
+    nm_deep_sort_p<EMAX, nm_p16>(pk, Pm, tid);
+    const nm_view_skew16 ga{reinterpret_cast<const unsigned*>(pk), 0}, gb{reinterpret_cast<const unsigned*>(pk), 16};
+    if (want_u) {
+      for (int e = tid; e < T; e += NM_DEEP_THREADS) {
+        nm_deep_acc one;
+        nm_deep_acc_init(&one);
+        nm_deep_element(ga, n0, gb, n1, e, true, &one);
+        nm_deep_acc_merge(&acc, one);
+      }
+    } else {
+      acc.dnum = nm_deep_walk(ga, n0, gb, n1, wlo, whi);
     }
   } else {
-    const int T = n0 + n1;
-    const int per = (T + NM_DEEP_THREADS - 1) / NM_DEEP_THREADS;
-    const int lo = tid * per < T ? tid * per : T;
-    const int hi = lo + per < T ? lo + per : T;
-    acc.dnum = nm_deep_walk(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, lo, hi);
+    nm_deep_sort_p<EMAX, float>(sa, P0, tid);
+    nm_deep_sort_p<EMAX, float>(sb, P1, tid);
+    if (want_u) {
+      for (int e = tid; e < T; e += NM_DEEP_THREADS) {
+        nm_deep_acc one;
+        nm_deep_acc_init(&one);
+        nm_deep_element(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, e, true, &one);
+        nm_deep_acc_merge(&acc, one);
+      }
+    } else {
+      acc.dnum = nm_deep_walk(nm_view_skew{sa}, n0, nm_view_skew{sb}, n1, wlo, whi);
+    }
   }
   acc.dnum = nm_warp_max_ll(acc.dnum);
   acc.r2 = nm_warp_sum_ll(acc.r2);
@@ -266,18 +329,28 @@ nm_deep_kernel(const nm_kargs a, const int want_u, const int want_t, const int w
   }
 }
 
-template <int EMAX>
+template <int EMAX, bool GRID>
 static int nm_launch_deep_t(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int smem_bytes, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(nm_deep_kernel<EMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(nm_deep_kernel<EMAX, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  nm_deep_kernel<EMAX><<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0, want_m ? 1 : 0);
+  nm_deep_kernel<EMAX, GRID><<<(unsigned)n_deep, NM_DEEP_THREADS, smem_bytes, st>>>(ka, want_u ? 1 : 0, want_t ? 1 : 0, want_m ? 1 : 0);
   return (int)cudaGetLastError();
 }
 
-// max_p2 = largest pow2(n0) + pow2(n1) among the deep rows (each >= NM_DEEP_MIN_P)
-int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
+// max_p2 = largest pow2(n0) + pow2(n1) among the deep rows (each >= NM_DEEP_MIN_P).  With ka.deep_retry_rows set the
+// 16-bit key-pair kernel runs first and the float32 kernel afterwards over the rows it listed (device-side count).
+int nm_launch_deep(const nm_kargs& ka_in, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
                    cudaStream_t st) {
+  nm_kargs ka = ka_in;
   // a group can be at most max_p2 - NM_DEEP_MIN_P long
-  if (max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS) return nm_launch_deep_t<16>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
-  return nm_launch_deep_t<128>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
+  const bool small = max_p2 - NM_DEEP_MIN_P <= 16 * NM_DEEP_THREADS;
+  if (ka.deep_retry_rows) {
+    const int e = small ? nm_launch_deep_t<16, true>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st)
+                        : nm_launch_deep_t<128, true>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
+    if (e != (int)cudaSuccess) return e;
+    ka.deep_rows = ka.deep_retry_rows;
+    ka.deep_count_ptr = ka.deep_retry_count;
+  }
+  return small ? nm_launch_deep_t<16, false>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st)
+               : nm_launch_deep_t<128, false>(ka, want_u, want_t, want_m, n_deep, smem_bytes, st);
 }

@@ -198,6 +198,8 @@ struct nm_kargs {
   const int32_t* deep_rows;
   int n_deep;
   const int* deep_count_ptr;  // when set: only the first *deep_count_ptr entries of deep_rows are rows (device-side count)
+  int32_t* deep_retry_rows;   // deep tier, grid keys: rows the key-pair kernel could not take (-> float32 kernel), or NULL = float32 only
+  int* deep_retry_count;
   // dense path (nm_lane_dense_kernel): rows == candidates, no deep rows.  The kernel validates
   // that against the plan summary on the device, writes the row index / coverage columns itself
   // and leaves norm.isf(p) / ln p of the KS p-value for the combine stencil.

@@ -183,6 +183,38 @@ def test_half_off_grid_call(det):
     assert_table_matches(t, vec(q, opt), opt)
 
 
+def test_deep_tier_grid_keys(det, det_float):
+    """Deep rows (block-per-position tier): positions whose values are three-place decimals sort ONE array of
+    16-bit key pairs (checked block-wide); others sort float32.  Unequal group sizes either way round, a row
+    beyond the 16-bit range, a row with the float next to a grid value -- identical to the float32 path and to
+    the oracle, KS only and with the rank statistics."""
+    rng = np.random.default_rng(33)
+    L = 400
+    c0 = np.full(L, 30, np.int64)
+    c1 = np.full(L, 30, np.int64)
+    deep = {5: (2000, 2000), 6: (3000, 600), 7: (600, 3000), 8: (129, 131), 9: (5, 140), 200: (2048, 2047), 201: (1000, 257),
+            202: (2000, 2000), 203: (2000, 2000), 399: (513, 512)}
+    for i, (a, b) in deep.items():
+        c0[i], c1[i] = a, b
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 3).astype(np.float32)
+    shift = np.zeros(L)
+    shift[5], shift[200] = 0.2, 4.0
+    v1 = np.round(rng.normal(0, 1, off1[-1]) + np.repeat(shift, c1), 3).astype(np.float32)
+    v1[off1[202]:off1[203]] += 40.0                                   # beyond the 16-bit range: float32 sorts
+    v0[off0[203]:off0[204]] = np.float32(0.25)                       # a false tie would change D and U here
+    v1[off1[203]:off1[203] + 1000] = np.nextafter(np.float32(0.25), np.float32(1))
+    v1[off1[203] + 1000:off1[204]] = np.nextafter(np.float32(0.25), np.float32(-1))
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, np.arange(L, dtype=np.int32))
+    for opt in (nm.DetectOptions(neighborPvalues=3, both_combinations=True),
+                nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False)):
+        t = det.detect(p, opt)
+        _tables_identical(t, det_float.detect(p, opt))
+        assert_table_matches(t, vec(p, opt), opt)
+    assert t.ks_dnum[203] == 2000 * 1000
+
+
 def test_grid_check_statement_on_the_device(det):
     """nm_grid_selftest: the device evaluates nm_grid_bits on all 2^32 float32 patterns -- a pattern passes
     iff it is fl32(fl64(k / 1000)), |k| <= 32766 (or -0.0), and the packed key halves are k + 32768."""
