@@ -624,7 +624,7 @@ static int nm_launch_tiers(nm_handle* h, const nm_kargs& ka, bool want_u, bool w
       kd.deep_retry_count = &h->d_sum->deep_fallback_count;
     }
     if (n_deep > sum.n_huge) {
-      const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, st);
+      const cudaError_t e = (cudaError_t)nm_launch_deep(kd, want_u, want_t, want_m, n_deep, max_deep_p2, deep_smem, h->sm_count, st);
       if (e != cudaSuccess)
         return nm_fail(h, NM_ERR_CUDA, "nm_deep_kernel launch failed: %s", cudaGetErrorString(e));
       h->launches++;

@@ -288,7 +288,7 @@ __host__ __device__ __forceinline__ int nm_deep_p2(int n) {
 }
 // host-side launcher of the deep tier (nm_deep_kernel.cu)
 int nm_launch_deep(const nm_kargs& ka, bool want_u, bool want_t, bool want_m, int n_deep, int max_p2, int smem_bytes,
-                   cudaStream_t st);
+                   int sm_count, cudaStream_t st);
 
 
 // host-side launcher of the lane tier (nm_lane_kernel.cu); returns a cudaError_t as int

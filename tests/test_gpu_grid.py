@@ -210,7 +210,14 @@ def test_deep_tier_grid_keys(det, det_float):
     for opt in (nm.DetectOptions(neighborPvalues=3, both_combinations=True),
                 nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False)):
         t = det.detect(p, opt)
-        _tables_identical(t, det_float.detect(p, opt))
+        f = det_float.detect(p, opt)
+        # bit for bit, except the Welch columns of deep rows: the two kernels sum the moments in different orders
+        for name in ("row_pos_index", "n0", "n1", "ks_dnum", "two_u", "flags", "ks_d", "ks_p", "u_stat", "u_p",
+                     "fisher_stat", "fisher_p", "stouffer_stat", "stouffer_p"):
+            x, y = getattr(t, name), getattr(f, name)
+            assert (x is None) == (y is None) and (x is None or np.array_equal(x, y, equal_nan=True)), name
+        if opt.want_t:
+            assert np.allclose(t.t_stat, f.t_stat, rtol=1e-11, atol=1e-13) and np.allclose(t.t_p, f.t_p, rtol=1e-9, atol=0)
         assert_table_matches(t, vec(p, opt), opt)
     assert t.ks_dnum[203] == 2000 * 1000
 
