@@ -54,6 +54,7 @@ BYTES_PER_POS = 4 * (COV + COV) + 16 + 28  # fp32 values + two int
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 HEAD_WANT = 1024           # rows of each rank's ranking head exchanged per step at N > 1
 HEAD_CAP = 4096            # record capacity of the exchange buffer (48-byte records)
+SM_RESERVE = 2             # SMs the persistent lane kernel leaves to NCCL's copy kernel at N > 1
 
 
 def workload_config(n_gpus: int):
@@ -74,7 +75,8 @@ def workload_config(n_gpus: int):
                             "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
                             "sharded, per step each rank's ranking head (>= %d rows, selected on the device) is all-gathered "
                             "over NCCL; sorting the gathered heads into the global ranking is host-side ranking work and, like "
-                            "all ranking at N = 1, not part of the timed step" % (n_gpus, HEAD_WANT)),
+                            "all ranking at N = 1, not part of the timed step; the all-gather of step k runs beside the compute of step k+1 "
+                            "(double-buffered, %d SMs left to NCCL) and every exchange completes inside the timed region" % (n_gpus, HEAD_WANT, SM_RESERVE)),
             "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -408,22 +410,43 @@ def run_gpu_arm(args):
     out = nm.alloc_device_table(opt, n_local, device)
     step_tm = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
     gathered = [None]
+    pending = [None, None]
+    step_no = [0]
     outs = [out]
+    if world > 1:
+        # The exchange of step k (ONE NCCL all-gather of the ranking heads, which the detect call of step k has
+        # selected behind its own kernels) runs on NCCL's stream beside the compute of step k+1: results and head
+        # buffers are double-buffered and the persistent lane kernel leaves a few SMs to NCCL's copy kernel.
+        # Every exchange completes inside the timed region (drained before the closing fence).
+        outs.append(nm.alloc_device_table(opt, n_local, device))
+        det.handle.set_sm_limit(max(1, det.handle.sm_count - args.sm_reserve))
+
+    def drain(b):
+        if pending[b] is not None:
+            pending[b][1].wait()
+            gathered[0] = pending[b][0]
+            pending[b] = None
 
     def step():
         if world == 1:
             rows = det.detect_device(dev, opt, out)  # returns with the results complete on the device
         else:
-            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, out)
+            b = step_no[0] & 1
+            step_no[0] += 1
+            drain(b)  # this buffer pair's previous exchange (two steps ago)
+            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[b], head_want=HEAD_WANT,
+                                  head_cap=HEAD_CAP, slot=b)
             rows = res.n_rows
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
         if world > 1:
-            # head selection kernels + ONE NCCL all-gather, on the device, stream-ordered after the tests
-            gathered[0] = sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP)
+            pending[b] = sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP, slot=b, async_op=True)
         return rows
 
     def fence():
+        if world > 1:
+            drain(0)
+            drain(1)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -446,6 +469,10 @@ def run_gpu_arm(args):
         lane_ms.append(step_tm["lane"])
         comb_ms.append(step_tm["combine"])
         plan_ms.append(step_tm["plan"])
+    if world > 1:  # the last two exchanges belong to the timed region
+        drain(0)
+        drain(1)
+        evs[args.steps].record()
     fence()
     per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     ms_total = evs[0].elapsed_time(evs[args.steps])
@@ -596,6 +623,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--sm-reserve", type=int, default=SM_RESERVE, help="N > 1: SMs left free for NCCL")
     ap.add_argument("--off-grid", action="store_true",
                     help="raw float32 normals instead of the reference's three-place decimals")
     ap.add_argument("--e2e-steps", type=int, default=5)

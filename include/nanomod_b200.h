@@ -191,6 +191,17 @@ int nm_rank_head_select_device(nm_handle* h, const double* key_comb, const doubl
                                int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
                                nm_head_row* records_dev, int64_t cap, void* cuda_stream);
 
+/* Arm that selection for the NEXT nm_detect_device call on this handle: the call launches it on its own
+ * stream right behind its last kernel and BEFORE its host wait (a sharded step then has no idle gap between the
+ * tests and the exchange of the heads), provided the call's rows turn out to be its candidates (nothing filtered)
+ * -- the key columns and the geometry are given for that case.  One shot: nm_head_fired() tells whether it ran;
+ * the arming is dropped when the call returns either way, and the caller then selects with
+ * nm_rank_head_select_device as before.  (Replaces nothing in the reference: see nm_rank_head_device.) */
+int nm_arm_head_select(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                       int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                       nm_head_row* records_dev, int64_t cap);
+int nm_head_fired(const nm_handle* h);
+
 /* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
  * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`
  * (device, 28*n bytes): the unit a rank sends to rank 0 in multi-GPU runs.

@@ -26,7 +26,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_last_grid_tiles", "nm_grid_selftest", "nm_rank_head_device", "nm_rank_head_select_device",
+                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_last_grid_tiles", "nm_grid_selftest", "nm_rank_head_device", "nm_rank_head_select_device", "nm_arm_head_select", "nm_head_fired",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -133,6 +133,11 @@ def load():
     lib.nm_rank_head_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                         C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                         C.c_void_p]
+    lib.nm_arm_head_select.restype = C.c_int
+    lib.nm_arm_head_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
+                                       C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64]
+    lib.nm_head_fired.restype = C.c_int
+    lib.nm_head_fired.argtypes = [C.c_void_p]
     lib.nm_rank_head_select_device.restype = C.c_int
     lib.nm_rank_head_select_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                                C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.c_void_p]
@@ -251,6 +256,15 @@ class Handle:
         self._check(self._lib.nm_rank_head_select_device(self._h, key_comb, key_ks, key_u, n_rows, 1 if reverse else 0, want,
                                                          None if geometry is None else C.byref(geometry), records_dev,
                                                          cap, C.c_void_p(stream)))
+
+    def arm_head_select(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, want: int, geometry,
+                        records_dev: int, cap: int) -> None:
+        """nm_arm_head_select: the next detect_device call launches this selection before its host wait"""
+        self._check(self._lib.nm_arm_head_select(self._h, key_comb, key_ks, key_u, n_rows, 1 if reverse else 0, want,
+                                                 None if geometry is None else C.byref(geometry), records_dev, cap))
+
+    def head_fired(self) -> bool:
+        return bool(self._lib.nm_head_fired(self._h))
 
     def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,
                             stream: int = 0) -> None:

@@ -387,6 +387,16 @@ struct nm_handle {
   int64_t launches;
   int sm_limit;        // SMs the persistent lane kernel may occupy (0 = all)
   int no_class_sort;   // NANOMOD_B200_NO_CLASS_SORT=1: never bin rows by network class (A/B experiments)
+  // nm_arm_head_select: a head selection to be launched by the next nm_detect_device call behind its own
+  // kernels, BEFORE the call's host wait (a sharded step then has no idle gap between the tests and the exchange)
+  struct {
+    int armed, fired;
+    const double* key[3];
+    int64_t n_rows, want, cap;
+    int reverse, have_geo;
+    nm_head_geo geo;
+    nm_head_record* records;
+  } head;
   int grid_skip;       // calls left for which the grid-key launch is skipped (the last attempt found off-grid data)
   nm_buf d_retry;      // retry list of the grid-key launch
   int grid_u;          // NANOMOD_B200_GRID_U=1: take the grid-key kernel also when U is wanted (tests of that walk)
@@ -759,6 +769,23 @@ static void nm_fill_comb_args(nm_comb_args* ca, const nm_pileup* pl, const nm_pa
   ca->f_stat = tb->fisher_stat; ca->f_p = tb->fisher_p; ca->s_stat = tb->stouffer_stat; ca->s_p = tb->stouffer_p;
 }
 
+// The armed head selection (nm_arm_head_select), launched behind the call's last kernel.  It was armed for a
+// call whose rows are its candidates; any other outcome leaves it unfired and the caller selects afterwards.
+static int nm_fire_armed_head(nm_handle* h, int64_t n_rows, int64_t n_pos, cudaStream_t st) {
+  h->head.fired = 0;
+  if (!h->head.armed || n_rows != n_pos) return NM_OK;
+  int rc = nm_reserve(h, &h->d_rank, nm_head_scratch_bytes(1));
+  if (rc != NM_OK) return rc;
+  int launches = 0;
+  const cudaError_t e = (cudaError_t)nm_head_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.reverse,
+                                                 h->head.want, h->head.cap, h->head.geo, h->d_rank.p, h->head.records,
+                                                 h->sm_count, &launches, st);
+  h->launches += launches;
+  if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "armed head selection failed: %s", cudaGetErrorString(e));
+  h->head.fired = 1;
+  return NM_OK;
+}
+
 // Dense path: plan_count has been launched; lane kernel (+ U/t tails) + combine stencil, one sync
 // at the end.  *refused is set when the kernel found another shape than `class_n` was sized for
 // (only possible for a speculative launch); nothing was computed then.
@@ -846,6 +873,7 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[4], st));
+  if ((rc = nm_fire_armed_head(h, n, n, st)) != NM_OK) return rc;
   NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
   *sum_out = *h->h_sum;
@@ -869,8 +897,19 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   return NM_OK;
 }
 
+static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_params* params, const nm_table* tb,
+                                 int64_t* n_rows_out, void* cuda_stream);
 extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_params* params,
                                 const nm_table* tb, int64_t* n_rows_out, void* cuda_stream) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  h->head.fired = 0;
+  const int rc = nm_detect_device_impl(h, pl, params, tb, n_rows_out, cuda_stream);
+  h->head.armed = 0;  // one shot (nm_arm_head_select)
+  if (rc != NM_OK) h->head.fired = 0;
+  return rc;
+}
+static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_params* params, const nm_table* tb,
+                                 int64_t* n_rows_out, void* cuda_stream) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
   if (!pl || !tb || !n_rows_out) return nm_fail(h, NM_ERR_BAD_ARG, "pileup/table/n_rows is NULL");
   nm_params prm;
@@ -1084,6 +1123,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
     h->launches++;
   }
   NM_CUDA(h, cudaEventRecord(h->ev[4], st));
+  if ((rc = nm_fire_armed_head(h, n_rows, n_pos, st)) != NM_OK) return rc;
   NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   NM_CUDA(h, cudaStreamSynchronize(st));
   h->last_grid_tiles = h->h_sum->grid_tiles;
@@ -1525,6 +1565,35 @@ extern "C" int nm_rank_head_select_device(nm_handle* h, const double* key_comb, 
   if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
   return NM_OK;
 }
+
+// Arm the same selection for the NEXT nm_detect_device call on this handle: that call launches it on its own
+// stream right behind its last kernel and before its host wait, provided the call's rows turn out to be its
+// candidates (nothing filtered) -- the key columns and the geometry are given for that case.  One shot:
+// nm_head_fired tells whether it ran; the arming is dropped when the call returns either way.
+extern "C" int nm_arm_head_select(nm_handle* h, const double* key_comb, const double* key_ks, const double* key_u,
+                                  int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
+                                  nm_head_row* records_dev, int64_t cap) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  h->head.armed = h->head.fired = 0;
+  if (!records_dev || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "records_dev is NULL or cap <= 0");
+  if (n_rows <= 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
+  if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
+  memset(&h->head.geo, 0, sizeof(h->head.geo));
+  if (geometry) {
+    if (!geometry->pos || !geometry->seg || geometry->row_offset < 0 || geometry->nearby < 0 ||
+        geometry->row_offset + n_rows > geometry->n_rows_total)
+      return nm_fail(h, NM_ERR_BAD_ARG, "head geometry: NULL pos/seg or a row range outside the row list");
+    h->head.geo.row_pos_index = geometry->row_pos_index; h->head.geo.pos = geometry->pos; h->head.geo.seg = geometry->seg;
+    h->head.geo.row_offset = geometry->row_offset; h->head.geo.n_rows_total = geometry->n_rows_total;
+    h->head.geo.nearby = geometry->nearby;
+  }
+  h->head.key[0] = key_comb; h->head.key[1] = key_ks; h->head.key[2] = key_u;
+  h->head.n_rows = n_rows; h->head.reverse = reverse; h->head.want = want > 0 ? want : 1; h->head.cap = cap;
+  h->head.records = (nm_head_record*)records_dev;
+  h->head.armed = 1;
+  return NM_OK;
+}
+extern "C" int nm_head_fired(const nm_handle* h) { return h ? h->head.fired : 0; }
 
 // ------------------------------------------------------------------------------------------
 // result records for the multi-GPU gather: 28 bytes per row, packed

@@ -197,8 +197,15 @@ __global__ void __launch_bounds__(256) nm_head_hist(const double* __restrict__ k
   __shared__ unsigned h[NM_HEAD_BINS];
   for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 256) h[b] = 0;
   __syncthreads();
-  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256)
-    atomicAdd(&h[(unsigned)(nm_head_image(k0, r, reverse) >> 52)], 1u);
+  // p-values crowd into a handful of exponent bins: the lanes of a warp that hit the same bin add once
+  // (MATCH.ANY), otherwise the shared-memory atomics of a warp serialise on 3-4 addresses
+  const int lane = threadIdx.x & 31;
+  for (int64_t r0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31); r0 < n; r0 += (int64_t)gridDim.x * 256) {
+    const int64_t r = r0 + lane;
+    const unsigned bin = r < n ? (unsigned)(nm_head_image(k0, r, reverse) >> 52) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&h[bin], (unsigned)__popc(peers));
+  }
   __syncthreads();
   for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 256)
     if (h[b]) atomicAdd(&hist[b], h[b]);

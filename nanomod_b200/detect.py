@@ -561,6 +561,24 @@ class Detector:
                                             None if u is None else u.data_ptr(), n_rows, not use_p, want, geo,
                                             records.data_ptr(), cap, stream)
 
+    def arm_head_select(self, out: Dict[str, "object"], row_lo: int, n_rows: int, options: DetectOptions, want: int,
+                        records, cap: int, geometry) -> None:
+        """Arm ``rank_head_select_device`` over rows [row_lo, row_lo + n_rows) of ``out`` for the NEXT
+        ``detect_device`` call: that call launches the selection behind its own kernels, before its host wait,
+        if its rows turn out to be its candidates (``handle.head_fired()`` tells)."""
+        use_p = options.rankUse == "pv"
+        m = options.testMethod
+        sl = slice(row_lo, row_lo + n_rows)
+        comb = None if m == "ks" else out[("fisher" if m == "fisher" else "stouffer") + ("_p" if use_p else "_stat")][sl]
+        ks = out["ks_p" if use_p else "ks_d"][sl]
+        u = out.get("u_p" if use_p else "u_stat")[sl] if options.want_u else None
+        rpi, pos, seg, row_offset, n_total, nearby = geometry
+        geo = _lib.nm_head_geometry(None if rpi is None else rpi.data_ptr(), pos.data_ptr(), seg.data_ptr(),
+                                    int(row_offset), int(n_total), int(nearby), 0)
+        self.handle.arm_head_select(None if comb is None else comb.data_ptr(), ks.data_ptr(),
+                                    None if u is None else u.data_ptr(), n_rows, not use_p, want, geo,
+                                    records.data_ptr(), cap)
+
     def pack_records(self, out: Dict[str, "object"], row_lo: int, n: int, options: DetectOptions, records,
                      stream: Optional[int] = None) -> None:
         """Device-resident table -> 28-byte records {ks_dnum, ks_p, comb stat, comb p} of rows

@@ -172,22 +172,42 @@ class ShardedDetector:
         sl, core_lo, core_hi = shard_with_halo(pileup, lo, hi, shard_halo(options))
         return DevicePileup.from_host(sl, device), core_lo, core_hi, lo - core_lo
 
+    def _head_buffers(self, dev, cap: int, world: int):
+        import torch
+        key = (str(dev), cap, world)
+        if getattr(self, "_head_key", None) != key:
+            self._head_key = key
+            self._head_mine = [torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._head_all = [torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+
     def detect_shard(self, dev, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
-                     out: Optional[Dict[str, "object"]] = None) -> ShardResult:
+                     out: Optional[Dict[str, "object"]] = None, head_want: int = 0, head_cap: int = HEAD_CAP,
+                     slot: int = 0) -> ShardResult:
         """Detection on a device-resident shard (``dev`` = core candidates [core_lo, core_hi) plus
-        halo).  Results stay on the GPU; no communication."""
+        halo).  Results stay on the GPU; no communication.  With ``head_want`` the selection of this
+        rank's ranking head (what ``gather_heads`` exchanges) is armed for the call: it is launched behind
+        the call's own kernels and before its host wait -- when the coverage filter drops nothing, which is
+        what the row range was armed for (``ShardResult.head_slot``; otherwise ``gather_heads`` selects)."""
         import torch
         from .detect import alloc_device_table
         if out is None:
             out = alloc_device_table(options, dev.n_pos, dev.off0.device)
+        if head_want > 0 and core_hi > core_lo:
+            world, _ = self._world()
+            self._head_buffers(dev.pos.device, head_cap, world)
+            self.engine.arm_head_select(out, core_lo, core_hi - core_lo, options, head_want, self._head_mine[slot & 1], head_cap,
+                                        (None, dev.pos, dev.seg, core_lo, dev.n_pos, nearby_rows(options)))
         n_rows = self.engine.detect_device(dev, options, out)
+        fired = head_want > 0 and self.engine.handle.head_fired()
         if n_rows == dev.n_pos:  # nothing filtered: rows are the candidates
             r_lo, r_hi = core_lo, core_hi
         else:
             rpi = out["row_pos_index"][:n_rows]
             edges = torch.searchsorted(rpi, torch.tensor([core_lo, core_hi], dtype=rpi.dtype, device=rpi.device))
             r_lo, r_hi = int(edges[0].item()), int(edges[1].item())
-        return ShardResult(out, dev, n_rows, r_lo, r_hi, cand_lo, options)
+        res = ShardResult(out, dev, n_rows, r_lo, r_hi, cand_lo, options)
+        res.head_slot = (slot & 1, head_want, head_cap) if fired else None
+        return res
 
     def local_head(self, res: ShardResult, want: int) -> LocalHead:
         """Leading rows of this rank's own ranking of its core rows (nm_rank_head_device: three
@@ -214,17 +234,14 @@ class ShardedDetector:
         o = res.options
         world, _ = self._world()
         dev = res.dev.pos.device
-        key = (str(dev), cap, world)
-        if getattr(self, "_head_key", None) != key:
-            self._head_key = key
-            self._head_mine = [torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
-            self._head_all = [torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._head_buffers(dev, cap, world)
         mine, allv = self._head_mine[slot & 1], self._head_all[slot & 1]
-        core = {c: res.out[c][res.r_lo:res.r_hi] for c in ("ks_p", "ks_d", "u_p", "u_stat", "fisher_p", "fisher_stat",
-                                                           "stouffer_p", "stouffer_stat") if c in res.out}
-        rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
-        self.engine.rank_head_select_device(core, res.n_core, o, want, mine, cap,
-                                            geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
+        if getattr(res, "head_slot", None) != (slot & 1, want, cap):  # not selected by the detect call itself
+            core = {c: res.out[c][res.r_lo:res.r_hi] for c in ("ks_p", "ks_d", "u_p", "u_stat", "fisher_p", "fisher_stat",
+                                                               "stouffer_p", "stouffer_stat") if c in res.out}
+            rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
+            self.engine.rank_head_select_device(core, res.n_core, o, want, mine, cap,
+                                                geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
         if world == 1:
             return (mine, None) if async_op else mine
         work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=async_op)
@@ -503,6 +520,7 @@ class ShardResult:
     r_hi: int
     cand_lo: int           # global candidate index of the shard's first candidate
     options: DetectOptions
+    head_slot: Optional[tuple] = None  # (slot, want, cap) when the detect call itself selected the ranking head
 
     @property
     def n_core(self) -> int:

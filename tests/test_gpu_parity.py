@@ -729,6 +729,33 @@ def test_sharded_device_heads_and_text(det, method, rank_use, tmp_path):
     assert sd.called_sites(res, p.seg_names) == full.called_sites()
 
 
+@pytest.mark.parametrize("drop", [0.0, 0.01])
+def test_head_selection_armed_for_the_detect_call(det, drop):
+    """detect_shard(head_want=...) arms the head selection so that the detect call launches it behind its own
+    kernels, before its host wait: same records as selecting afterwards.  With filtered rows the armed range does
+    not apply, nothing fires, and gather_heads selects as before."""
+    import torch
+    from nanomod_b200.sharded import HEAD_REC, shard_halo, shard_with_halo
+    p = nm.synthetic_pileup(20000, 70, 66, drop_frac1=drop, round_decimals=3, seed=12)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False, SaveTest=0)
+    sd = ShardedDetector(det)
+    lo, hi = 4000, 16000
+    sl, core_lo, core_hi = shard_with_halo(p, lo, hi, shard_halo(opt))
+    dev = nm.DevicePileup.from_host(sl, "cuda:0")
+    for _ in range(2):  # second round: the speculative dense launch
+        plain = sd.detect_shard(dev, core_lo, core_hi, lo - core_lo, opt)
+        assert plain.head_slot is None
+        want_rec = sd.gather_heads(plain, 300, cap=1024).cpu().numpy().view(HEAD_REC).copy()
+        armed = sd.detect_shard(dev, core_lo, core_hi, lo - core_lo, opt, head_want=300, head_cap=1024)
+        assert (armed.head_slot is not None) == (drop == 0.0)
+        got_rec = sd.gather_heads(armed, 300, cap=1024).cpu().numpy().view(HEAD_REC).copy()
+        n = int(want_rec[0]["row"])
+        assert n >= 300 and int(got_rec[0]["row"]) == n
+        a = np.sort(want_rec[1:n + 1], order=["row"])
+        b = np.sort(got_rec[1:n + 1], order=["row"])
+        assert a.tobytes() == b.tobytes()
+
+
 # ---------------------------------------------------------------------------------------------
 # pipelined host entry (slabs with halos, copies overlapped with compute) == the one-piece call
 # ---------------------------------------------------------------------------------------------
