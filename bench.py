@@ -73,10 +73,12 @@ def workload_config(n_gpus: int):
                        "raw float32 Gaussian currents (--off-grid): not the three-place decimals the reference stores"),
             "parallelism": ("1 GPU" if n_gpus == 1 else
                             "genome shards x%d (weak scaling), halo of 10 candidates recomputed per side; the table stays "
-                            "sharded, per step each rank's ranking head (>= %d rows, selected on the device) is all-gathered "
-                            "over NCCL; sorting the gathered heads into the global ranking is host-side ranking work and, like "
-                            "all ranking at N = 1, not part of the timed step; the all-gather of step k runs beside the compute of step k+1 "
-                            "(double-buffered, %d SMs left to NCCL) and every exchange completes inside the timed region" % (n_gpus, HEAD_WANT, SM_RESERVE)),
+                            "sharded; per step each rank's ranking head (>= %d rows) is selected on the device behind the step's own "
+                            "kernels and exchanged by the selection kernels themselves, which store it into every rank's buffer over "
+                            "NVLink (peer-mapped HBM; `head_exchange` says whether that or the NCCL all-gather fallback ran); sorting "
+                            "the gathered heads into the global ranking is host-side ranking work and, like all ranking at N = 1, not "
+                            "part of the timed step; every exchange completes inside the timed region" % (n_gpus, HEAD_WANT)),
+            "queue": "steps are issued through nm_detect_device_async, the host one step ahead of the device (two result tables alternate)",
             "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
 
 
@@ -407,51 +409,80 @@ def run_gpu_arm(args):
     halo_hi = halo if rank < world - 1 else 0
     n_local = L + halo_lo + halo_hi
     dev, _shift = make_device_workload(n_local, COV, COV, device, seed=SEED + rank, pos0=rank * L - halo_lo)
-    out = nm.alloc_device_table(opt, n_local, device)
+    # Steps are queued through the asynchronous entry (nm_detect_device_async): the host stays one step ahead of
+    # the device (step k is finished -- its summary looked at -- after step k+1 has been queued), so the device
+    # never idles between steps; two result tables alternate.  At N > 1 the exchange of a step's ranking heads
+    # is fused into their selection: the selection kernels, launched behind the step's own kernels, store the
+    # head into every rank's buffer over NVLink (peer-mapped HBM, nanomod_b200.sharded.HeadExchange) -- no
+    # collective kernel, no SMs set aside.  Without peer mapping the heads go through an NCCL all-gather instead.
+    outs = [nm.alloc_device_table(opt, n_local, device) for _ in range(2)]
     step_tm = {"plan": 0.0, "lane": 0.0, "deep": 0.0, "combine": 0.0}
     gathered = [None]
-    pending = [None, None]
-    step_no = [0]
-    outs = [out]
+    nccl_pending = [None, None]
+    in_flight = []
+    issued = [0]
+    last_res = [None]
+    rows_seen = [0]
+    xchg = None
     if world > 1:
-        # The exchange of step k (ONE NCCL all-gather of the ranking heads, which the detect call of step k has
-        # selected behind its own kernels) runs on NCCL's stream beside the compute of step k+1: results and head
-        # buffers are double-buffered and the persistent lane kernel leaves a few SMs to NCCL's copy kernel.
-        # Every exchange completes inside the timed region (drained before the closing fence).
-        outs.append(nm.alloc_device_table(opt, n_local, device))
-        det.handle.set_sm_limit(max(1, det.handle.sm_count - args.sm_reserve))
+        xchg = None if args.nccl_heads else sd.peer_exchange(HEAD_CAP, device)
+        if xchg is None or not xchg.ok:
+            xchg = None
+            det.handle.set_sm_limit(max(1, det.handle.sm_count - args.sm_reserve))
+    exchange = "peer" if xchg is not None else "nccl"
 
-    def drain(b):
-        if pending[b] is not None:
-            pending[b][1].wait()
-            gathered[0] = pending[b][0]
-            pending[b] = None
+    def nccl_drain(b):
+        if nccl_pending[b] is not None:
+            nccl_pending[b][1].wait()
+            gathered[0] = nccl_pending[b][0]
+            nccl_pending[b] = None
 
-    def step():
+    def issue():
+        b = issued[0] & 1
+        issued[0] += 1
         if world == 1:
-            rows = det.detect_device(dev, opt, out)  # returns with the results complete on the device
+            in_flight.append((b, det.detect_device_async(dev, opt, outs[b])))
         else:
-            b = step_no[0] & 1
-            step_no[0] += 1
-            drain(b)  # this buffer pair's previous exchange (two steps ago)
-            res = sd.detect_shard(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[b], head_want=HEAD_WANT,
-                                  head_cap=HEAD_CAP, slot=b)
-            rows = res.n_rows
+            nccl_drain(b)  # NCCL mode: this buffer pair's previous exchange (two steps ago)
+            in_flight.append((b, sd.detect_shard_async(dev, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[b],
+                                                       head_want=HEAD_WANT, head_cap=HEAD_CAP, slot=b, peer=xchg is not None)))
+
+    def complete():
+        b, pend = in_flight.pop(0)
+        if world == 1:
+            rows_seen[0], _ = det.detect_finish(pend)
+        else:
+            res = sd.finish_shard(pend)
+            rows_seen[0] = res.n_rows
+            last_res[0] = res
+            if xchg is None:
+                nccl_pending[b] = sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP, slot=b, async_op=True)
+            elif res.head_slot is None:  # the armed selection did not run with the step: select + store now
+                sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP, slot=b, async_op=True, peer=True)
         for k, v in det.handle.last_timings().items():
             step_tm[k] = v
-        if world > 1:
-            pending[b] = sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP, slot=b, async_op=True)
-        return rows
+
+    def step():
+        issue()
+        if len(in_flight) > 1:
+            complete()
+
+    def flush():
+        while in_flight:
+            complete()
+        nccl_drain(0)
+        nccl_drain(1)
 
     def fence():
-        if world > 1:
-            drain(0)
-            drain(1)
+        flush()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
+    # the first calls establish the shape synchronously; then W warm-up steps through the queue
+    for b in range(2):
+        det.detect_device(dev, opt, outs[b])
     for _ in range(args.warmup):
         step()
     fence()
@@ -462,18 +493,27 @@ def run_gpu_arm(args):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches1 = det.launch_count
     evs[0].record()
-    rows = 0
     for k in range(args.steps):
-        rows = step()
+        step()
         evs[k + 1].record()
-        lane_ms.append(step_tm["lane"])
-        comb_ms.append(step_tm["combine"])
-        plan_ms.append(step_tm["plan"])
-    if world > 1:  # the last two exchanges belong to the timed region
-        drain(0)
-        drain(1)
+        if k > 0:
+            lane_ms.append(step_tm["lane"])
+            comb_ms.append(step_tm["combine"])
+            plan_ms.append(step_tm["plan"])
+    flush()  # the last step's validation (and, NCCL mode, the last exchanges) belong to the timed region
+    lane_ms.append(step_tm["lane"])
+    comb_ms.append(step_tm["combine"])
+    plan_ms.append(step_tm["plan"])
+    if world > 1:
         evs[args.steps].record()
     fence()
+    rows = rows_seen[0]
+    if world > 1 and xchg is not None:
+        # after the fence every rank's kernels are done: every section of the last step's slot carries its epoch
+        slot = (issued[0] - 1) & 1
+        ep = xchg.epochs(slot)
+        assert np.all(ep == last_res[0].head_epoch), (ep, last_res[0].head_epoch)
+        gathered[0] = xchg.gathered(slot).clone()
     per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     ms_total = evs[0].elapsed_time(evs[args.steps])
     launches = det.launch_count - launches1
@@ -501,6 +541,8 @@ def run_gpu_arm(args):
 
         hout_t = {c: torch.from_numpy(hout[c]) for c in cols}
 
+        e2e_no = [0]
+
         def e2e_step():
             if world == 1:
                 tbl = det.detect(hp, opt, out=hout)  # nm_detect_host: pinned host CSR in, result columns out
@@ -509,8 +551,10 @@ def run_gpu_arm(args):
                 # the sharded product path from host buffers: H2D of the shard, detect_shard, heads
                 # all-gathered, this rank's rows back to (pinned) host memory
                 d = nm.DevicePileup.from_host(hp, device)
-                res = sd.detect_shard(d, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[0])
-                sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP)
+                res = sd.detect_shard(d, halo_lo, halo_lo + L, rank * L - halo_lo, opt, outs[0], head_want=HEAD_WANT,
+                                      head_cap=HEAD_CAP, slot=e2e_no[0] & 1, peer=xchg is not None)
+                sd.gather_heads(res, HEAD_WANT, cap=HEAD_CAP, slot=e2e_no[0] & 1, peer=xchg is not None)
+                e2e_no[0] += 1
                 for c in cols:
                     hout_t[c][:res.n_core].copy_(res.core(c), non_blocking=True)
                 torch.cuda.synchronize()
@@ -532,7 +576,7 @@ def run_gpu_arm(args):
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": 1e3 * float(tt.item()) / e_steps,
                "pcie_GBps": (h2d + d2h) / (float(tt.item()) / e_steps) / 1e9,
                "api": ("nanomod_b200.Detector.detect (nm_detect_host): pinned host CSR in, result columns out" if world == 1 else
-                       "DevicePileup.from_host (pinned) + ShardedDetector.detect_shard + gather_heads (NCCL) + the rank's rows to pinned host")}
+                       "DevicePileup.from_host (pinned) + ShardedDetector.detect_shard + gather_heads (%s) + the rank's rows to pinned host" % exchange)}
     # ---- the same through the 16-bit transport format (N = 1): the workload's values rounded to the
     # reference's 0.001 grid (norm_mean = round(x, 3)), shipped as int16 milli-units, expanded on the GPU
     e2e_i16 = None
@@ -561,7 +605,8 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     variants = None
     if rank == 0 and world == 1 and not args.no_variants and L == GENOME:
-        del dev, out
+        del dev
+        outs.clear()
         torch.cuda.empty_cache()
         variants = run_variants(det, device)
 
@@ -600,6 +645,7 @@ def run_gpu_arm(args):
         if world > 1:
             heads = sd.heads_from_gathered(gathered[0], opt, HEAD_CAP)
             line["head_rows_exchanged"] = [int(h.rows.shape[0]) for h in heads]
+            line["head_exchange"] = exchange
         if variants is not None:
             line["variants"] = variants
         if e2e_i16 is not None:
@@ -623,7 +669,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
-    ap.add_argument("--sm-reserve", type=int, default=SM_RESERVE, help="N > 1: SMs left free for NCCL")
+    ap.add_argument("--sm-reserve", type=int, default=SM_RESERVE, help="N > 1, NCCL heads: SMs left free for NCCL")
+    ap.add_argument("--nccl-heads", action="store_true",
+                    help="N > 1: exchange the ranking heads by an NCCL all-gather instead of peer-memory stores")
     ap.add_argument("--off-grid", action="store_true",
                     help="raw float32 normals instead of the reference's three-place decimals")
     ap.add_argument("--e2e-steps", type=int, default=5)

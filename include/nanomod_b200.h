@@ -191,6 +191,22 @@ int nm_rank_head_select_device(nm_handle* h, const double* key_comb, const doubl
                                int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
                                nm_head_row* records_dev, int64_t cap, void* cuda_stream);
 
+/* Asynchronous form of nm_detect_device for callers that run call after call on the same shape (genome
+ * shards, slabs, benchmark steps): up to TWO calls may be in flight on a handle, so the device never idles while
+ * the host looks at a result.  nm_detect_device_async returns a ticket (0 or 1) as soon as the work is queued
+ * on `cuda_stream` -- without any host wait when the handle's previous call had the dense shape (nothing
+ * filtered, nothing deep, one network class): the kernels are launched on that assumption and validate it on
+ * the device.  Any other call is run to completion before the function returns (the ticket is still valid).
+ * nm_detect_finish(ticket) waits for that call only, re-runs it the ordinary way if the device refused the
+ * assumed shape, and reports n_rows and whether an armed head selection (nm_arm_head_select) ran with it.
+ * Inputs and outputs of a call must stay untouched until it is finished; two calls in flight must write
+ * different tables; tickets are finished in the order they were issued.  nm_last_timings / nm_last_path /
+ * nm_last_grid_tiles describe the call finished last.  (No counterpart in the reference, whose mtest2 is one
+ * synchronous pass: myDetect.py:364-462.) */
+int nm_detect_device_async(nm_handle* h, const nm_pileup* pileup, const nm_params* params, const nm_table* table,
+                           void* cuda_stream, int* ticket_out);
+int nm_detect_finish(nm_handle* h, int ticket, int64_t* n_rows_out, int* head_fired_out);
+
 /* Arm that selection for the NEXT nm_detect_device call on this handle: the call launches it on its own
  * stream right behind its last kernel and BEFORE its host wait (a sharded step then has no idle gap between the
  * tests and the exchange of the heads), provided the call's rows turn out to be its candidates (nothing filtered)
@@ -201,6 +217,32 @@ int nm_arm_head_select(nm_handle* h, const double* key_comb, const double* key_k
                        int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
                        nm_head_row* records_dev, int64_t cap);
 int nm_head_fired(const nm_handle* h);
+
+/* The exchange of a sharded run's heads, fused into their selection.  nm_head_set_peers names, for the NEXT
+ * nm_arm_head_select or nm_rank_head_select_device call on the handle (one shot), up to NM_MAX_PEERS record
+ * buffers in peer-visible device memory: the selection kernels then store the header and every record they
+ * select into each base[p] as well (plain stores over NVLink into the peers' HBM) -- base[p] is this rank's
+ * section (cap + 1 records) of peer p's gathered-heads buffer, so when the kernels of all ranks have finished
+ * every rank holds every head, with no collective kernel and no SM set aside for one.  The header's
+ * `reserved` word carries `epoch` (the caller's step number: readers tell a section still holding an older
+ * step from it), or -1 when the detect call the selection was armed for did not compute (a refused
+ * speculative launch, nm_detect_device_async).  Completion is the caller's to establish (stream/device
+ * synchronisation on every rank + a barrier) before the buffer is read.
+ * nm_peer_alloc / nm_peer_open wrap cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle for buffers shared
+ * between the one-process-per-GPU ranks of a node; within one process any device pointer will do.
+ * (Replaces nothing in the reference, which is single-process: see nm_rank_head_device.) */
+#define NM_MAX_PEERS 16
+#define NM_IPC_HANDLE_BYTES 64
+typedef struct nm_head_peers {
+  int32_t n_peers;
+  int32_t epoch;
+  nm_head_row* base[NM_MAX_PEERS];
+} nm_head_peers;
+int nm_head_set_peers(nm_handle* h, const nm_head_peers* peers);
+int nm_peer_alloc(nm_handle* h, int64_t bytes, void** dev_ptr_out, unsigned char* ipc_handle_out /* 64 bytes */);
+int nm_peer_open(nm_handle* h, const unsigned char* ipc_handle, void** dev_ptr_out);
+int nm_peer_close(nm_handle* h, void* dev_ptr);
+int nm_peer_free(nm_handle* h, void* dev_ptr);
 
 /* Packs rows [row_lo, row_lo + n) of a device-resident table into fixed 28-byte records
  * { int32 ks_dnum | double ks_p | double comb_stat | double comb_p } (no padding) in `records`

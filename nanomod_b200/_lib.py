@@ -26,7 +26,7 @@ ERROR_NAMES = {1: "NM_ERR_BAD_ARG", 2: "NM_ERR_BAD_PARAM", 3: "NM_ERR_CUDA", 4: 
 
 # every symbol include/nanomod_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = ["nm_version", "nm_padded_len", "nm_create", "nm_destroy", "nm_last_error",
-                    "nm_detect_device", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_last_grid_tiles", "nm_grid_selftest", "nm_rank_head_device", "nm_rank_head_select_device", "nm_arm_head_select", "nm_head_fired",
+                    "nm_detect_device", "nm_detect_device_async", "nm_detect_finish", "nm_detect_host", "nm_launch_count", "nm_last_timings", "nm_last_path", "nm_last_grid_tiles", "nm_grid_selftest", "nm_rank_head_device", "nm_rank_head_select_device", "nm_arm_head_select", "nm_head_fired", "nm_head_set_peers", "nm_peer_alloc", "nm_peer_open", "nm_peer_close", "nm_peer_free",
                     "nm_set_sm_limit", "nm_sm_count", "nm_rank_device", "nm_rank_host", "nm_pack_records_device",
                     "nm_format_bound", "nm_format_sign_test"]
 
@@ -70,6 +70,14 @@ class nm_head_geometry(C.Structure):
 
 HEAD_ROW_DTYPE = [("row", "<i8"), ("seg", "<i4"), ("pos", "<i4"), ("full_nbhd", "<i4"), ("reserved", "<i4"),
                   ("key", "<u8", (3,))]
+
+
+NM_MAX_PEERS = 16
+NM_IPC_HANDLE_BYTES = 64
+
+
+class nm_head_peers(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("epoch", C.c_int32), ("base", C.c_void_p * NM_MAX_PEERS)]
 
 
 class nm_text_columns(C.Structure):
@@ -133,6 +141,21 @@ def load():
     lib.nm_rank_head_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                         C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                         C.c_void_p]
+    lib.nm_detect_device_async.restype = C.c_int
+    lib.nm_detect_device_async.argtypes = [C.c_void_p, C.POINTER(nm_pileup), C.POINTER(nm_params), C.POINTER(nm_table),
+                                           C.c_void_p, C.POINTER(C.c_int)]
+    lib.nm_detect_finish.restype = C.c_int
+    lib.nm_detect_finish.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    lib.nm_head_set_peers.restype = C.c_int
+    lib.nm_head_set_peers.argtypes = [C.c_void_p, C.POINTER(nm_head_peers)]
+    lib.nm_peer_alloc.restype = C.c_int
+    lib.nm_peer_alloc.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.nm_peer_open.restype = C.c_int
+    lib.nm_peer_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.nm_peer_close.restype = C.c_int
+    lib.nm_peer_close.argtypes = [C.c_void_p, C.c_void_p]
+    lib.nm_peer_free.restype = C.c_int
+    lib.nm_peer_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.nm_arm_head_select.restype = C.c_int
     lib.nm_arm_head_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
                                        C.POINTER(nm_head_geometry), C.c_void_p, C.c_int64]
@@ -232,6 +255,20 @@ class Handle:
                                                C.c_void_p(int(stream))))
         return int(n_rows.value)
 
+    def detect_device_async(self, pileup: nm_pileup, params: nm_params, table: nm_table, stream: int = 0) -> int:
+        """nm_detect_device_async: queues the call, returns its ticket (finish with ``detect_finish``)."""
+        ticket = C.c_int(-1)
+        self._check(self._lib.nm_detect_device_async(self._h, C.byref(pileup), C.byref(params), C.byref(table),
+                                                     C.c_void_p(int(stream)), C.byref(ticket)))
+        return int(ticket.value)
+
+    def detect_finish(self, ticket: int):
+        """nm_detect_finish -> (n_rows, head_fired)"""
+        n_rows = C.c_int64(0)
+        fired = C.c_int(0)
+        self._check(self._lib.nm_detect_finish(self._h, int(ticket), C.byref(n_rows), C.byref(fired)))
+        return int(n_rows.value), bool(fired.value)
+
     def rank_host(self, key_comb, key_ks, key_u, n_rows: int, reverse: bool, order) -> None:
         """nm_rank_host on raw host addresses (0 / None = key absent)."""
         self._check(self._lib.nm_rank_host(self._h, C.c_void_p(key_comb or 0), C.c_void_p(key_ks),
@@ -265,6 +302,37 @@ class Handle:
 
     def head_fired(self) -> bool:
         return bool(self._lib.nm_head_fired(self._h))
+
+    def head_set_peers(self, bases, epoch: int) -> None:
+        """nm_head_set_peers: the next head selection also stores its header and records into these device
+        addresses (this rank's section of each peer's gathered-heads buffer); ``bases`` empty/None clears."""
+        if not bases:
+            self._check(self._lib.nm_head_set_peers(self._h, None))
+            return
+        pr = nm_head_peers()
+        pr.n_peers = len(bases)
+        pr.epoch = int(epoch)
+        for i, b in enumerate(bases):
+            pr.base[i] = int(b)
+        self._check(self._lib.nm_head_set_peers(self._h, C.byref(pr)))
+
+    def peer_alloc(self, nbytes: int):
+        """nm_peer_alloc -> (device address, 64-byte CUDA IPC handle)"""
+        ptr = C.c_void_p(0)
+        hd = C.create_string_buffer(NM_IPC_HANDLE_BYTES)
+        self._check(self._lib.nm_peer_alloc(self._h, int(nbytes), C.byref(ptr), hd))
+        return int(ptr.value), bytes(hd.raw)
+
+    def peer_open(self, ipc_handle: bytes) -> int:
+        ptr = C.c_void_p(0)
+        self._check(self._lib.nm_peer_open(self._h, C.create_string_buffer(bytes(ipc_handle), NM_IPC_HANDLE_BYTES), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._check(self._lib.nm_peer_close(self._h, C.c_void_p(int(ptr))))
+
+    def peer_free(self, ptr: int) -> None:
+        self._check(self._lib.nm_peer_free(self._h, C.c_void_p(int(ptr))))
 
     def pack_records_device(self, table: nm_table, row_lo: int, n: int, which_combine: int, records: int,
                             stream: int = 0) -> None:

@@ -396,7 +396,9 @@ struct nm_handle {
     int reverse, have_geo;
     nm_head_geo geo;
     nm_head_record* records;
+    nm_head_peers_dev peers;
   } head;
+  nm_head_peers_dev next_peers;  // nm_head_set_peers: taken by the next arming / selection (one shot)
   int grid_skip;       // calls left for which the grid-key launch is skipped (the last attempt found off-grid data)
   nm_buf d_retry;      // retry list of the grid-key launch
   int grid_u;          // NANOMOD_B200_GRID_U=1: take the grid-key kernel also when U is wanted (tests of that walk)
@@ -415,7 +417,22 @@ struct nm_handle {
   cudaStream_t s_in, s_out;
   cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
   int64_t slab;         // candidates per slab (NANOMOD_B200_SLAB; 0 = never pipeline)
-  cudaEvent_t ev[5];   // plan start | tests start | deep start | combine start | end
+  cudaEvent_t* ev;     // plan start | tests start | deep start | combine start | end: the set of the call being issued
+  cudaEvent_t ev_sets[3][5];  // set 0: synchronous calls; sets 1, 2: the two slots of nm_detect_device_async
+  nm_summary* h_sums[3];      // pinned; h_sum points at the current call's (same numbering)
+  cudaEvent_t ev_done[2];     // end of an asynchronous call's work on its stream
+  // nm_detect_device_async: up to two calls in flight.  A call launched on the previous call's shape is
+  // validated (and re-run if the device refused it) by nm_detect_finish.
+  struct nm_pending {
+    int active, done;      // issued and not yet finished | completed synchronously when it was issued
+    int64_t n_rows;
+    nm_pileup pl;
+    nm_params prm;
+    nm_table tb;
+    void* stream;
+    int try_grid, n_launched, head_fired;
+  } pend[2];
+  int async_next;
   double last_ms[4];   // plan, lane tier, deep tier, combine of the most recent call
   char err[512];
 };
@@ -517,9 +534,16 @@ extern "C" int nm_create(int device, nm_handle** out) {
     if (cudaSetDevice(device) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = NM_ERR_CUDA; break; }
     if (cudaMalloc(&h->d_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
-    if (cudaMallocHost(&h->h_sum, sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
-    for (int k = 0; k < 5 && rc == NM_OK; ++k)
-      if (cudaEventCreate(&h->ev[k]) != cudaSuccess) rc = NM_ERR_CUDA;
+    for (int s = 0; s < 3 && rc == NM_OK; ++s) {
+      if (cudaMallocHost(&h->h_sums[s], sizeof(nm_summary)) != cudaSuccess) { rc = NM_ERR_OOM; break; }
+      for (int k = 0; k < 5 && rc == NM_OK; ++k)
+        if (cudaEventCreate(&h->ev_sets[s][k]) != cudaSuccess) rc = NM_ERR_CUDA;
+    }
+    if (rc != NM_OK) break;
+    h->h_sum = h->h_sums[0];
+    h->ev = h->ev_sets[0];
+    for (int s = 0; s < 2 && rc == NM_OK; ++s)
+      if (cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming) != cudaSuccess) rc = NM_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) rc = NM_ERR_CUDA;
     if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) rc = NM_ERR_CUDA;
     for (int k = 0; k < 2 && rc == NM_OK; ++k)
@@ -560,11 +584,15 @@ extern "C" void nm_destroy(nm_handle* h) {
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->d_sum) cudaFree(h->d_sum);
-  if (h->h_sum) cudaFreeHost(h->h_sum);
+  for (int s = 0; s < 3; ++s) {
+    if (h->h_sums[s]) cudaFreeHost(h->h_sums[s]);
+    for (int k = 0; k < 5; ++k)
+      if (h->ev_sets[s][k]) cudaEventDestroy(h->ev_sets[s][k]);
+  }
+  for (int s = 0; s < 2; ++s)
+    if (h->ev_done[s]) cudaEventDestroy(h->ev_done[s]);
   if (h->h_head) cudaFreeHost(h->h_head);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
-  for (int k = 0; k < 5; ++k)
-    if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   free(h);
 }
 
@@ -779,7 +807,7 @@ static int nm_fire_armed_head(nm_handle* h, int64_t n_rows, int64_t n_pos, cudaS
   int launches = 0;
   const cudaError_t e = (cudaError_t)nm_head_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.reverse,
                                                  h->head.want, h->head.cap, h->head.geo, h->d_rank.p, h->head.records,
-                                                 h->sm_count, &launches, st);
+                                                 h->sm_count, &launches, st, h->head.peers.n > 0 ? &h->head.peers : nullptr);
   h->launches += launches;
   if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "armed head selection failed: %s", cudaGetErrorString(e));
   h->head.fired = 1;
@@ -789,8 +817,10 @@ static int nm_fire_armed_head(nm_handle* h, int64_t n_rows, int64_t n_pos, cudaS
 // Dense path: plan_count has been launched; lane kernel (+ U/t tails) + combine stencil, one sync
 // at the end.  *refused is set when the kernel found another shape than `class_n` was sized for
 // (only possible for a speculative launch); nothing was computed then.
-static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb, int class_n,
-                        cudaStream_t st, nm_summary* sum_out, bool* refused) {
+// Split in two for nm_detect_device_async: nm_dense_enqueue issues everything up to the read-back of the
+// summary into h->h_sum, nm_dense_complete looks at it once the stream has got there.
+static int nm_dense_enqueue(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb, int class_n,
+                            cudaStream_t st, int* try_grid_out, int* n_launched_out) {
   const bool want_u = prm.want_u != 0, want_t = prm.want_t != 0;
   const bool want_f = (prm.combine & NM_COMBINE_FISHER) != 0, want_s = (prm.combine & NM_COMBINE_STOUFFER) != 0;
   const int64_t n = pl->n_pos;
@@ -875,7 +905,12 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   NM_CUDA(h, cudaEventRecord(h->ev[4], st));
   if ((rc = nm_fire_armed_head(h, n, n, st)) != NM_OK) return rc;
   NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
-  NM_CUDA(h, cudaStreamSynchronize(st));
+  *try_grid_out = try_grid ? 1 : 0;
+  *n_launched_out = (try_grid ? 2 : 1) + ((want_u || want_t) ? 1 : 0) + ((want_f || want_s) ? 1 : 0);
+  return NM_OK;
+}
+
+static int nm_dense_complete(nm_handle* h, int try_grid, int n_launched, nm_summary* sum_out, bool* refused) {
   *sum_out = *h->h_sum;
   h->last_grid_tiles = sum_out->grid_tiles;
   *refused = sum_out->dense_retry != 0;
@@ -884,7 +919,7 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   else if (h->grid_skip > 0 && !*refused)
     --h->grid_skip;
   if (*refused) {
-    h->launches -= (try_grid ? 2 : 1) + ((want_u || want_t) ? 1 : 0) + ((want_f || want_s) ? 1 : 0);  // they did not compute
+    h->launches -= n_launched;  // they did not compute
     // the refused kernels ran on an unvalidated shape: the tails / combine launches read rows the
     // lane kernel never wrote, which is harmless (every column is rewritten by the general path)
     return NM_OK;
@@ -894,6 +929,32 @@ static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm,
   if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->last_ms[1] = ms;
   if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->last_ms[2] = ms;
   if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->last_ms[3] = ms;
+  return NM_OK;
+}
+
+static int nm_run_dense(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb, int class_n,
+                        cudaStream_t st, nm_summary* sum_out, bool* refused) {
+  int try_grid = 0, n_launched = 0;
+  const int rc = nm_dense_enqueue(h, pl, prm, tb, class_n, st, &try_grid, &n_launched);
+  if (rc != NM_OK) return rc;
+  NM_CUDA(h, cudaStreamSynchronize(st));
+  return nm_dense_complete(h, try_grid, n_launched, sum_out, refused);
+}
+
+// argument checks of a device call on float32 values
+static int nm_check_call(nm_handle* h, const nm_pileup* pl, const nm_params& prm, const nm_table* tb) {
+  const bool want_u = prm.want_u != 0, want_t = prm.want_t != 0;
+  const bool want_f = (prm.combine & NM_COMBINE_FISHER) != 0, want_s = (prm.combine & NM_COMBINE_STOUFFER) != 0;
+  if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
+    return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
+  if ((((uintptr_t)pl->vals0) | ((uintptr_t)pl->vals1)) & 15)
+    return nm_fail(h, NM_ERR_BAD_ARG, "vals0/vals1 must be 16-byte aligned");
+  if (!tb->row_pos_index || !tb->n0 || !tb->n1 || !tb->ks_dnum || !tb->ks_p)
+    return nm_fail(h, NM_ERR_BAD_ARG, "table lacks a mandatory output (row_pos_index,n0,n1,ks_dnum,ks_p)");
+  if (want_u && (!tb->two_u || !tb->u_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_u needs two_u and u_p");
+  if (want_t && (!tb->t_stat || !tb->t_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_t needs t_stat and t_p");
+  if (want_f && (!tb->fisher_stat || !tb->fisher_p)) return nm_fail(h, NM_ERR_BAD_ARG, "fisher outputs missing");
+  if (want_s && (!tb->stouffer_stat || !tb->stouffer_p)) return nm_fail(h, NM_ERR_BAD_ARG, "stouffer outputs missing");
   return NM_OK;
 }
 
@@ -940,16 +1001,7 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
     pl_f32.vals0_i16 = pl_f32.vals1_i16 = nullptr;
     pl = &pl_f32;
   }
-  if (!pl->vals0 || !pl->vals1 || !pl->off0 || !pl->off1 || !pl->pos || !pl->seg)
-    return nm_fail(h, NM_ERR_BAD_ARG, "pileup has a NULL array");
-  if ((((uintptr_t)pl->vals0) | ((uintptr_t)pl->vals1)) & 15)
-    return nm_fail(h, NM_ERR_BAD_ARG, "vals0/vals1 must be 16-byte aligned");
-  if (!tb->row_pos_index || !tb->n0 || !tb->n1 || !tb->ks_dnum || !tb->ks_p)
-    return nm_fail(h, NM_ERR_BAD_ARG, "table lacks a mandatory output (row_pos_index,n0,n1,ks_dnum,ks_p)");
-  if (want_u && (!tb->two_u || !tb->u_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_u needs two_u and u_p");
-  if (want_t && (!tb->t_stat || !tb->t_p)) return nm_fail(h, NM_ERR_BAD_ARG, "want_t needs t_stat and t_p");
-  if (want_f && (!tb->fisher_stat || !tb->fisher_p)) return nm_fail(h, NM_ERR_BAD_ARG, "fisher outputs missing");
-  if (want_s && (!tb->stouffer_stat || !tb->stouffer_p)) return nm_fail(h, NM_ERR_BAD_ARG, "stouffer outputs missing");
+  if ((rc = nm_check_call(h, pl, prm, tb)) != NM_OK) return rc;
 
   const bool ds_on = pl->seg_cov != nullptr && pl->n_seg > 0 && prm.ds_times > 0;
   NM_CUDA(h, cudaSetDevice(h->device));
@@ -1138,6 +1190,125 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
     if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess) h->last_ms[3] = ms;
   }
   return NM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Asynchronous device entry: a caller that runs detection call after call on the same shape (genome shards,
+// slabs, the steps of a benchmark) keeps up to two calls in flight, so that the device never waits for the host
+// between them.  A call is issued without a host wait when the handle's previous call had the dense shape
+// (nothing filtered, nothing deep, one network class): plan + lane + combine (+ an armed head selection) are
+// launched on that assumption, the device validates it, and nm_detect_finish re-runs the call the ordinary way
+// if the device refused.  Any other call is simply run to completion here.
+// ------------------------------------------------------------------------------------------
+extern "C" int nm_detect_device_async(nm_handle* h, const nm_pileup* pl, const nm_params* params, const nm_table* tb,
+                                      void* cuda_stream, int* ticket_out) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!pl || !tb || !ticket_out) return nm_fail(h, NM_ERR_BAD_ARG, "pileup/table/ticket is NULL");
+  *ticket_out = -1;
+  const int s = h->async_next & 1;
+  nm_handle::nm_pending* pd = &h->pend[s];
+  if (pd->active) {
+    h->head.armed = 0;
+    return nm_fail(h, NM_ERR_BAD_ARG, "two asynchronous calls are in flight: nm_detect_finish the older one first");
+  }
+  const nm_handle::nm_pending* other = &h->pend[s ^ 1];
+  if (other->active && !other->done && other->tb.ks_dnum == tb->ks_dnum) {
+    h->head.armed = 0;
+    return nm_fail(h, NM_ERR_BAD_ARG, "the two calls in flight must write different tables");
+  }
+  nm_params prm;
+  int rc = nm_check_params(h, params, &prm);
+  if (rc != NM_OK) { h->head.armed = 0; return rc; }
+  const bool ds_on = pl->seg_cov != nullptr && pl->n_seg > 0 && prm.ds_times > 0;
+  const bool fast = h->dense_class > 0 && !h->no_dense && !ds_on && pl->vals0 && pl->vals1 && pl->n_pos > 0 &&
+                    pl->n_pos <= 0x7fffffffLL - NM_PLAN_PER_BLOCK;
+  memset(pd, 0, sizeof(*pd));
+  if (!fast) {
+    int64_t n_rows = 0;
+    rc = nm_detect_device(h, pl, params, tb, &n_rows, cuda_stream);
+    if (rc != NM_OK) return rc;
+    pd->active = pd->done = 1;
+    pd->n_rows = n_rows;
+    pd->head_fired = h->head.fired;
+    *ticket_out = s;
+    h->async_next++;
+    return NM_OK;
+  }
+  h->head.fired = 0;
+  if ((rc = nm_check_call(h, pl, prm, tb)) != NM_OK) { h->head.armed = 0; return rc; }
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t n_pos = pl->n_pos;
+  const int nblk = (int)((n_pos + NM_PLAN_PER_BLOCK - 1) / NM_PLAN_PER_BLOCK);
+  if ((rc = nm_reserve(h, &h->d_block_count, sizeof(int) * (size_t)nblk)) != NM_OK) return rc;
+  if ((rc = nm_reserve(h, &h->d_deep_rows, sizeof(int32_t) * (size_t)n_pos)) != NM_OK) return rc;
+  h->ev = h->ev_sets[1 + s];
+  h->h_sum = h->h_sums[1 + s];
+  h->err[0] = 0;
+  do {
+    cudaError_t e;
+    rc = NM_ERR_CUDA;
+    if ((e = cudaEventRecord(h->ev[0], st)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(h->d_sum, 0, sizeof(nm_summary), st)) != cudaSuccess) break;
+    nm_plan_count<<<nblk, NM_PLAN_THREADS, 0, st>>>(pl->off0, pl->off1, n_pos, prm.min_coverage, pl->seg,
+                                                    pl->n_seg > 0 ? pl->n_seg : 0, nullptr, (int*)h->d_block_count.p, h->d_sum);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    h->launches += 1;
+    if ((e = cudaEventRecord(h->ev[1], st)) != cudaSuccess) break;
+    if ((rc = nm_dense_enqueue(h, pl, prm, tb, h->dense_class, st, &pd->try_grid, &pd->n_launched)) != NM_OK) break;
+    rc = NM_ERR_CUDA;
+    if ((e = cudaEventRecord(h->ev_done[s], st)) != cudaSuccess) break;
+    rc = NM_OK;
+  } while (0);
+  h->ev = h->ev_sets[0];
+  h->h_sum = h->h_sums[0];
+  pd->head_fired = h->head.fired;
+  h->head.armed = 0;
+  h->head.fired = 0;
+  if (rc != NM_OK) {
+    if (rc == NM_ERR_CUDA && !h->err[0]) nm_fail(h, rc, "asynchronous launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+  }
+  pd->active = 1;
+  pd->pl = *pl; pd->prm = *params; pd->tb = *tb; pd->stream = cuda_stream;
+  *ticket_out = s;
+  h->async_next++;
+  return NM_OK;
+}
+
+extern "C" int nm_detect_finish(nm_handle* h, int ticket, int64_t* n_rows_out, int* head_fired_out) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (ticket < 0 || ticket > 1 || !h->pend[ticket].active || !n_rows_out)
+    return nm_fail(h, NM_ERR_BAD_ARG, "no asynchronous call behind ticket %d (or n_rows is NULL)", ticket);
+  nm_handle::nm_pending* pd = &h->pend[ticket];
+  pd->active = 0;
+  if (head_fired_out) *head_fired_out = 0;
+  if (pd->done) {
+    *n_rows_out = pd->n_rows;
+    if (head_fired_out) *head_fired_out = pd->head_fired;
+    return NM_OK;
+  }
+  NM_CUDA(h, cudaSetDevice(h->device));
+  NM_CUDA(h, cudaEventSynchronize(h->ev_done[ticket]));
+  nm_summary sum;
+  bool refused = false;
+  h->ev = h->ev_sets[1 + ticket];
+  h->h_sum = h->h_sums[1 + ticket];
+  const int rc = nm_dense_complete(h, pd->try_grid, pd->n_launched, &sum, &refused);
+  h->ev = h->ev_sets[0];
+  h->h_sum = h->h_sums[0];
+  if (rc != NM_OK) return rc;
+  if (!refused) {
+    h->dense_class = nm_lane_class(sum.max_lane_n);
+    h->last_path = 2;
+    *n_rows_out = pd->pl.n_pos;
+    if (head_fired_out) *head_fired_out = pd->head_fired;
+    return NM_OK;
+  }
+  // the shape was not the previous call's: the ordinary call, from its plan pass (behind whatever else is in
+  // flight on the stream); calls issued meanwhile on the same assumption are refused and re-run in their turn
+  h->dense_class = 0;
+  return nm_detect_device(h, &pd->pl, &pd->prm, &pd->tb, n_rows_out, pd->stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1559,8 +1730,12 @@ extern "C" int nm_rank_head_select_device(nm_handle* h, const double* key_comb, 
   }
   int launches = 0;
   static_assert(sizeof(nm_head_record) == sizeof(nm_head_row), "device and ABI head records must have one layout");
+  nm_head_peers_dev peers = h->next_peers;
+  peers.refused = nullptr;
+  h->next_peers.n = 0;
   const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want > 0 ? want : 1, cap, geo,
-                                                 h->d_rank.p, (nm_head_record*)records_dev, h->sm_count, &launches, st);
+                                                 h->d_rank.p, (nm_head_record*)records_dev, h->sm_count, &launches, st,
+                                                 peers.n > 0 ? &peers : nullptr);
   h->launches += launches;
   if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "head selection failed: %s", cudaGetErrorString(e));
   return NM_OK;
@@ -1590,7 +1765,76 @@ extern "C" int nm_arm_head_select(nm_handle* h, const double* key_comb, const do
   h->head.key[0] = key_comb; h->head.key[1] = key_ks; h->head.key[2] = key_u;
   h->head.n_rows = n_rows; h->head.reverse = reverse; h->head.want = want > 0 ? want : 1; h->head.cap = cap;
   h->head.records = (nm_head_record*)records_dev;
+  h->head.peers = h->next_peers;
+  h->head.peers.refused = &h->d_sum->dense_retry;
+  h->next_peers.n = 0;
   h->head.armed = 1;
+  return NM_OK;
+}
+
+// Peers of the next head selection (armed or direct; one shot): the selection kernels store the header and the
+// records into every base[p] as well -- the all-gather of a sharded run's heads, fused into their selection.
+extern "C" int nm_head_set_peers(nm_handle* h, const nm_head_peers* peers) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  memset(&h->next_peers, 0, sizeof(h->next_peers));
+  if (!peers) return NM_OK;
+  if (peers->n_peers < 0 || peers->n_peers > NM_MAX_PEERS)
+    return nm_fail(h, NM_ERR_BAD_ARG, "n_peers (%d) outside [0, %d]", peers->n_peers, NM_MAX_PEERS);
+  for (int p = 0; p < peers->n_peers; ++p) {
+    if (!peers->base[p]) return nm_fail(h, NM_ERR_BAD_ARG, "peer %d has a NULL buffer", p);
+    h->next_peers.base[p] = (nm_head_record*)peers->base[p];
+  }
+  h->next_peers.n = peers->n_peers;
+  h->next_peers.epoch = peers->epoch;
+  return NM_OK;
+}
+
+// Peer-visible device buffers (CUDA IPC): what nm_head_set_peers points at when the peers are other processes.
+extern "C" int nm_peer_alloc(nm_handle* h, int64_t bytes, void** dev_ptr_out, unsigned char* ipc_handle_out) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (bytes <= 0 || !dev_ptr_out || !ipc_handle_out) return nm_fail(h, NM_ERR_BAD_ARG, "nm_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == NM_IPC_HANDLE_BYTES, "IPC handle size");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  void* p = nullptr;
+  NM_CUDA(h, cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t hd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return nm_fail(h, NM_ERR_CUDA, "nm_peer_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle_out, &hd, sizeof(hd));
+  *dev_ptr_out = p;
+  return NM_OK;
+}
+extern "C" int nm_peer_open(nm_handle* h, const unsigned char* ipc_handle, void** dev_ptr_out) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!ipc_handle || !dev_ptr_out) return nm_fail(h, NM_ERR_BAD_ARG, "nm_peer_open: bad argument");
+  NM_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, sizeof(hd));
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return nm_fail(h, NM_ERR_CUDA, "nm_peer_open: %s", cudaGetErrorString(e));
+  }
+  *dev_ptr_out = p;
+  return NM_OK;
+}
+extern "C" int nm_peer_close(nm_handle* h, void* dev_ptr) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!dev_ptr) return NM_OK;
+  NM_CUDA(h, cudaSetDevice(h->device));
+  NM_CUDA(h, cudaIpcCloseMemHandle(dev_ptr));
+  return NM_OK;
+}
+extern "C" int nm_peer_free(nm_handle* h, void* dev_ptr) {
+  if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  if (!dev_ptr) return NM_OK;
+  NM_CUDA(h, cudaSetDevice(h->device));
+  NM_CUDA(h, cudaFree(dev_ptr));
   return NM_OK;
 }
 extern "C" int nm_head_fired(const nm_handle* h) { return h ? h->head.fired : 0; }

@@ -10,6 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "nm_device.cuh"
 #include "nm_rank.cuh"
@@ -250,7 +251,8 @@ __device__ void nm_head_search(const unsigned* hist, const unsigned* part, unsig
 
 // hist[NM_HEAD_BINS] = cut bin, hist[NM_HEAD_BINS + 1] = rows in bins <= cut, [+2] = compaction cursor (0)
 __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, unsigned want, unsigned cap, int fit_cap,
-                                                   nm_head_record* __restrict__ header, long long n) {
+                                                   nm_head_record* __restrict__ header, long long n,
+                                                   const nm_head_peers_dev peers) {
   __shared__ unsigned part[256];
   unsigned s = 0;
   for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
@@ -272,11 +274,13 @@ __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, 
     if (header) {  // entry 0 of the caller's record buffer
       nm_head_record hdr;
       hdr.row = cum <= cap ? cum : 0;
-      hdr.seg = hdr.pos = hdr.full_nbhd = hdr.pad = 0;
+      hdr.seg = hdr.pos = hdr.full_nbhd = 0;
+      hdr.pad = (peers.refused && *peers.refused) ? -1 : peers.epoch;
       hdr.key[0] = (unsigned long long)n;
       hdr.key[1] = (cum == (unsigned)n && cum <= cap) ? 1ull : 0ull;
       hdr.key[2] = (unsigned)cut;
       header[0] = hdr;
+      for (int p = 0; p < peers.n; ++p) peers.base[p][0] = hdr;
     }
   }
 }
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, 
 __global__ void __launch_bounds__(256)
 nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, int64_t n,
                 int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap,
-                const nm_head_geo geo) {
+                const nm_head_geo geo, const nm_head_peers_dev peers) {
   const unsigned cut = hist[NM_HEAD_BINS];
   if (cut == 0xffffffffu) return;
   for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < n; r += (int64_t)gridDim.x * 256) {
@@ -316,6 +320,7 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
           }
         }
         out[slot] = rec;
+        for (int p = 0; p < peers.n; ++p) peers.base[p][1 + slot] = rec;  // peer memory: the exchange itself
       }
     }
   }
@@ -328,7 +333,11 @@ size_t nm_head_scratch_bytes(int64_t cap) {
 }
 
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st) {
+                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st,
+                const nm_head_peers_dev* peers_in) {
+  nm_head_peers_dev peers;
+  memset(&peers, 0, sizeof(peers));
+  if (peers_in && records) peers = *peers_in;
   unsigned* hist = (unsigned*)scratch;
   nm_head_record* recs = records ? records + 1
                                  : (nm_head_record*)((unsigned char*)scratch + nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)));
@@ -343,8 +352,8 @@ int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8 * (int64_t)sm_count) blocks = 8 * (int64_t)sm_count;
   nm_head_hist<<<(unsigned)blocks, 256, 0, st>>>(k[0], n, reverse, hist);
-  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n), (unsigned)cap, records ? 1 : 0, records, (long long)n);
-  nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap, geo);
+  nm_head_cut<<<1, 256, 0, st>>>(hist, (unsigned)(want < n ? want : n), (unsigned)cap, records ? 1 : 0, records, (long long)n, peers);
+  nm_head_compact<<<(unsigned)blocks, 256, 0, st>>>(k[0], k[1], k[2], n, reverse, hist, recs, (unsigned)cap, geo, peers);
   *launches += 3;
   return (int)cudaGetLastError();
 }

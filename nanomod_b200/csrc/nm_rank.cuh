@@ -44,9 +44,21 @@ struct nm_head_geo {
   int64_t n_rows_total;
   int nearby;
 };
+// optional peers of the selection (a sharded run): the header and every record are ALSO stored, by the
+// same kernels, into each peer's gathered-heads buffer (peer-mapped device memory over NVLink; base[p] is
+// this rank's section there) -- the all-gather of the heads is fused into their selection.  The header's pad
+// word carries `epoch` (which step's heads these are), or -1 when *refused is non-zero (the detect call the
+// selection was armed for did not compute: nm_summary::dense_retry).
+#define NM_MAX_PEERS 16
+struct nm_head_peers_dev {
+  int n, epoch;
+  nm_head_record* base[NM_MAX_PEERS];
+  const int* refused;
+};
 size_t nm_head_scratch_bytes(int64_t cap);
 // records == NULL: the records follow the histogram block inside scratch.  Otherwise records[0] becomes
 // a header (row = rows selected, key[0] = n, key[1] = 1 when the head holds every row, key[2] = cut bin)
 // and records[1 .. cap] the selection; the cut is lowered to the bins that fit `cap` records.
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
-                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st);
+                const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st,
+                const nm_head_peers_dev* peers = nullptr);

@@ -593,7 +593,7 @@ class Detector:
         self.handle.pack_records_device(tb, row_lo, n, which, records.data_ptr(), stream)
 
     def detect_device(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
-                      stream: Optional[int] = None) -> int:
+                      stream: Optional[int] = None, _async: bool = False) -> int:
         """Device-resident call.  ``out`` maps column name -> torch CUDA tensor with capacity
         n_pos (see ``alloc_device_table``).  Returns n_rows; results are complete on return."""
         import torch
@@ -611,7 +611,21 @@ class Detector:
                             int(dev.i16_total1) if i16 else 0)
         if stream is None:
             stream = torch.cuda.current_stream(dev.off0.device).cuda_stream
+        if _async:
+            return self.handle.detect_device_async(pl, options.to_params(), tb, stream)
         return self.handle.detect_device(pl, options.to_params(), tb, stream)
+
+    def detect_device_async(self, dev: "DevicePileup", options: DetectOptions, out: Dict[str, "object"],
+                            stream: Optional[int] = None) -> int:
+        """``detect_device`` without the host wait (nm_detect_device_async): queues the call and returns a ticket
+        for ``detect_finish``.  Up to two calls may be in flight, writing different ``out`` tables; ``dev`` and
+        ``out`` must stay alive and untouched until the call is finished."""
+        return self.detect_device(dev, options, out, stream, _async=True)
+
+    def detect_finish(self, ticket: int):
+        """Waits for the call behind ``ticket`` (re-running it if the device refused the assumed shape);
+        returns (n_rows, head_fired)."""
+        return self.handle.detect_finish(ticket)
 
 
 @dataclass

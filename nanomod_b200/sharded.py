@@ -128,6 +128,64 @@ def gather_tables(local: SignTestTable, group=None, device=None) -> Optional[Sig
     return unpack_records(np.concatenate(parts, axis=0), local)
 
 
+class _DevView:
+    """a device address as a torch uint8 tensor (zero copy, through __cuda_array_interface__)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class HeadExchange:
+    """Gathered-heads buffers in peer-visible HBM: every rank owns one buffer of two slots x world
+    sections of (cap + 1) records, and maps every peer's buffer (nm_peer_alloc / nm_peer_open, CUDA
+    IPC between the one-process-per-GPU ranks of a node).  A rank's head selection stores its
+    records straight into its section of EVERY rank's buffer (nm_head_set_peers), so the exchange
+    needs no collective kernel.  Building one is collective over the group."""
+
+    def __init__(self, handle, group, cap: int, device):
+        import torch
+        import torch.distributed as dist
+        self.handle, self.group, self.cap, self.device = handle, group, cap, device
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.section = (cap + 1) * HEAD_REC.itemsize
+        self.slot_bytes = self.world * self.section
+        self.ptr, ipc = handle.peer_alloc(2 * self.slot_bytes)
+        self.peer_ptrs = [self.ptr] * self.world
+        self.ok = True
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, ipc, group=group)
+            opened = []
+            try:
+                for r in range(self.world):
+                    if r != self.rank:
+                        self.peer_ptrs[r] = handle.peer_open(handles[r])
+                        opened.append(self.peer_ptrs[r])
+            except Exception:  # no peer mapping on this node: every rank falls back to the NCCL all-gather
+                self.ok = False
+            flag = torch.tensor([1 if self.ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            self.ok = bool(int(flag.item()))
+            self._opened = opened
+        self._local = torch.as_tensor(_DevView(self.ptr, 2 * self.slot_bytes), device=device)
+
+    def bases(self, slot: int) -> List[int]:
+        """this rank's section of slot ``slot`` in every rank's buffer"""
+        off = (slot & 1) * self.slot_bytes + self.rank * self.section
+        return [p + off for p in self.peer_ptrs]
+
+    def gathered(self, slot: int):
+        """this rank's copy of all sections of a slot (a view: valid once every rank's kernels are done)"""
+        lo = (slot & 1) * self.slot_bytes
+        return self._local[lo:lo + self.slot_bytes]
+
+    def epochs(self, slot: int) -> np.ndarray:
+        """the header epoch of every section of a slot, as it is on the device now"""
+        hdr = self.gathered(slot).view(self.world, self.section)[:, :HEAD_REC.itemsize].contiguous().cpu().numpy()
+        return hdr.view(HEAD_REC)["reserved"].reshape(-1).astype(np.int64)
+
+
 class ShardedDetector:
     """Runs the detection stage on this rank's shard and gathers the table on rank 0.
 
@@ -180,25 +238,38 @@ class ShardedDetector:
             self._head_mine = [torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
             self._head_all = [torch.zeros(world * (cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device=dev) for _ in range(2)]
 
-    def detect_shard(self, dev, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
-                     out: Optional[Dict[str, "object"]] = None, head_want: int = 0, head_cap: int = HEAD_CAP,
-                     slot: int = 0) -> ShardResult:
-        """Detection on a device-resident shard (``dev`` = core candidates [core_lo, core_hi) plus
-        halo).  Results stay on the GPU; no communication.  With ``head_want`` the selection of this
-        rank's ranking head (what ``gather_heads`` exchanges) is armed for the call: it is launched behind
-        the call's own kernels and before its host wait -- when the coverage filter drops nothing, which is
-        what the row range was armed for (``ShardResult.head_slot``; otherwise ``gather_heads`` selects)."""
+    def peer_exchange(self, cap: int, device):
+        """The peer-memory head exchange of this group (built on first use -- collectively: every rank must
+        make its first head-selecting call at the same point).  None when the engine has no device handle;
+        ``.ok`` False when the node offers no peer mapping (the NCCL all-gather of ``gather_heads`` is used)."""
+        handle = getattr(self.engine, "handle", None)
+        if handle is None or not hasattr(handle, "peer_alloc"):
+            return None
+        x = getattr(self, "_xchg", None)
+        if x is None or x.cap != cap:
+            x = self._xchg = HeadExchange(handle, self.group, cap, device)
+            self._epoch = 0
+        return x
+
+    def _arm_head(self, dev, out, core_lo: int, core_hi: int, options: DetectOptions, head_want: int, head_cap: int,
+                  slot: int, peer: bool):
+        """arms the head selection for the next detect call; returns the epoch of a peer-memory exchange (or 0)"""
+        world, _ = self._world()
+        self._head_buffers(dev.pos.device, head_cap, world)
+        epoch = 0
+        if peer:
+            x = self.peer_exchange(head_cap, dev.pos.device)
+            if x is not None and x.ok:
+                self._epoch += 1
+                epoch = self._epoch
+                self.engine.handle.head_set_peers(x.bases(slot), epoch)
+        self.engine.arm_head_select(out, core_lo, core_hi - core_lo, options, head_want, self._head_mine[slot & 1], head_cap,
+                                    (None, dev.pos, dev.seg, core_lo, dev.n_pos, nearby_rows(options)))
+        return epoch
+
+    def _shard_result(self, dev, out, n_rows: int, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
+                      fired: bool, slot: int, head_want: int, head_cap: int, epoch: int) -> "ShardResult":
         import torch
-        from .detect import alloc_device_table
-        if out is None:
-            out = alloc_device_table(options, dev.n_pos, dev.off0.device)
-        if head_want > 0 and core_hi > core_lo:
-            world, _ = self._world()
-            self._head_buffers(dev.pos.device, head_cap, world)
-            self.engine.arm_head_select(out, core_lo, core_hi - core_lo, options, head_want, self._head_mine[slot & 1], head_cap,
-                                        (None, dev.pos, dev.seg, core_lo, dev.n_pos, nearby_rows(options)))
-        n_rows = self.engine.detect_device(dev, options, out)
-        fired = head_want > 0 and self.engine.handle.head_fired()
         if n_rows == dev.n_pos:  # nothing filtered: rows are the candidates
             r_lo, r_hi = core_lo, core_hi
         else:
@@ -207,7 +278,47 @@ class ShardedDetector:
             r_lo, r_hi = int(edges[0].item()), int(edges[1].item())
         res = ShardResult(out, dev, n_rows, r_lo, r_hi, cand_lo, options)
         res.head_slot = (slot & 1, head_want, head_cap) if fired else None
+        res.head_epoch = epoch  # > 0: a peer-memory exchange was armed under this epoch (stored iff head_slot)
         return res
+
+    def detect_shard(self, dev, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
+                     out: Optional[Dict[str, "object"]] = None, head_want: int = 0, head_cap: int = HEAD_CAP,
+                     slot: int = 0, peer: bool = False) -> ShardResult:
+        """Detection on a device-resident shard (``dev`` = core candidates [core_lo, core_hi) plus
+        halo).  Results stay on the GPU; no communication.  With ``head_want`` the selection of this
+        rank's ranking head (what ``gather_heads`` exchanges) is armed for the call: it is launched behind
+        the call's own kernels and before its host wait -- when the coverage filter drops nothing, which is
+        what the row range was armed for (``ShardResult.head_slot``; otherwise ``gather_heads`` selects).
+        ``peer=True``: the armed selection also stores the head into every rank's gathered-heads buffer
+        (``HeadExchange``), i.e. the exchange itself happens inside the selection kernels."""
+        from .detect import alloc_device_table
+        if out is None:
+            out = alloc_device_table(options, dev.n_pos, dev.off0.device)
+        epoch = 0
+        if head_want > 0 and core_hi > core_lo:
+            epoch = self._arm_head(dev, out, core_lo, core_hi, options, head_want, head_cap, slot, peer)
+        n_rows = self.engine.detect_device(dev, options, out)
+        fired = head_want > 0 and self.engine.handle.head_fired()
+        return self._shard_result(dev, out, n_rows, core_lo, core_hi, cand_lo, options, fired, slot, head_want, head_cap, epoch)
+
+    def detect_shard_async(self, dev, core_lo: int, core_hi: int, cand_lo: int, options: DetectOptions,
+                           out: Dict[str, "object"], head_want: int = 0, head_cap: int = HEAD_CAP, slot: int = 0,
+                           peer: bool = True):
+        """``detect_shard`` without the host wait (nm_detect_device_async): the step is queued and a pending
+        record returned for ``finish_shard``.  Up to two steps may be in flight, on different ``out`` tables and
+        ``slot`` values; a caller that keeps one step queued ahead never leaves the GPU idle between steps."""
+        epoch = 0
+        if head_want > 0 and core_hi > core_lo:
+            epoch = self._arm_head(dev, out, core_lo, core_hi, options, head_want, head_cap, slot, peer)
+        ticket = self.engine.detect_device_async(dev, options, out)
+        return (ticket, dev, out, core_lo, core_hi, cand_lo, options, slot, head_want, head_cap, epoch)
+
+    def finish_shard(self, pending) -> ShardResult:
+        """Completes a step queued by ``detect_shard_async`` (waits for that step only)."""
+        ticket, dev, out, core_lo, core_hi, cand_lo, options, slot, head_want, head_cap, epoch = pending
+        n_rows, fired = self.engine.detect_finish(ticket)
+        return self._shard_result(dev, out, n_rows, core_lo, core_hi, cand_lo, options, fired and head_want > 0, slot,
+                                  head_want, head_cap, epoch)
 
     def local_head(self, res: ShardResult, want: int) -> LocalHead:
         """Leading rows of this rank's own ranking of its core rows (nm_rank_head_device: three
@@ -221,27 +332,58 @@ class ShardedDetector:
         return LocalHead(rows["row"].astype(np.int64), rows["seg"].astype(np.int32), rows["pos"].astype(np.int32),
                          np.ascontiguousarray(rows["key"]), rows["full_nbhd"] != 0, res.n_core, len(rows) == res.n_core)
 
-    def gather_heads(self, res: ShardResult, want: int, cap: int = HEAD_CAP, slot: int = 0, async_op: bool = False):
-        """The multi-GPU exchange of a step, all on the device and without a host wait: three
-        streaming kernels select the head of this rank's ranking into a record buffer
-        (nm_rank_head_select_device) and ONE NCCL all-gather hands every rank all heads.  Returns the
-        gathered records as a CUDA tensor; ``heads_from_gathered`` parses it when the ranking is needed.
-        ``async_op=True`` returns (tensor, work): the collective then runs beside whatever the caller
-        launches next (``slot`` selects one of two buffer pairs, so a step can overlap the exchange of
-        the previous one); ``work.wait()`` before the tensor is read."""
+    def gather_heads(self, res: ShardResult, want: int, cap: int = HEAD_CAP, slot: int = 0, async_op: bool = False,
+                     peer: bool = False):
+        """The multi-GPU exchange of a step, all on the device: three streaming kernels select the head of
+        this rank's ranking into a record buffer (nm_rank_head_select_device) -- unless the detect call has
+        done so already (``detect_shard(head_want=...)``) -- and every rank gets all heads.
+
+        ``peer=False``: ONE NCCL all-gather.  Returns the gathered records as a CUDA tensor;
+        ``heads_from_gathered`` parses it.  ``async_op=True`` returns (tensor, work): the collective runs
+        beside whatever the caller launches next (``slot`` selects one of two buffer pairs);
+        ``work.wait()`` before the tensor is read.
+
+        ``peer=True`` (falls back to the above when the node has no peer mapping): the selection kernels
+        store the head into every rank's buffer themselves (``HeadExchange``), no collective kernel runs.
+        The call then waits for its own kernels, meets the other ranks at a barrier -- after which every
+        head has arrived -- and returns a copy of the gathered records; with ``async_op=True`` it returns
+        (view, None) at once and establishing completion (device synchronisation + barrier) is the caller's."""
         import torch
         import torch.distributed as dist
         o = res.options
         world, _ = self._world()
         dev = res.dev.pos.device
         self._head_buffers(dev, cap, world)
+        x = self.peer_exchange(cap, dev) if peer else None
+        use_peer = x is not None and x.ok
         mine, allv = self._head_mine[slot & 1], self._head_all[slot & 1]
-        if getattr(res, "head_slot", None) != (slot & 1, want, cap):  # not selected by the detect call itself
+        selected = getattr(res, "head_slot", None) == (slot & 1, want, cap)
+        epoch = getattr(res, "head_epoch", 0)
+        if use_peer and not (selected and epoch > 0):
+            selected = False
+            if epoch <= 0:  # every rank draws the same number: calls are collective
+                self._epoch += 1
+                epoch = res.head_epoch = self._epoch
+            self.engine.handle.head_set_peers(x.bases(slot), epoch)
+        if not selected:  # not selected by the detect call itself
             core = {c: res.out[c][res.r_lo:res.r_hi] for c in ("ks_p", "ks_d", "u_p", "u_stat", "fisher_p", "fisher_stat",
                                                                "stouffer_p", "stouffer_stat") if c in res.out}
             rpi = None if res.n_rows == res.dev.n_pos else res.out["row_pos_index"]
             self.engine.rank_head_select_device(core, res.n_core, o, want, mine, cap,
                                                 geometry=(rpi, res.dev.pos, res.dev.seg, res.r_lo, res.n_rows, nearby_rows(o)))
+            if use_peer:
+                res.head_slot = (slot & 1, want, cap)
+        if use_peer:
+            if async_op:
+                return x.gathered(slot), None
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier(group=self.group)
+            got = x.gathered(slot).clone()
+            ep = x.epochs(slot)
+            if not np.all(ep == epoch):
+                raise RuntimeError("head exchange: sections carry epochs %s, expected %d" % (ep.tolist(), epoch))
+            return got
         if world == 1:
             return (mine, None) if async_op else mine
         work = dist.all_gather_into_tensor(allv, mine, group=self.group, async_op=async_op)
@@ -521,6 +663,7 @@ class ShardResult:
     cand_lo: int           # global candidate index of the shard's first candidate
     options: DetectOptions
     head_slot: Optional[tuple] = None  # (slot, want, cap) when the detect call itself selected the ranking head
+    head_epoch: int = 0                # epoch of the peer-memory exchange armed with it (0: none)
 
     @property
     def n_core(self) -> int:

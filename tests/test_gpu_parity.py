@@ -756,6 +756,126 @@ def test_head_selection_armed_for_the_detect_call(det, drop):
         assert a.tobytes() == b.tobytes()
 
 
+def _table_bytes(out, n):
+    return {c: out[c][:n].cpu().numpy().tobytes() for c in out if out[c].dim() == 1}
+
+
+def test_queued_calls_equal_synchronous_calls(det):
+    """nm_detect_device_async / nm_detect_finish: two calls in flight on the assumed (dense) shape give the
+    tables of the synchronous call; a call whose shape is not the previous one's is refused on the device and
+    re-run by finish; calls that are not dense at all run synchronously behind the same interface."""
+    import torch
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False, SaveTest=0)
+    pa = nm.synthetic_pileup(30000, 100, 100, round_decimals=3, seed=21)
+    pb = nm.synthetic_pileup(30000, 100, 100, round_decimals=3, seed=22)
+    pc = nm.synthetic_pileup(30000, 40, 44, round_decimals=3, seed=23)            # dense, another network class
+    pd = nm.synthetic_pileup(30000, 100, 100, drop_frac1=0.01, round_decimals=3, seed=24)  # filtered rows: general path
+    devs = [nm.DevicePileup.from_host(p, "cuda:0") for p in (pa, pb, pc, pd)]
+    want = []
+    for d in devs:
+        o = nm.alloc_device_table(opt, d.n_pos, "cuda:0")
+        n = det.detect_device(d, opt, o)
+        want.append((n, _table_bytes(o, n)))
+    det.detect_device(devs[0], opt, nm.alloc_device_table(opt, devs[0].n_pos, "cuda:0"))  # establishes the dense shape
+    outs = [nm.alloc_device_table(opt, 30000, "cuda:0") for _ in range(2)]
+    order = [0, 1, 0, 2, 2, 0, 3, 1, 1, 0]
+    paths = []
+    pend = []
+    for k, i in enumerate(order):
+        pend.append((i, k & 1, det.detect_device_async(devs[i], opt, outs[k & 1])))
+        if len(pend) > 1:
+            i0, b0, t0 = pend.pop(0)
+            n, _ = det.detect_finish(t0)
+            paths.append(det.handle.last_path())
+            assert n == want[i0][0]
+            assert _table_bytes(outs[b0], n) == want[i0][1], "queued call %d differs from the synchronous call" % i0
+    i0, b0, t0 = pend.pop(0)
+    n, _ = det.detect_finish(t0)
+    assert n == want[i0][0] and _table_bytes(outs[b0], n) == want[i0][1]
+    assert 2 in paths, "no call was launched on the assumed shape"
+    # a third call in flight, and two calls writing one table, are refused
+    t1 = det.detect_device_async(devs[0], opt, outs[0])
+    with pytest.raises(nm.NmError):
+        det.detect_device_async(devs[1], opt, outs[0])
+    t2 = det.detect_device_async(devs[1], opt, outs[1])
+    with pytest.raises(nm.NmError):
+        det.detect_device_async(devs[0], opt, nm.alloc_device_table(opt, 30000, "cuda:0"))
+    assert det.detect_finish(t1)[0] == 30000 and det.detect_finish(t2)[0] == 30000
+    with pytest.raises(nm.NmError):
+        det.detect_finish(t1)
+
+
+@pytest.mark.parametrize("drop", [0.0, 0.01])
+def test_head_selection_stores_into_peer_buffers(det, drop):
+    """nm_head_set_peers: the selection kernels store the header (with the epoch) and every record into each
+    peer section as well -- here two sections in this GPU's own memory stand in for two ranks' buffers.  Through
+    ShardedDetector (world 1): the armed, queued and after-the-call selections all land in the exchange buffer."""
+    import torch
+    from nanomod_b200.sharded import HEAD_REC, shard_halo, shard_with_halo
+    p = nm.synthetic_pileup(20000, 70, 66, drop_frac1=drop, round_decimals=3, seed=12)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False, SaveTest=0)
+    sd = ShardedDetector(det)
+    lo, hi = 4000, 16000
+    sl, core_lo, core_hi = shard_with_halo(p, lo, hi, shard_halo(opt))
+    dev = nm.DevicePileup.from_host(sl, "cuda:0")
+    cap, want = 1024, 300
+    plain = sd.detect_shard(dev, core_lo, core_hi, lo - core_lo, opt)
+    ref = sd.gather_heads(plain, want, cap=cap).cpu().numpy().view(HEAD_REC).copy()
+    n = int(ref[0]["row"])
+    assert n >= want
+
+    def same(buf, epoch):
+        b = buf.cpu().numpy().view(HEAD_REC)
+        assert int(b[0]["row"]) == n and int(b[0]["reserved"]) == epoch
+        assert b[0]["key"].tobytes() == ref[0]["key"].tobytes()
+        assert np.sort(b[1:n + 1], order=["row"]).tobytes() == np.sort(ref[1:n + 1], order=["row"]).tobytes()
+
+    # C ABI: two peer sections
+    peers = [torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+    mine = torch.zeros((cap + 1) * HEAD_REC.itemsize, dtype=torch.uint8, device="cuda:0")
+    det.handle.head_set_peers([t.data_ptr() for t in peers], 7)
+    core = {c: plain.out[c][plain.r_lo:plain.r_hi] for c in ("ks_p", "stouffer_p")}
+    rpi = None if plain.n_rows == dev.n_pos else plain.out["row_pos_index"]
+    from nanomod_b200.sharded import nearby_rows
+    det.rank_head_select_device(core, plain.n_core, opt, want, mine, cap,
+                                geometry=(rpi, dev.pos, dev.seg, plain.r_lo, plain.n_rows, nearby_rows(opt)))
+    torch.cuda.synchronize()
+    same(mine, 7)
+    for t in peers:
+        same(t, 7)
+    # one shot: the next selection stores nowhere else
+    for t in peers:
+        t.zero_()
+    det.rank_head_select_device(core, plain.n_core, opt, want, mine, cap,
+                                geometry=(rpi, dev.pos, dev.seg, plain.r_lo, plain.n_rows, nearby_rows(opt)))
+    torch.cuda.synchronize()
+    assert all(int(t.sum().item()) == 0 for t in peers)
+    # product path at world size 1
+    res = sd.detect_shard(dev, core_lo, core_hi, lo - core_lo, opt, head_want=want, head_cap=cap, slot=0, peer=True)
+    assert (res.head_slot is not None) == (drop == 0.0) and res.head_epoch > 0
+    same(sd.gather_heads(res, want, cap=cap, slot=0, peer=True), res.head_epoch)
+    outs = [nm.alloc_device_table(opt, dev.n_pos, "cuda:0") for _ in range(2)]
+    pend = [sd.detect_shard_async(dev, core_lo, core_hi, lo - core_lo, opt, outs[k], head_want=want, head_cap=cap, slot=k,
+                                  peer=True) for k in range(2)]
+    for k in range(2):
+        r = sd.finish_shard(pend[k])
+        assert r.n_rows == plain.n_rows
+        same(sd.gather_heads(r, want, cap=cap, slot=k, peer=True), r.head_epoch)
+
+
+def test_peer_buffer_alloc_and_view(det):
+    import torch
+    from nanomod_b200.sharded import _DevView
+    ptr, ipc = det.handle.peer_alloc(4096)
+    assert ptr != 0 and len(ipc) == 64
+    t = torch.as_tensor(_DevView(ptr, 4096), device="cuda:0")
+    assert int(t.sum().item()) == 0
+    t[:16] = 3
+    assert int(torch.as_tensor(_DevView(ptr, 4096), device="cuda:0").sum().item()) == 48
+    del t
+    det.handle.peer_free(ptr)
+
+
 # ---------------------------------------------------------------------------------------------
 # pipelined host entry (slabs with halos, copies overlapped with compute) == the one-piece call
 # ---------------------------------------------------------------------------------------------

@@ -53,6 +53,68 @@ def small(det, rank, world):
     return int(flag.item()) == 0
 
 
+def peer_exchange(det, rank, world):
+    """The peer-memory head exchange (selection kernels storing into every rank's buffer over NVLink) against
+    the NCCL all-gather of the same heads: dense shards (armed selection, synchronous and queued steps) and
+    shards with filtered rows (selection after the call)."""
+    from nanomod_b200.sharded import HEAD_REC
+    device = torch.device("cuda", torch.cuda.current_device())
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False, SaveTest=0)
+    sd = ShardedDetector(det)
+    cap, want = 2048, 300
+    x = sd.peer_exchange(cap, device)
+    if x is None or not x.ok:
+        if rank == 0:
+            print("multi_gpu_check peer world=%d SKIPPED: no peer mapping on this node" % world)
+        return True
+
+    def sections(buf):
+        a = buf.cpu().numpy().view(HEAD_REC).reshape(world, cap + 1).copy()
+        out = []
+        for r in range(world):
+            k = int(a[r, 0]["row"])
+            hdr = a[r, 0].copy()
+            hdr["reserved"] = 0
+            out.append((hdr.tobytes(), np.sort(a[r, 1:k + 1], order=["row"]).tobytes()))
+        return out
+
+    bad = 0
+    for drop in (0.0, 0.01):
+        p = nm.synthetic_pileup(120_000, 70, 66, drop_frac1=drop, round_decimals=3, seed=5)
+        dev, core_lo, core_hi, cand_lo = sd.shard_device(p, opt, device)
+        outs = [nm.alloc_device_table(opt, dev.n_pos, device) for _ in range(2)]
+        res = sd.detect_shard(dev, core_lo, core_hi, cand_lo, opt, outs[0])
+        ref = sections(sd.gather_heads(res, want, cap=cap))                      # NCCL all-gather
+        res = sd.detect_shard(dev, core_lo, core_hi, cand_lo, opt, outs[0], head_want=want, head_cap=cap, slot=0, peer=True)
+        got = sections(sd.gather_heads(res, want, cap=cap, slot=0, peer=True))   # peer stores + barrier
+        bad += 0 if got == ref else 1
+        # queued steps: two in flight, then completion established by device synchronisation + barrier
+        pend = []
+        last = None
+        for k in range(5):
+            pend.append(sd.detect_shard_async(dev, core_lo, core_hi, cand_lo, opt, outs[k & 1], head_want=want, head_cap=cap,
+                                              slot=k & 1, peer=True))
+            if len(pend) > 1:
+                last = sd.finish_shard(pend.pop(0))
+                if last.head_slot is None:
+                    sd.gather_heads(last, want, cap=cap, slot=(k - 1) & 1, async_op=True, peer=True)
+        last = sd.finish_shard(pend.pop(0))
+        if last.head_slot is None:
+            sd.gather_heads(last, want, cap=cap, slot=0, async_op=True, peer=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ep = x.epochs(0)
+        bad += 0 if np.all(ep == last.head_epoch) else 1
+        bad += 0 if sections(x.gathered(0).clone()) == ref else 1
+        dist.barrier()
+    flag = torch.tensor([bad], device="cuda")
+    dist.all_reduce(flag)
+    ok = int(flag.item()) == 0
+    if rank == 0:
+        print("multi_gpu_check peer world=%d peer_exchange_identical_to_nccl_all_gather=%s" % (world, ok))
+    return ok
+
+
 def chr20(det, rank, world, steps=10):
     from bench import make_device_workload
     device = torch.device("cuda", torch.cuda.current_device())
@@ -116,6 +178,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     det = nm.Detector(lr)
     ok = small(det, rank, world)
+    ok &= peer_exchange(det, rank, world)
     if "--chr20" in sys.argv:
         ok &= chr20(det, rank, world)
     dist.barrier()
