@@ -397,7 +397,13 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpus = None
     if world > 1:
+        # one process per GPU: stay on the CPUs (and so the host memory) of the GPU's own NUMA node
+        from nanomod_b200.sharded import bind_to_gpu_cpus
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[local_rank]) if visible and visible.replace(",", "").isdigit() else local_rank
+        cpus = bind_to_gpu_cpus(phys)
         dist.init_process_group("nccl", device_id=device)
     det = nm.Detector(local_rank)
     sd = ShardedDetector(det)
@@ -646,6 +652,7 @@ def run_gpu_arm(args):
             heads = sd.heads_from_gathered(gathered[0], opt, HEAD_CAP)
             line["head_rows_exchanged"] = [int(h.rows.shape[0]) for h in heads]
             line["head_exchange"] = exchange
+            line["rank0_cpu_affinity"] = ("%d CPUs of the GPU's NUMA node" % len(cpus)) if cpus else "unchanged"
         if variants is not None:
             line["variants"] = variants
         if e2e_i16 is not None:

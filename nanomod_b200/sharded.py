@@ -128,6 +128,30 @@ def gather_tables(local: SignTestTable, group=None, device=None) -> Optional[Sig
     return unpack_records(np.concatenate(parts, axis=0), local)
 
 
+def bind_to_gpu_cpus(device_index: int) -> Optional[List[int]]:
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off (NVML's ideal CPU
+    affinity).  One process per GPU on a multi-socket host: pinned staging buffers allocated afterwards
+    are first-touched on that node, so the host<->device copies of the ranks do not all cross one
+    socket's memory controller.  Returns the CPU list, or None when NVML / the platform does not
+    offer it (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class _DevView:
     """a device address as a torch uint8 tensor (zero copy, through __cuda_array_interface__)"""
 
