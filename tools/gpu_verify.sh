@@ -1,8 +1,8 @@
 #!/bin/bash
-# The full single-GPU check run under gpurun: GPU tests, smoke, bench (both arms), memcheck over the
-# newer paths, ncu launch list and --set full captures of the dominant kernels -> gpurun_out/final2/
+# The single-GPU check run under gpurun: GPU tests, smoke, bench (both arms), memcheck over the newest paths,
+# ncu launch list and a --set full capture of the dominant kernel -> gpurun_out/final3/
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-O=gpurun_out/final2; mkdir -p $O
+O=gpurun_out/final3; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/gpu.txt
 echo "== pytest gpu"; timeout 2400 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider --durations=8 > $O/pytest_gpu.log 2>&1; echo "rc=$?"; tail -14 $O/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
@@ -18,10 +18,10 @@ for k,v in d["variants"].items():
     if "kernel_ms" in v: print(k, "%.3f ms"%v["ms_per_step"], {a: round(b,3) for a,b in v["kernel_ms"].items()}, "frac %.3f path %d"%(v["tests_kernel_frac_of_hbm_peak"], v["path"]))
     else: print(k, {a: v[a] for a in ("value","ms_per_step","pcie_GBps")})
 PY
-echo "== memcheck"; timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -q -p no:cacheprovider -k "dense or speculative or cfg1_variants or bad_offsets or ranking_head or pipelined or int16 or beyond_the_shared or sharded_device or deep or golden" > $O/memcheck.log 2>&1; echo "rc=$?"; tail -4 $O/memcheck.log
-echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-variants > $O/ncu_launch.log 2>&1; echo "rc=$?"
-echo "== ncu full (lane)"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:nm_lane_dense_kernel -s 3 -c 1 -f -o $O/prof_lane python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-variants > $O/ncu_full.log 2>&1; echo "rc=$?"
-echo "== ncu full (plan, combine)"; timeout 600 ncu --set full --clock-control none -k regex:nm_combine_kernel\|nm_plan_count -s 6 -c 2 -f -o $O/prof_small python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-variants > $O/ncu_small.log 2>&1; echo "rc=$?"
-echo "== ncu full (deep, cfg5)"; timeout 900 ncu --set full --clock-control none -k regex:nm_deep_kernel -s 2 -c 1 -f -o $O/prof_deep python tools/bench_configs.py cfg5 > $O/ncu_deep.log 2>&1; echo "rc=$?"
-echo "== ncu full (all tests: lane with U and t, tails)"; timeout 900 ncu --set full --clock-control none -k regex:nm_lane_dense_kernel\|nm_tails_kernel -s 6 -c 2 -f -o $O/prof_cfg3 python tools/bench_configs.py cfg3 > $O/ncu_cfg3.log 2>&1; echo "rc=$?"
+echo "== memcheck (queued calls, peer stores, armed selection)"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "queued or peer or armed or sharded_device" > $O/memcheck.log 2>&1; echo "rc=$?"; tail -4 $O/memcheck.log
+echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-variants > $O/ncu_launch.log 2>&1; echo "rc=$?"
+echo "== ncu full (lane)"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:nm_lane_grid_kernel -s 3 -c 1 -f -o $O/prof_lane python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-variants > $O/ncu_full.log 2>&1; echo "rc=$?"
+python tools/summarize_profile.py launches $O/launches.csv > $O/launches.md 2>&1
+python tools/summarize_profile.py full $O/prof_lane.ncu-rep > $O/prof_lane.md 2>&1
 ls -la $O
+exit 0
