@@ -57,10 +57,12 @@ HEAD_CAP = 4096            # record capacity of the exchange buffer (48-byte rec
 SM_RESERVE = 2             # SMs the persistent lane kernel leaves to NCCL's copy kernel at N > 1
 
 
-def workload_config(n_gpus: int):
-    return {"workload": "E. coli K-12 scale synthetic pileup, %d positions/GPU, 2x%dx, KS + weighted "
-                        "Stouffer window +-%d" % (GENOME, COV, NB),
-            "positions_per_gpu": GENOME, "coverage": [COV, COV], "neighborPvalues": NB, "WeightsDif": WEIGHTS_DIF,
+def workload_config(n_gpus: int, positions: int = GENOME):
+    return {"workload": ("E. coli K-12 scale synthetic pileup, %d positions/GPU, 2x%dx, KS + weighted Stouffer window +-%d"
+                         if positions == GENOME and COV == 100 else
+                         "synthetic pileup (non-default size: --positions / --coverage), %d positions/GPU, 2x%dx, KS + weighted "
+                         "Stouffer window +-%d") % (positions, COV, NB),
+            "positions_per_gpu": positions, "coverage": [COV, COV], "neighborPvalues": NB, "WeightsDif": WEIGHTS_DIF,
             "MinCoverage": MIN_COV, "testMethod": "stouffer",
             "tests": "KS test + weighted Stouffer combination per position (want_u = want_t = 0: the Mann-Whitney U "
                      "and Welch t columns of the reference's table are NOT computed in this configuration; "
@@ -79,7 +81,7 @@ def workload_config(n_gpus: int):
                             "the gathered heads into the global ranking is host-side ranking work and, like all ranking at N = 1, not "
                             "part of the timed step; every exchange completes inside the timed region" % (n_gpus, HEAD_WANT)),
             "queue": "steps are issued through nm_detect_device_async, the host one step ahead of the device (two result tables alternate)",
-            "l2": "inputs (3.7 GB/GPU) are larger than the 126 MB L2; no explicit flush"}
+            "l2": "inputs (%.1f GB/GPU) are larger than the 126 MB L2; no explicit flush" % (positions * 2 * COV * 4 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -630,7 +632,7 @@ def run_gpu_arm(args):
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": ("u16 keys (exact images of the float32 inputs, checked on the device), i32 ranks, f64 tails"
                           if kernel == "nm_lane_grid_kernel" else "f32 keys, i32 ranks, f64 tails"),
-                "data": "synthetic", "config": workload_config(world),
+                "data": "synthetic", "config": workload_config(world, L),
                 "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])) if cap else None,
@@ -669,12 +671,16 @@ def run_gpu_arm(args):
 
 
 def main():
+    global GRID, COV, BYTES_PER_POS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--positions", type=int, default=GENOME, help="positions per GPU (default: E. coli scale)")
+    ap.add_argument("--coverage", type=int, default=COV,
+                    help="reads per group and position (default 100; 30 with --positions 64444167/N is BASELINE configs[3] "
+                         "split over N GPUs: the strong-scaling experiment of profiles/round2_cfg4_strong_scaling.json)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
@@ -686,8 +692,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=40000)
     args = ap.parse_args()
-    global GRID
     GRID = not args.off_grid
+    COV = args.coverage
+    BYTES_PER_POS = 4 * (COV + COV) + 16 + 28
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

@@ -286,6 +286,13 @@ struct nm_comb_args {
   double* f_p;
   double* s_stat;
   double* s_p;
+  // candidate list for an armed head selection (nm_rank.cuh): rows [head_lo, head_hi) whose combined p
+  // (head_col 0: Stouffer, 1: Fisher) has a key image in an exponent bin <= head_thr_bin are appended
+  int32_t* head_cand;
+  int* head_cursor;
+  int64_t head_lo, head_hi;
+  unsigned head_thr_bin;
+  int head_cap, head_col;
 };
 
 struct nm_comb_win {
@@ -361,6 +368,13 @@ __global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_co
   nm_combine_row(nb, a.w, a.wnorm, W, a.want_fisher != 0, a.want_stouffer != 0, &fs, &fp, &ss, &sp);
   if (a.want_fisher) { a.f_stat[r] = fs; a.f_p[r] = fp; }
   if (a.want_stouffer) { a.s_stat[r] = ss; a.s_p[r] = sp; }
+  if (a.head_cand && r >= a.head_lo && r < a.head_hi) {
+    const unsigned bin = (unsigned)(nm_key_image(a.head_col ? fp : sp) >> 52);
+    if (bin <= a.head_thr_bin) {
+      const int slot = atomicAdd(a.head_cursor, 1);
+      if (slot < a.head_cap) a.head_cand[slot] = (int32_t)(r - a.head_lo);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -397,7 +411,9 @@ struct nm_handle {
     nm_head_geo geo;
     nm_head_record* records;
     nm_head_peers_dev peers;
+    int use_cands;       // this call's combine kernel lists the candidates (nm_head_from_cands_run selects)
   } head;
+  nm_buf d_head_cand;
   nm_head_peers_dev next_peers;  // nm_head_set_peers: taken by the next arming / selection (one shot)
   int grid_skip;       // calls left for which the grid-key launch is skipped (the last attempt found off-grid data)
   nm_buf d_retry;      // retry list of the grid-key launch
@@ -565,7 +581,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1, &h->d_retry};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1, &h->d_retry, &h->d_head_cand};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -799,15 +815,56 @@ static void nm_fill_comb_args(nm_comb_args* ca, const nm_pileup* pl, const nm_pa
 
 // The armed head selection (nm_arm_head_select), launched behind the call's last kernel.  It was armed for a
 // call whose rows are its candidates; any other outcome leaves it unfired and the caller selects afterwards.
+#define NM_HEAD_CAND_MIN 65536
+static int nm_head_cand_cap(int64_t want) { return (int)(32 * want > NM_HEAD_CAND_MIN ? 32 * want : NM_HEAD_CAND_MIN); }
+
+// Lets the combine kernel of this call list the candidates of the armed head selection, when the selection's
+// primary key is the combined p-value column the kernel writes (rankUse = 'pv') over a row range of this table.
+static int nm_head_cands_setup(nm_handle* h, nm_comb_args* ca, const nm_table* tb, int64_t n_rows) {
+  h->head.use_cands = 0;
+  if (!h->head.armed || h->head.reverse || ca->nb <= 0 || !h->head.key[0] || h->head.want > (1 << 20)) return NM_OK;
+  int col = -1;
+  const double* base = nullptr;
+  if (ca->want_stouffer && h->head.key[0] >= tb->stouffer_p && h->head.key[0] < tb->stouffer_p + n_rows) { col = 0; base = tb->stouffer_p; }
+  else if (ca->want_fisher && h->head.key[0] >= tb->fisher_p && h->head.key[0] < tb->fisher_p + n_rows) { col = 1; base = tb->fisher_p; }
+  if (col < 0) return NM_OK;
+  const int64_t lo = h->head.key[0] - base;
+  if (lo + h->head.n_rows > n_rows) return NM_OK;
+  const unsigned thr = nm_head_thr_bin(h->head.n_rows, h->head.want);
+  if (!thr) return NM_OK;
+  const int cap = nm_head_cand_cap(h->head.want);
+  const int rc = nm_reserve(h, &h->d_head_cand, sizeof(int32_t) * (size_t)cap);
+  if (rc != NM_OK) return rc;
+  ca->head_cand = (int32_t*)h->d_head_cand.p;
+  ca->head_cursor = &h->d_sum->head_cursor;  // zeroed with the summary at the start of the call
+  ca->head_lo = lo; ca->head_hi = lo + h->head.n_rows;
+  ca->head_thr_bin = thr; ca->head_cap = cap; ca->head_col = col;
+  h->head.use_cands = 1;
+  return NM_OK;
+}
+
+// The armed head selection (nm_arm_head_select), launched behind the call's last kernel.  It was armed for a
+// call whose rows are its candidates; any other outcome leaves it unfired and the caller selects afterwards.
 static int nm_fire_armed_head(nm_handle* h, int64_t n_rows, int64_t n_pos, cudaStream_t st) {
   h->head.fired = 0;
+  const int use_cands = h->head.use_cands;
+  h->head.use_cands = 0;
   if (!h->head.armed || n_rows != n_pos) return NM_OK;
   int rc = nm_reserve(h, &h->d_rank, nm_head_scratch_bytes(1));
   if (rc != NM_OK) return rc;
   int launches = 0;
-  const cudaError_t e = (cudaError_t)nm_head_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.reverse,
-                                                 h->head.want, h->head.cap, h->head.geo, h->d_rank.p, h->head.records,
-                                                 h->sm_count, &launches, st, h->head.peers.n > 0 ? &h->head.peers : nullptr);
+  const nm_head_peers_dev* peers = h->head.peers.n > 0 ? &h->head.peers : nullptr;
+  cudaError_t e;
+  if (use_cands) {
+    nm_head_peers_dev pr = h->head.peers;  // the refusal flag is wanted with or without peers
+    e = (cudaError_t)nm_head_from_cands_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.want,
+                                            h->head.cap, h->head.geo, (const int32_t*)h->d_head_cand.p, &h->d_sum->head_cursor,
+                                            nm_head_cand_cap(h->head.want), h->head.records, &h->d_sum->head_fail, &launches, st, &pr);
+  } else {
+    e = (cudaError_t)nm_head_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.reverse,
+                                 h->head.want, h->head.cap, h->head.geo, h->d_rank.p, h->head.records,
+                                 h->sm_count, &launches, st, peers);
+  }
   h->launches += launches;
   if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "armed head selection failed: %s", cudaGetErrorString(e));
   h->head.fired = 1;
@@ -898,6 +955,7 @@ static int nm_dense_enqueue(nm_handle* h, const nm_pileup* pl, const nm_params& 
     ca.row_pos_index = nullptr;  // row == candidate
     ca.z_pre = ka.comb_z;
     ca.ln_pre = ka.comb_ln;
+    if ((rc = nm_head_cands_setup(h, &ca, tb, n)) != NM_OK) return rc;
     nm_launch_combine(ca, n, st);
     NM_CUDA(h, cudaGetLastError());
     h->launches++;
@@ -914,6 +972,7 @@ static int nm_dense_complete(nm_handle* h, int try_grid, int n_launched, nm_summ
   *sum_out = *h->h_sum;
   h->last_grid_tiles = sum_out->grid_tiles;
   *refused = sum_out->dense_retry != 0;
+  if (sum_out->head_fail) h->head.fired = 0;  // the candidate list could not give the head: the caller selects
   if (try_grid && !*refused)
     h->grid_skip = sum_out->grid_giveup ? NM_GRID_SKIP_CALLS : 0;
   else if (h->grid_skip > 0 && !*refused)
@@ -1056,6 +1115,7 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
     h->last_path = 3;
     if (nm_dense_shape(sum)) {  // dense after all, only another network class: launch it again, sized right
       NM_CUDA(h, cudaMemsetAsync(&h->d_sum->dense_retry, 0, 7 * sizeof(int), st));  // + the cursors and grid-key counters
+      NM_CUDA(h, cudaMemsetAsync(&h->d_sum->head_cursor, 0, 2 * sizeof(int), st));   // + the head candidates of the refused pass
       rc = nm_run_dense(h, pl, prm, tb, nm_lane_class(sum.max_lane_n), st, &sum, &refused);
       if (rc != NM_OK) return rc;
       if (refused) return nm_fail(h, NM_ERR_CUDA, "internal: dense launch refused after validation");
@@ -1302,7 +1362,7 @@ extern "C" int nm_detect_finish(nm_handle* h, int ticket, int64_t* n_rows_out, i
     h->dense_class = nm_lane_class(sum.max_lane_n);
     h->last_path = 2;
     *n_rows_out = pd->pl.n_pos;
-    if (head_fired_out) *head_fired_out = pd->head_fired;
+    if (head_fired_out) *head_fired_out = pd->head_fired && !sum.head_fail;
     return NM_OK;
   }
   // the shape was not the previous call's: the ordinary call, from its plan pass (behind whatever else is in

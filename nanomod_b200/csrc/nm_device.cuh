@@ -126,6 +126,8 @@ struct nm_summary {
   // every block adds to entry (blockIdx & 31): tens of thousands of atomics on ONE address serialise in L2
   int spread[32][4];
   int n_huge;                 // deep rows beyond the shared-memory deep tier (nm_huge.cu takes them)
+  int head_cursor;            // candidates the combine kernel listed for an armed head selection (nm_rank.cuh)
+  int head_fail;              // that list could not give the head (too few / too many candidates): select the ordinary way
   unsigned long long huge_v0, huge_v1;  // their values in group 0 / 1
 };
 

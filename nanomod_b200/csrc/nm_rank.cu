@@ -285,6 +285,36 @@ __global__ void __launch_bounds__(256) nm_head_cut(unsigned* __restrict__ hist, 
   }
 }
 
+// one record of the head: the row, its three key images, its position and plot1's neighbourhood test
+__device__ __forceinline__ nm_head_record nm_head_make_record(const double* __restrict__ k1, const double* __restrict__ k2,
+                                                              int64_t r, unsigned long long i0, int reverse,
+                                                              const nm_head_geo& geo) {
+  nm_head_record rec;
+  rec.row = (long long)r;
+  rec.key[0] = i0;
+  rec.key[1] = k1 ? nm_head_image(k1, r, reverse) : 0ull;
+  rec.key[2] = k2 ? nm_head_image(k2, r, reverse) : 0ull;
+  rec.seg = rec.pos = -1;
+  rec.full_nbhd = 0;
+  rec.pad = 0;
+  if (geo.pos) {
+    // the row inside the caller's whole row list (the ranked range may be a slice of it)
+    const int64_t g = geo.row_offset + r;
+    const int64_t c = geo.row_pos_index ? (int64_t)geo.row_pos_index[g] : g;
+    rec.seg = geo.seg[c];
+    rec.pos = geo.pos[c];
+    // plot1 (myDetect.py:153-164): rows g-nearby .. g+nearby must be one contiguous run; positions
+    // increase strictly inside a segment, so it is one iff its ends are 2*nearby positions apart
+    const int64_t lo = g - geo.nearby, hi = g + geo.nearby;
+    if (lo >= 0 && hi < geo.n_rows_total) {
+      const int64_t cl = geo.row_pos_index ? (int64_t)geo.row_pos_index[lo] : lo;
+      const int64_t ch = geo.row_pos_index ? (int64_t)geo.row_pos_index[hi] : hi;
+      rec.full_nbhd = (geo.seg[cl] == geo.seg[ch] && (long long)geo.pos[ch] - (long long)geo.pos[cl] == 2LL * geo.nearby) ? 1 : 0;
+    }
+  }
+  return rec;
+}
+
 __global__ void __launch_bounds__(256)
 nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, int64_t n,
                 int reverse, unsigned* __restrict__ hist, nm_head_record* __restrict__ out, unsigned cap,
@@ -296,29 +326,7 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
     if ((unsigned)(i0 >> 52) <= cut) {
       const unsigned slot = atomicAdd(&hist[NM_HEAD_BINS + 2], 1u);
       if (slot < cap) {
-        nm_head_record rec;
-        rec.row = (long long)r;
-        rec.key[0] = i0;
-        rec.key[1] = k1 ? nm_head_image(k1, r, reverse) : 0ull;
-        rec.key[2] = k2 ? nm_head_image(k2, r, reverse) : 0ull;
-        rec.seg = rec.pos = -1;
-        rec.full_nbhd = 0;
-        rec.pad = 0;
-        if (geo.pos) {
-          // the row inside the caller's whole row list (the ranked range may be a slice of it)
-          const int64_t g = geo.row_offset + r;
-          const int64_t c = geo.row_pos_index ? (int64_t)geo.row_pos_index[g] : g;
-          rec.seg = geo.seg[c];
-          rec.pos = geo.pos[c];
-          // plot1 (myDetect.py:153-164): rows g-nearby .. g+nearby must be one contiguous run; positions
-          // increase strictly inside a segment, so it is one iff its ends are 2*nearby positions apart
-          const int64_t lo = g - geo.nearby, hi = g + geo.nearby;
-          if (lo >= 0 && hi < geo.n_rows_total) {
-            const int64_t cl = geo.row_pos_index ? (int64_t)geo.row_pos_index[lo] : lo;
-            const int64_t ch = geo.row_pos_index ? (int64_t)geo.row_pos_index[hi] : hi;
-            rec.full_nbhd = (geo.seg[cl] == geo.seg[ch] && (long long)geo.pos[ch] - (long long)geo.pos[cl] == 2LL * geo.nearby) ? 1 : 0;
-          }
-        }
+        const nm_head_record rec = nm_head_make_record(k1, k2, r, i0, reverse, geo);
         out[slot] = rec;
         for (int p = 0; p < peers.n; ++p) peers.base[p][1 + slot] = rec;  // peer memory: the exchange itself
       }
@@ -326,7 +334,102 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
   }
 }
 
+// histogram, cut and compaction over the candidate list the combine kernel left (nm_rank.cuh), by one block
+__global__ void __launch_bounds__(1024)
+nm_head_from_cands(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, long long n,
+                   unsigned want, unsigned cap, const nm_head_geo geo, const int32_t* __restrict__ cands,
+                   const int* __restrict__ cursor, int cand_cap, nm_head_record* __restrict__ records, int* __restrict__ fail,
+                   const nm_head_peers_dev peers) {
+  __shared__ unsigned hist[NM_HEAD_BINS];
+  __shared__ unsigned part[256];
+  __shared__ unsigned s_cut, s_slot;
+  __shared__ int s_ok;
+  const int listed = *cursor;
+  const bool over = listed > cand_cap;
+  const int nc = over ? 0 : listed;
+  for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 1024) hist[b] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += 1024)
+    atomicAdd(&hist[(unsigned)(nm_head_image(k0, cands[i], 0) >> 52)], 1u);
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    unsigned s = 0;
+    for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
+    part[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cut_w, cut_f;
+    unsigned cum_w, cum_f;
+    nm_head_search(hist, part, want, cap, &cut_w, &cum_w, &cut_f, &cum_f);
+    // every bin up to the listing threshold is counted in full, so the cut is the full histogram's cut as soon as
+    // the list holds `want` rows
+    const bool ok = !over && (unsigned)nc >= want;
+    int cut = cut_w;
+    unsigned cum = cum_w;
+    if (cum_w > cap) {
+      cut = cut_f;
+      cum = cum_f;
+    }
+    const bool refused = peers.refused && *peers.refused;
+    if (!ok) *fail = 1;
+    nm_head_record hdr;
+    hdr.row = (ok && cum <= cap) ? cum : 0;
+    hdr.seg = hdr.pos = hdr.full_nbhd = 0;
+    hdr.pad = refused ? -1 : ok ? peers.epoch : -2;
+    hdr.key[0] = (unsigned long long)n;
+    hdr.key[1] = (ok && cum == (unsigned)n && cum <= cap) ? 1ull : 0ull;
+    hdr.key[2] = (unsigned)cut;
+    records[0] = hdr;
+    for (int p = 0; p < peers.n; ++p) peers.base[p][0] = hdr;
+    s_cut = (unsigned)cut;
+    s_slot = 0;
+    s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_ok || s_cut == 0xffffffffu) return;
+  const unsigned cut = s_cut;
+  for (int i = threadIdx.x; i < nc; i += 1024) {
+    const int64_t r = cands[i];
+    const unsigned long long i0 = nm_head_image(k0, r, 0);
+    if ((unsigned)(i0 >> 52) <= cut) {
+      const unsigned slot = atomicAdd(&s_slot, 1u);
+      if (slot < cap) {
+        const nm_head_record rec = nm_head_make_record(k1, k2, r, i0, 0, geo);
+        records[1 + slot] = rec;
+        for (int p = 0; p < peers.n; ++p) peers.base[p][1 + slot] = rec;
+      }
+    }
+  }
+}
+
 }  // namespace
+
+unsigned nm_head_thr_bin(int64_t n, int64_t want) {
+  if (want <= 0 || n < 8 * want) return 0;
+  int j = 0;
+  while (j < 60 && (n >> (j + 1)) >= 4 * want) ++j;  // largest j with n / 2^j >= 4 * want
+  if (j < 1) return 0;
+  return 0x800u + 1023u - (unsigned)j - 1u;  // image >> 52 of the positive doubles below 2^-j
+}
+
+int nm_head_from_cands_run(const double* comb, const double* ks, const double* u, int64_t n, int64_t want, int64_t cap,
+                           const nm_head_geo& geo, const int32_t* cands, const int* cursor, int cand_cap,
+                           nm_head_record* records, int* fail, int* launches, cudaStream_t st,
+                           const nm_head_peers_dev* peers_in) {
+  nm_head_peers_dev peers;
+  memset(&peers, 0, sizeof(peers));
+  if (peers_in) peers = *peers_in;
+  const double* cols[3] = {comb, ks, u};
+  const double* k[3] = {nullptr, nullptr, nullptr};
+  int m = 0;
+  for (int c = 0; c < 3; ++c)
+    if (cols[c]) k[m++] = cols[c];
+  nm_head_from_cands<<<1, 1024, 0, st>>>(k[0], k[1], k[2], (long long)n, (unsigned)(want < n ? want : n), (unsigned)cap, geo,
+                                         cands, cursor, cand_cap, records, fail, peers);
+  *launches += 1;
+  return (int)cudaGetLastError();
+}
 
 size_t nm_head_scratch_bytes(int64_t cap) {
   return nm_align256(sizeof(unsigned) * (NM_HEAD_BINS + 4)) + sizeof(nm_head_record) * (size_t)cap;

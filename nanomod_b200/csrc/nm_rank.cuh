@@ -62,3 +62,22 @@ size_t nm_head_scratch_bytes(int64_t cap);
 int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n, int reverse, int64_t want, int64_t cap,
                 const nm_head_geo& geo, void* scratch, nm_head_record* records, int sm_count, int* launches, cudaStream_t st,
                 const nm_head_peers_dev* peers = nullptr);
+
+// Head selection from a candidate list.  When the selection is armed for a detect call whose primary ranking
+// key is the combined p-value, the combine kernel itself lists every core row whose key image falls into an
+// exponent bin <= thr_bin (p < 2^-j, j chosen so that a null table gives 4..8 x `want` such rows: a fraction of a
+// percent of the rows, one atomic each); one block then does histogram, cut and compaction over that list
+// instead of three passes over every row.  Same header, same records (in another order).  *fail is raised --
+// and nothing usable written -- when the list overflowed or holds fewer than `want` rows.
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long nm_key_image(double x) {  // == nm_rank_key (nm_rank.cu)
+  if (x != x) return ~0ull;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x + 0.0);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+#endif
+unsigned nm_head_thr_bin(int64_t n, int64_t want);  // 0: the table is too short for the candidate path
+int nm_head_from_cands_run(const double* comb, const double* ks, const double* u, int64_t n, int64_t want, int64_t cap,
+                           const nm_head_geo& geo, const int32_t* cands, const int* cursor, int cand_cap,
+                           nm_head_record* records, int* fail, int* launches, cudaStream_t st,
+                           const nm_head_peers_dev* peers);

@@ -756,6 +756,34 @@ def test_head_selection_armed_for_the_detect_call(det, drop):
         assert a.tobytes() == b.tobytes()
 
 
+@pytest.mark.parametrize("kind", ["null", "identical_groups", "all_shifted"])
+def test_armed_head_from_the_combine_kernels_candidate_list(det, kind):
+    """With p-value ranking the armed selection works from the candidate list the combine kernel leaves (rows
+    whose combined p lies below a power of two chosen from want / n) instead of three passes over all rows:
+    same header and records as selecting afterwards.  When the list cannot give the head (identical groups:
+    every p is 1, no candidates) the call reports the selection as not run and the caller selects as before."""
+    from nanomod_b200.sharded import HEAD_REC
+    p = nm.synthetic_pileup(30000, 70, 66, round_decimals=3, seed=31)
+    if kind == "identical_groups":
+        p = nm.Pileup(vals0=p.vals0, off0=p.off0, vals1=p.vals0.copy(), off1=p.off0.copy(), pos=p.pos, seg=p.seg,
+                      base=p.base, seg_names=p.seg_names)
+    elif kind == "all_shifted":
+        p.vals1[:] = np.round(p.vals1 + 1.5, 3)
+    opt = nm.DetectOptions(neighborPvalues=3, testMethod="stouffer", want_u=False, want_t=False, SaveTest=0)
+    sd = ShardedDetector(det)
+    dev = nm.DevicePileup.from_host(p, "cuda:0")
+    lo, hi = 10, 29990
+    for _ in range(2):
+        plain = sd.detect_shard(dev, lo, hi, 0, opt)
+        want_rec = sd.gather_heads(plain, 400, cap=2048).cpu().numpy().view(HEAD_REC).copy()
+        armed = sd.detect_shard(dev, lo, hi, 0, opt, head_want=400, head_cap=2048)
+        assert (armed.head_slot is not None) == (kind != "identical_groups")
+        got_rec = sd.gather_heads(armed, 400, cap=2048).cpu().numpy().view(HEAD_REC).copy()
+        n = int(want_rec[0]["row"])
+        assert int(got_rec[0]["row"]) == n and got_rec[0]["key"].tobytes() == want_rec[0]["key"].tobytes()
+        assert np.sort(want_rec[1:n + 1], order=["row"]).tobytes() == np.sort(got_rec[1:n + 1], order=["row"]).tobytes()
+
+
 def _table_bytes(out, n):
     return {c: out[c][:n].cpu().numpy().tobytes() for c in out if out[c].dim() == 1}
 
