@@ -288,7 +288,7 @@ struct nm_comb_args {
   double* s_p;
   // candidate list for an armed head selection (nm_rank.cuh): rows [head_lo, head_hi) whose combined p
   // (head_col 0: Stouffer, 1: Fisher) has a key image in an exponent bin <= head_thr_bin are appended
-  int32_t* head_cand;
+  int2* head_cand;      // {row - head_lo, exponent bin}
   int* head_cursor;
   int64_t head_lo, head_hi;
   unsigned head_thr_bin;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NM_COMB_THREADS) nm_combine_kernel(const nm_co
     const unsigned bin = (unsigned)(nm_key_image(a.head_col ? fp : sp) >> 52);
     if (bin <= a.head_thr_bin) {
       const int slot = atomicAdd(a.head_cursor, 1);
-      if (slot < a.head_cap) a.head_cand[slot] = (int32_t)(r - a.head_lo);
+      if (slot < a.head_cap) a.head_cand[slot] = make_int2((int)(r - a.head_lo), (int)bin);
     }
   }
 }
@@ -412,11 +412,15 @@ struct nm_handle {
     nm_head_record* records;
     nm_head_peers_dev peers;
     int use_cands;       // this call's combine kernel lists the candidates (nm_head_from_cands_run selects)
+    unsigned thr_bin;    // ... rows whose key image lies in an exponent bin <= this
   } head;
   nm_buf d_head_cand;
+  int head_cut_hint;     // bin at which the last candidate-list selection reached `want` (0: none / it failed)
+  int64_t head_hint_n, head_hint_want;  // ... for this many rows and this `want`
   nm_head_peers_dev next_peers;  // nm_head_set_peers: taken by the next arming / selection (one shot)
   int grid_skip;       // calls left for which the grid-key launch is skipped (the last attempt found off-grid data)
   nm_buf d_retry;      // retry list of the grid-key launch
+  int no_head_cands;   // NANOMOD_B200_NO_HEAD_CANDS=1: armed head selections always take the three-pass form (A/B experiments)
   int grid_u;          // NANOMOD_B200_GRID_U=1: take the grid-key kernel also when U is wanted (tests of that walk)
   int no_grid;         // NANOMOD_B200_NO_GRID=1: never try the 16-bit grid-key sort of the lane tier (A/B experiments, tests)
   int no_dense;        // NANOMOD_B200_NO_DENSE=1: never take the dense path (A/B experiments, tests of the general path)
@@ -542,6 +546,8 @@ extern "C" int nm_create(int device, nm_handle** out) {
     h->no_dense = (d && d[0] == '1') ? 1 : 0;
     const char* gk = getenv("NANOMOD_B200_NO_GRID");
     h->no_grid = (gk && gk[0] == '1') ? 1 : 0;
+    const char* hc = getenv("NANOMOD_B200_NO_HEAD_CANDS");
+    h->no_head_cands = (hc && hc[0] == '1') ? 1 : 0;
     const char* gu = getenv("NANOMOD_B200_GRID_U");
     h->grid_u = (gu && gu[0] == '1') ? 1 : 0;
   }
@@ -822,7 +828,7 @@ static int nm_head_cand_cap(int64_t want) { return (int)(32 * want > NM_HEAD_CAN
 // primary key is the combined p-value column the kernel writes (rankUse = 'pv') over a row range of this table.
 static int nm_head_cands_setup(nm_handle* h, nm_comb_args* ca, const nm_table* tb, int64_t n_rows) {
   h->head.use_cands = 0;
-  if (!h->head.armed || h->head.reverse || ca->nb <= 0 || !h->head.key[0] || h->head.want > (1 << 20)) return NM_OK;
+  if (h->no_head_cands || !h->head.armed || h->head.reverse || ca->nb <= 0 || !h->head.key[0] || h->head.want > (1 << 20)) return NM_OK;
   int col = -1;
   const double* base = nullptr;
   if (ca->want_stouffer && h->head.key[0] >= tb->stouffer_p && h->head.key[0] < tb->stouffer_p + n_rows) { col = 0; base = tb->stouffer_p; }
@@ -830,16 +836,22 @@ static int nm_head_cands_setup(nm_handle* h, nm_comb_args* ca, const nm_table* t
   if (col < 0) return NM_OK;
   const int64_t lo = h->head.key[0] - base;
   if (lo + h->head.n_rows > n_rows) return NM_OK;
-  const unsigned thr = nm_head_thr_bin(h->head.n_rows, h->head.want);
+  unsigned thr = nm_head_thr_bin(h->head.n_rows, h->head.want);  // what a null table needs
   if (!thr) return NM_OK;
+  // a table with many significant rows holds far more rows below that than the head needs: after a selection
+  // of the same size that succeeded, list only up to two bins above its cut
+  if (h->head_cut_hint > 0 && h->head_hint_n == h->head.n_rows && h->head_hint_want == h->head.want &&
+      (unsigned)h->head_cut_hint + 2u < thr)
+    thr = (unsigned)h->head_cut_hint + 2u;
   const int cap = nm_head_cand_cap(h->head.want);
-  const int rc = nm_reserve(h, &h->d_head_cand, sizeof(int32_t) * (size_t)cap);
+  const int rc = nm_reserve(h, &h->d_head_cand, sizeof(int2) * (size_t)cap);
   if (rc != NM_OK) return rc;
-  ca->head_cand = (int32_t*)h->d_head_cand.p;
+  ca->head_cand = (int2*)h->d_head_cand.p;
   ca->head_cursor = &h->d_sum->head_cursor;  // zeroed with the summary at the start of the call
   ca->head_lo = lo; ca->head_hi = lo + h->head.n_rows;
   ca->head_thr_bin = thr; ca->head_cap = cap; ca->head_col = col;
   h->head.use_cands = 1;
+  h->head.thr_bin = thr;
   return NM_OK;
 }
 
@@ -858,8 +870,11 @@ static int nm_fire_armed_head(nm_handle* h, int64_t n_rows, int64_t n_pos, cudaS
   if (use_cands) {
     nm_head_peers_dev pr = h->head.peers;  // the refusal flag is wanted with or without peers
     e = (cudaError_t)nm_head_from_cands_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.want,
-                                            h->head.cap, h->head.geo, (const int32_t*)h->d_head_cand.p, &h->d_sum->head_cursor,
-                                            nm_head_cand_cap(h->head.want), h->head.records, &h->d_sum->head_fail, &launches, st, &pr);
+                                            h->head.cap, h->head.geo, h->d_head_cand.p, &h->d_sum->head_cursor,
+                                            nm_head_cand_cap(h->head.want), h->head.thr_bin,
+                                            h->head.records, &h->d_sum->head_fail, &h->d_sum->head_cut, &launches, st, &pr);
+    h->head_hint_n = h->head.n_rows;  // what the hint of this call's summary will be about
+    h->head_hint_want = h->head.want;
   } else {
     e = (cudaError_t)nm_head_run(h->head.key[0], h->head.key[1], h->head.key[2], h->head.n_rows, h->head.reverse,
                                  h->head.want, h->head.cap, h->head.geo, h->d_rank.p, h->head.records,
@@ -973,6 +988,7 @@ static int nm_dense_complete(nm_handle* h, int try_grid, int n_launched, nm_summ
   h->last_grid_tiles = sum_out->grid_tiles;
   *refused = sum_out->dense_retry != 0;
   if (sum_out->head_fail) h->head.fired = 0;  // the candidate list could not give the head: the caller selects
+  if (!*refused && (sum_out->head_cut > 0 || sum_out->head_fail)) h->head_cut_hint = sum_out->head_fail ? 0 : sum_out->head_cut;
   if (try_grid && !*refused)
     h->grid_skip = sum_out->grid_giveup ? NM_GRID_SKIP_CALLS : 0;
   else if (h->grid_skip > 0 && !*refused)

@@ -128,6 +128,7 @@ struct nm_summary {
   int n_huge;                 // deep rows beyond the shared-memory deep tier (nm_huge.cu takes them)
   int head_cursor;            // candidates the combine kernel listed for an armed head selection (nm_rank.cuh)
   int head_fail;              // that list could not give the head (too few / too many candidates): select the ordinary way
+  int head_cut;               // exponent bin at which that selection reached `want` rows (0: none)
   unsigned long long huge_v0, huge_v1;  // their values in group 0 / 1
 };
 

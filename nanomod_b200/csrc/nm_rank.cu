@@ -334,70 +334,107 @@ nm_head_compact(const double* __restrict__ k0, const double* __restrict__ k1, co
   }
 }
 
-// histogram, cut and compaction over the candidate list the combine kernel left (nm_rank.cuh), by one block
+// histogram, cut and compaction over the candidate list the combine kernel left (nm_rank.cuh), by one block.
+// An entry is {row, exponent bin of its key image}; bins are counted relative to the listing threshold
+// (rel = thr_bin - bin >= 0: larger rel = smaller p), so the histogram is 2048 shared-memory words, the cumulative
+// counts from the smallest p upwards are one block-wide suffix scan, and the cut is found by all threads at once.
+#define NM_HEAD_REL_BINS 2048
 __global__ void __launch_bounds__(1024)
 nm_head_from_cands(const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2, long long n,
-                   unsigned want, unsigned cap, const nm_head_geo geo, const int32_t* __restrict__ cands,
-                   const int* __restrict__ cursor, int cand_cap, nm_head_record* __restrict__ records, int* __restrict__ fail,
-                   const nm_head_peers_dev peers) {
-  __shared__ unsigned hist[NM_HEAD_BINS];
-  __shared__ unsigned part[256];
-  __shared__ unsigned s_cut, s_slot;
-  __shared__ int s_ok;
+                   unsigned want, unsigned cap, const nm_head_geo geo, const int2* __restrict__ cands,
+                   const int* __restrict__ cursor, int cand_cap, unsigned thr_bin, nm_head_record* __restrict__ records,
+                   int* __restrict__ fail, int* __restrict__ cut_out, const nm_head_peers_dev peers) {
+  __shared__ unsigned hist[NM_HEAD_REL_BINS];   // then: suffix sums
+  __shared__ unsigned warp_tot[32];
+  __shared__ int s_rel_w, s_rel_f;               // largest rel with suffix >= want | smallest rel with suffix <= cap
+  __shared__ unsigned s_slot;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int listed = *cursor;
   const bool over = listed > cand_cap;
   const int nc = over ? 0 : listed;
-  for (int b = threadIdx.x; b < NM_HEAD_BINS; b += 1024) hist[b] = 0;
+  hist[tid] = 0;
+  hist[tid + 1024] = 0;
+  if (tid == 0) { s_rel_w = -1; s_rel_f = NM_HEAD_REL_BINS; s_slot = 0; }
   __syncthreads();
-  for (int i = threadIdx.x; i < nc; i += 1024)
-    atomicAdd(&hist[(unsigned)(nm_head_image(k0, cands[i], 0) >> 52)], 1u);
-  __syncthreads();
-  if (threadIdx.x < 256) {
-    unsigned s = 0;
-    for (int b = 0; b < NM_HEAD_BINS / 256; ++b) s += hist[threadIdx.x * (NM_HEAD_BINS / 256) + b];
-    part[threadIdx.x] = s;
+  constexpr int U = 8;  // entries in flight per thread: the loop is latency-bound (one block)
+  for (int i0 = 0; i0 < nc; i0 += U * 1024) {
+    unsigned rel[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 1024 + tid;
+      rel[u] = i < nc ? thr_bin - (unsigned)__ldg(&cands[i].y) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // lanes of a warp that hit the same bin add once: the candidates crowd into the few bins next to the threshold
+      const unsigned peers_m = __match_any_sync(0xffffffffu, rel[u]);
+      if (rel[u] < NM_HEAD_REL_BINS && lane == __ffs(peers_m) - 1) atomicAdd(&hist[rel[u]], (unsigned)__popc(peers_m));
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int cut_w, cut_f;
-    unsigned cum_w, cum_f;
-    nm_head_search(hist, part, want, cap, &cut_w, &cum_w, &cut_f, &cum_f);
-    // every bin up to the listing threshold is counted in full, so the cut is the full histogram's cut as soon as
-    // the list holds `want` rows
-    const bool ok = !over && (unsigned)nc >= want;
-    int cut = cut_w;
-    unsigned cum = cum_w;
-    if (cum_w > cap) {
-      cut = cut_f;
-      cum = cum_f;
-    }
+  // suffix sums: thread t owns rel = 2047 - 2t and 2046 - 2t (descending rel = ascending p)
+  const int r_hi = NM_HEAD_REL_BINS - 1 - 2 * tid, r_lo = r_hi - 1;
+  const unsigned c_hi = hist[r_hi], c_lo = hist[r_lo];
+  unsigned inc = c_hi + c_lo;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  unsigned base = 0;
+  for (int w = 0; w < wid; ++w) base += warp_tot[w];
+  const unsigned suf_lo = base + inc, suf_hi = suf_lo - c_lo;  // rows with rel >= r_lo / >= r_hi
+  __syncthreads();
+  hist[r_hi] = suf_hi;
+  hist[r_lo] = suf_lo;
+  if (suf_hi >= want) atomicMax(&s_rel_w, r_hi); else if (suf_lo >= want) atomicMax(&s_rel_w, r_lo);
+  if (suf_lo <= cap) atomicMin(&s_rel_f, r_lo); else if (suf_hi <= cap) atomicMin(&s_rel_f, r_hi);
+  __syncthreads();
+  // every bin up to the listing threshold is counted in full, so the cut is the full histogram's cut as soon as
+  // the list holds `want` rows
+  const bool ok = !over && s_rel_w >= 0;
+  int rel_cut = ok ? s_rel_w : 0;
+  unsigned cum = ok ? hist[rel_cut] : 0;
+  if (ok && cum > cap) {
+    // the caller's buffer is fixed: stop at the last bin whose cumulative count still fits -- occupied or not, as the
+    // three-pass form names it: the bin just below the first one that does not fit (rel 2047 is always empty)
+    rel_cut = s_rel_f;
+    cum = hist[rel_cut];
+  }
+  if (tid == 0) {
     const bool refused = peers.refused && *peers.refused;
     if (!ok) *fail = 1;
+    *cut_out = ok ? (int)(thr_bin - (unsigned)s_rel_w) : 0;  // the bin that reaches `want`: the next call lists up to just above it
     nm_head_record hdr;
     hdr.row = (ok && cum <= cap) ? cum : 0;
     hdr.seg = hdr.pos = hdr.full_nbhd = 0;
     hdr.pad = refused ? -1 : ok ? peers.epoch : -2;
     hdr.key[0] = (unsigned long long)n;
     hdr.key[1] = (ok && cum == (unsigned)n && cum <= cap) ? 1ull : 0ull;
-    hdr.key[2] = (unsigned)cut;
+    hdr.key[2] = (unsigned long long)(thr_bin - (unsigned)rel_cut);
     records[0] = hdr;
     for (int p = 0; p < peers.n; ++p) peers.base[p][0] = hdr;
-    s_cut = (unsigned)cut;
-    s_slot = 0;
-    s_ok = ok ? 1 : 0;
   }
-  __syncthreads();
-  if (!s_ok || s_cut == 0xffffffffu) return;
-  const unsigned cut = s_cut;
-  for (int i = threadIdx.x; i < nc; i += 1024) {
-    const int64_t r = cands[i];
-    const unsigned long long i0 = nm_head_image(k0, r, 0);
-    if ((unsigned)(i0 >> 52) <= cut) {
-      const unsigned slot = atomicAdd(&s_slot, 1u);
-      if (slot < cap) {
-        const nm_head_record rec = nm_head_make_record(k1, k2, r, i0, 0, geo);
-        records[1 + slot] = rec;
-        for (int p = 0; p < peers.n; ++p) peers.base[p][1 + slot] = rec;
+  if (!ok) return;
+  for (int i0 = 0; i0 < nc; i0 += U * 1024) {
+    int2 c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 1024 + tid;
+      c[u] = i < nc ? __ldg(&cands[i]) : make_int2(0, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c[u].y >= 0 && thr_bin - (unsigned)c[u].y >= (unsigned)rel_cut && (unsigned)c[u].y <= thr_bin) {
+        const unsigned slot = atomicAdd(&s_slot, 1u);
+        if (slot < cap) {
+          const int64_t r = c[u].x;
+          const nm_head_record rec = nm_head_make_record(k1, k2, r, nm_head_image(k0, r, 0), 0, geo);
+          records[1 + slot] = rec;
+          for (int p = 0; p < peers.n; ++p) peers.base[p][1 + slot] = rec;
+        }
       }
     }
   }
@@ -414,8 +451,8 @@ unsigned nm_head_thr_bin(int64_t n, int64_t want) {
 }
 
 int nm_head_from_cands_run(const double* comb, const double* ks, const double* u, int64_t n, int64_t want, int64_t cap,
-                           const nm_head_geo& geo, const int32_t* cands, const int* cursor, int cand_cap,
-                           nm_head_record* records, int* fail, int* launches, cudaStream_t st,
+                           const nm_head_geo& geo, const void* cands, const int* cursor, int cand_cap, unsigned thr_bin,
+                           nm_head_record* records, int* fail, int* cut_out, int* launches, cudaStream_t st,
                            const nm_head_peers_dev* peers_in) {
   nm_head_peers_dev peers;
   memset(&peers, 0, sizeof(peers));
@@ -426,7 +463,7 @@ int nm_head_from_cands_run(const double* comb, const double* ks, const double* u
   for (int c = 0; c < 3; ++c)
     if (cols[c]) k[m++] = cols[c];
   nm_head_from_cands<<<1, 1024, 0, st>>>(k[0], k[1], k[2], (long long)n, (unsigned)(want < n ? want : n), (unsigned)cap, geo,
-                                         cands, cursor, cand_cap, records, fail, peers);
+                                         (const int2*)cands, cursor, cand_cap, thr_bin, records, fail, cut_out, peers);
   *launches += 1;
   return (int)cudaGetLastError();
 }

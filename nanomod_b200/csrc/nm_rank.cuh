@@ -68,7 +68,9 @@ int nm_head_run(const double* comb, const double* ks, const double* u, int64_t n
 // exponent bin <= thr_bin (p < 2^-j, j chosen so that a null table gives 4..8 x `want` such rows: a fraction of a
 // percent of the rows, one atomic each); one block then does histogram, cut and compaction over that list
 // instead of three passes over every row.  Same header, same records (in another order).  *fail is raised --
-// and nothing usable written -- when the list overflowed or holds fewer than `want` rows.
+// and nothing usable written -- when the list overflowed or holds fewer than `want` rows.  *cut_out receives the
+// bin that reached `want`: a table with many significant rows has far more rows below the null threshold than the
+// head needs, so the next call on the handle lists only up to two bins above the last cut (nm_api.cu).
 #if defined(__CUDACC__)
 __device__ __forceinline__ unsigned long long nm_key_image(double x) {  // == nm_rank_key (nm_rank.cu)
   if (x != x) return ~0ull;
@@ -78,6 +80,6 @@ __device__ __forceinline__ unsigned long long nm_key_image(double x) {  // == nm
 #endif
 unsigned nm_head_thr_bin(int64_t n, int64_t want);  // 0: the table is too short for the candidate path
 int nm_head_from_cands_run(const double* comb, const double* ks, const double* u, int64_t n, int64_t want, int64_t cap,
-                           const nm_head_geo& geo, const int32_t* cands, const int* cursor, int cand_cap,
-                           nm_head_record* records, int* fail, int* launches, cudaStream_t st,
+                           const nm_head_geo& geo, const void* cands /* int2 {row, bin} */, const int* cursor, int cand_cap,
+                           unsigned thr_bin, nm_head_record* records, int* fail, int* cut_out, int* launches, cudaStream_t st,
                            const nm_head_peers_dev* peers);
