@@ -1784,6 +1784,9 @@ extern "C" int nm_rank_head_select_device(nm_handle* h, const double* key_comb, 
                                           int64_t n_rows, int reverse, int64_t want, const nm_head_geometry* geometry,
                                           nm_head_row* records_dev, int64_t cap, void* cuda_stream) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
+  nm_head_peers_dev peers = h->next_peers;  // one shot, whatever becomes of this call
+  peers.refused = nullptr;
+  h->next_peers.n = 0;
   if (!records_dev || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "records_dev is NULL or cap <= 0");
   if (n_rows < 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
   if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
@@ -1806,9 +1809,6 @@ extern "C" int nm_rank_head_select_device(nm_handle* h, const double* key_comb, 
   }
   int launches = 0;
   static_assert(sizeof(nm_head_record) == sizeof(nm_head_row), "device and ABI head records must have one layout");
-  nm_head_peers_dev peers = h->next_peers;
-  peers.refused = nullptr;
-  h->next_peers.n = 0;
   const cudaError_t e = (cudaError_t)nm_head_run(key_comb, key_ks, key_u, n_rows, reverse, want > 0 ? want : 1, cap, geo,
                                                  h->d_rank.p, (nm_head_record*)records_dev, h->sm_count, &launches, st,
                                                  peers.n > 0 ? &peers : nullptr);
@@ -1826,6 +1826,8 @@ extern "C" int nm_arm_head_select(nm_handle* h, const double* key_comb, const do
                                   nm_head_row* records_dev, int64_t cap) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
   h->head.armed = h->head.fired = 0;
+  const nm_head_peers_dev peers_now = h->next_peers;  // one shot, whatever becomes of this call
+  h->next_peers.n = 0;
   if (!records_dev || cap <= 0) return nm_fail(h, NM_ERR_BAD_ARG, "records_dev is NULL or cap <= 0");
   if (n_rows <= 0 || n_rows > 0x7fffffffLL) return nm_fail(h, NM_ERR_BAD_ARG, "n_rows (%lld) out of range", (long long)n_rows);
   if (!key_comb && !key_ks && !key_u) return nm_fail(h, NM_ERR_BAD_ARG, "no ranking key given");
@@ -1841,9 +1843,8 @@ extern "C" int nm_arm_head_select(nm_handle* h, const double* key_comb, const do
   h->head.key[0] = key_comb; h->head.key[1] = key_ks; h->head.key[2] = key_u;
   h->head.n_rows = n_rows; h->head.reverse = reverse; h->head.want = want > 0 ? want : 1; h->head.cap = cap;
   h->head.records = (nm_head_record*)records_dev;
-  h->head.peers = h->next_peers;
+  h->head.peers = peers_now;
   h->head.peers.refused = &h->d_sum->dense_retry;
-  h->next_peers.n = 0;
   h->head.armed = 1;
   return NM_OK;
 }

@@ -194,6 +194,25 @@ class HeadExchange:
             self._opened = opened
         self._local = torch.as_tensor(_DevView(self.ptr, 2 * self.slot_bytes), device=device)
 
+    def close(self) -> None:
+        """Unmaps the peers' buffers, meets the other ranks (nobody may still store into a buffer that is
+        about to go), frees this rank's buffer.  Collective, like the constructor."""
+        import torch
+        import torch.distributed as dist
+        if self.ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for p in getattr(self, "_opened", []):
+            try:
+                self.handle.peer_close(p)
+            except Exception:
+                pass
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._local = None
+        self.handle.peer_free(self.ptr)
+        self.ptr, self.ok = None, False
+
     def bases(self, slot: int) -> List[int]:
         """this rank's section of slot ``slot`` in every rank's buffer"""
         off = (slot & 1) * self.slot_bytes + self.rank * self.section
@@ -271,6 +290,8 @@ class ShardedDetector:
             return None
         x = getattr(self, "_xchg", None)
         if x is None or x.cap != cap:
+            if x is not None:
+                x.close()
             x = self._xchg = HeadExchange(handle, self.group, cap, device)
             self._epoch = 0
         return x

@@ -889,6 +889,11 @@ def test_head_selection_stores_into_peer_buffers(det, drop):
         r = sd.finish_shard(pend[k])
         assert r.n_rows == plain.n_rows
         same(sd.gather_heads(r, want, cap=cap, slot=k, peer=True), r.head_epoch)
+    # another capacity: the old exchange buffer is closed, a new one built
+    x_old = sd.peer_exchange(cap, dev.pos.device)
+    x_new = sd.peer_exchange(2 * cap, dev.pos.device)
+    assert x_old.ptr is None and x_new.ptr is not None and x_new.cap == 2 * cap
+    x_new.close()
 
 
 def test_peer_buffer_alloc_and_view(det):

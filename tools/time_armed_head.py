@@ -25,5 +25,4 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 hdr = sd._head_mine[0][:48].cpu().numpy().view(nm.sharded.HEAD_REC)
-print(json.dumps({"ms_per_step_sync": e0.elapsed_time(e1) / 10, "fired": res.head_slot is not None, "head_rows": int(hdr[0]["row"]),
-                  "launches_per_step": None}))
+print(json.dumps({"ms_per_step_sync": e0.elapsed_time(e1) / 10, "fired": res.head_slot is not None, "head_rows": int(hdr[0]["row"])}))
