@@ -184,6 +184,17 @@ def test_struct_layouts_match_header(tmp_path):
     assert got == [ctypes.sizeof(_lib.nm_params), ctypes.sizeof(_lib.nm_pileup), ctypes.sizeof(_lib.nm_table),
                    _lib.nm_table.flags.offset, _lib.nm_table.moments.offset]
     assert got[:3] == [48, 112, 17 * 8]
+    # the head-exchange structures (nm_head_row = HEAD_REC of nanomod_b200.sharded, nm_head_geometry, nm_head_peers)
+    from nanomod_b200.sharded import HEAD_REC
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nanomod_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(nm_head_row), offsetof(nm_head_row, key),'
+                   ' offsetof(nm_head_row, reserved), sizeof(nm_head_geometry), sizeof(nm_head_peers),'
+                   ' offsetof(nm_head_peers, epoch), offsetof(nm_head_peers, base), NM_MAX_PEERS, NM_IPC_HANDLE_BYTES);return 0;}\n')
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [HEAD_REC.itemsize, HEAD_REC.fields["key"][1], HEAD_REC.fields["reserved"][1],
+                   ctypes.sizeof(_lib.nm_head_geometry), ctypes.sizeof(_lib.nm_head_peers), _lib.nm_head_peers.epoch.offset,
+                   _lib.nm_head_peers.base.offset, _lib.NM_MAX_PEERS, _lib.NM_IPC_HANDLE_BYTES]
 
 
 def test_no_cpu_fallback_without_gpu():
