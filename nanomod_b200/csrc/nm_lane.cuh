@@ -225,10 +225,11 @@ NM_HD void nm_ceb(float& a, float& b, int, int) {
 #ifndef NM_CE_MIX
 #define NM_CE_MIX 3
 #endif
-// packed 16-bit pairs: their own mix (the grid-key kernel's walk and key check lean on the ALU pipe
-// harder than the float32 kernel's); 0 = every comparator in the IMAD flavour
+// packed 16-bit pairs: their own mix; 0 = every comparator in the IMAD flavour.  Measured on the bench
+// workload (lane kernel, tools/gpu_r2_u.sh): 1 -> 1.531 ms, 2 -> 1.508, 3 -> 1.521, 4 -> 1.568, 0 -> 2.09 (spills):
+// one packed pass instead of two float32 sorts leaves the ALU pipe room for every second comparator.
 #ifndef NM_CE_MIX_P16
-#define NM_CE_MIX_P16 3
+#define NM_CE_MIX_P16 2
 #endif
 template <class T>
 NM_HD constexpr bool nm_ce_is_a(int p) { return p % NM_CE_MIX == 0; }
