@@ -38,7 +38,9 @@ enum { NM_COMBINE_NONE = 0, NM_COMBINE_FISHER = 1, NM_COMBINE_STOUFFER = 2 };
 #define NM_MAX_NB 32          /* largest neighborPvalues the combine kernel accepts */
 #define NM_LANE_TIER_MAX 128  /* coverage per group handled by the lane-per-position tier */
 #define NM_DEEP_TIER_MAX_POOLED 49152 /* pow2(n0)+pow2(n1) cap of the block-per-position tier */
-#define NM_DS_MAX_READS 256    /* reads per group a down-sampled position may have */
+#define NM_DS_MAX_READS 256    /* reads per group up to which a down-sampled position takes the warp kernel */
+#define NM_DS_DEEP_MAX_READS 32768 /* ... and the block kernel beyond (a down-sampled group longer than this: NM_ERR_TOO_DEEP) */
+#define NM_DS_DEEP_MAX_COV 1024    /* largest --coverages threshold for positions with more than NM_DS_MAX_READS reads */
 #define NM_DS_MAX_TIMES 1024   /* largest `downsampling` */
 
 /* Options that reach the device (subset of `moptions`, read at myDetect.py:301-414).

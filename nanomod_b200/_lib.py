@@ -17,6 +17,8 @@ NM_COMBINE_NONE, NM_COMBINE_FISHER, NM_COMBINE_STOUFFER = 0, 1, 2
 NM_MAX_NB = 32
 NM_LANE_TIER_MAX = 128
 NM_DS_MAX_READS = 256
+NM_DS_DEEP_MAX_READS = 32768
+NM_DS_DEEP_MAX_COV = 1024
 NM_DS_MAX_TIMES = 1024
 NM_RECORD_BYTES = 28
 

@@ -59,7 +59,7 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
               int* __restrict__ block_count, nm_summary* __restrict__ sum) {
   const int64_t p0 = (int64_t)blockIdx.x * NM_PLAN_PER_BLOCK + (int64_t)threadIdx.x * NM_PLAN_PER_THREAD;
   int cnt = 0, max_lane = 0, max_slack = 0, n_deep = 0, max_deep = 0, n_cand = 0, max_deep_t = 0, n_le64 = 0, n_le104 = 0;
-  bool bad = false, ds_deep = false;
+  bool bad = false, ds_deep = false, ds_huge = false;
 #pragma unroll
   for (int k = 0; k < NM_PLAN_PER_THREAD; ++k) {
     const int64_t p = p0 + k;
@@ -74,7 +74,11 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
         if (seg_cov && n_seg > 0 && (unsigned)seg[p] < (unsigned)n_seg) {
           // a row the down-sampling branch will take, but too long for it: known before any test runs
           const int cov = seg_cov[seg[p]];
-          if (cov > 0 && (n0 > cov || n1 > cov) && (n0 > NM_DS_MAX_READS || n1 > NM_DS_MAX_READS)) ds_deep = true;
+          if (cov > 0 && (n0 > cov || n1 > cov) && (n0 > NM_DS_MAX_READS || n1 > NM_DS_MAX_READS)) {
+            ds_deep = true;
+            if (cov > NM_DS_DEEP_MAX_COV || (n0 > cov && n0 > NM_DS_DEEP_MAX_READS) || (n1 > cov && n1 > NM_DS_DEEP_MAX_READS))
+              ds_huge = true;
+          }
         }
         const int64_t m = n0 > n1 ? n0 : n1;
         if (m <= NM_LANE_TIER_MAX) {
@@ -104,7 +108,7 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
   // block totals: warp reductions, one shared-memory hop, ONE set of atomics per block -- and only
   // those that would change the summary (every block hitting the same addresses costs tens of
   // microseconds at 4.6 M candidates)
-  unsigned flags = (bad ? 1u : 0u) | (ds_deep ? 2u : 0u);
+  unsigned flags = (bad ? 1u : 0u) | (ds_deep ? 2u : 0u) | (ds_huge ? 4u : 0u);
   flags = __reduce_or_sync(0xffffffffu, flags);
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   n_cand = __reduce_add_sync(0xffffffffu, n_cand);
@@ -138,7 +142,7 @@ nm_plan_count(const int64_t* __restrict__ off0, const int64_t* __restrict__ off1
       fl |= red[9][w];
     }
     if (fl & 1) sum->bad_input = 1;
-    if (fl & 2) sum->ds_too_deep = 1;
+    if (fl & 6) atomicOr(&sum->ds_too_deep, (int)((fl >> 1) & 3));
     if (nc != total) atomicAdd(&sum->n_filtered, nc - total);
     int* sp = sum->spread[blockIdx.x & (NM_SPREAD - 1)];
     if (total) atomicAdd(&sp[0], total);
@@ -415,6 +419,7 @@ struct nm_handle {
     unsigned thr_bin;    // ... rows whose key image lies in an exponent bin <= this
   } head;
   nm_buf d_head_cand;
+  nm_buf d_ds_scratch;   // sorted groups of nm_downsample_deep_kernel, per CTA
   int head_cut_hint;     // bin at which the last candidate-list selection reached `want` (0: none / it failed)
   int64_t head_hint_n, head_hint_want;  // ... for this many rows and this `want`
   nm_head_peers_dev next_peers;  // nm_head_set_peers: taken by the next arming / selection (one shot)
@@ -587,7 +592,7 @@ extern "C" void nm_destroy(nm_handle* h) {
   cudaSetDevice(h->device);
   nm_buf* bufs[] = {&h->d_block_count, &h->d_deep_rows, &h->d_acc_r2, &h->d_acc_tie, &h->d_acc_mom, &h->d_vals0, &h->d_vals1,
                     &h->d_off0,        &h->d_off1,      &h->d_pos,   &h->d_seg, &h->d_rank, &h->d_seg_cov, &h->d_perm[0], &h->d_perm[1], &h->d_class_scratch, &h->d_rank_keys[0],
-                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1, &h->d_retry, &h->d_head_cand};
+                    &h->d_rank_keys[1], &h->d_rank_keys[2], &h->d_rank_order, &h->d_comb_z, &h->d_comb_ln, &h->d_deep_fallback, &h->d_exp0, &h->d_exp1, &h->d_retry, &h->d_head_cand, &h->d_ds_scratch};
   for (nm_buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (nm_buf& b : h->d_out)
@@ -1145,10 +1150,11 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
   if (!have_sum) return nm_fail(h, NM_ERR_CUDA, "internal: plan summary missing");
   if (sum.bad_input)
     return nm_fail(h, NM_ERR_BAD_ARG, "offsets are not non-decreasing, or a segment id is outside [0, n_seg)");
-  if (ds_on && sum.ds_too_deep)  // known from the plan pass: refuse before any test has run
+  if (ds_on && (sum.ds_too_deep & 2))  // known from the plan pass: refuse before any test has run
     return nm_fail(h, NM_ERR_TOO_DEEP,
-                   "--coverages: a position to be down-sampled has more than %d reads in a group; the down-sampling "
-                   "branch supports at most that many (run without --coverages, or thin the pileup first)", NM_DS_MAX_READS);
+                   "--coverages: a position to be down-sampled has a group of more than %d reads, or more than %d reads with a "
+                   "threshold above %d; the down-sampling branch does not take it (run without --coverages, or thin the pileup first)",
+                   NM_DS_DEEP_MAX_READS, NM_DS_MAX_READS, NM_DS_DEEP_MAX_COV);
 
   // ---- plan, second pass: ordered compaction of the kept candidates into rows
   {
@@ -1239,6 +1245,15 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
                                                            h->sm_count, st);
     if (e != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_downsample_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
+    if (sum.ds_too_deep & 1) {  // rows beyond the warp kernel's shared-memory script: one CTA per row
+      if ((rc = nm_reserve(h, &h->d_ds_scratch, nm_downsample_deep_scratch_bytes(h->sm_count))) != NM_OK) return rc;
+      NM_CUDA(h, cudaMemsetAsync(&h->d_sum->ds_deep_cursor, 0, sizeof(int), st));
+      const cudaError_t e2 = (cudaError_t)nm_launch_downsample_deep(ka, pl->pos, pl->seg, pl->seg_cov, prm.ds_times, prm.ds_index,
+                                                                  prm.ds_seed, &h->d_sum->ds_deep_cursor, &h->d_sum->ds_too_deep,
+                                                                  (float*)h->d_ds_scratch.p, h->sm_count, st);
+      if (e2 != cudaSuccess) return nm_fail(h, NM_ERR_CUDA, "nm_downsample_deep_kernel launch failed: %s", cudaGetErrorString(e2));
+      h->launches++;
+    }
     NM_CUDA(h, cudaMemcpyAsync(h->h_sum, h->d_sum, sizeof(nm_summary), cudaMemcpyDeviceToHost, st));
   }
 
@@ -1256,7 +1271,7 @@ static int nm_detect_device_impl(nm_handle* h, const nm_pileup* pl, const nm_par
   NM_CUDA(h, cudaStreamSynchronize(st));
   h->last_grid_tiles = h->h_sum->grid_tiles;
   if (ds_on && h->h_sum->ds_too_deep)
-    return nm_fail(h, NM_ERR_TOO_DEEP, "down-sampling supports at most %d reads per group", NM_DS_MAX_READS);
+    return nm_fail(h, NM_ERR_TOO_DEEP, "down-sampling supports at most %d reads per group", NM_DS_DEEP_MAX_READS);
   {
     float ms = 0.f;
     // ev[1] is re-recorded after the plan readback, so [0] covers only the plan kernels' span

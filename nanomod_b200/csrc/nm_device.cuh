@@ -107,7 +107,8 @@ struct nm_summary {
   int deep_cursor;
   int tile_cursor[3];   // lane-tier work queues (tiles beyond the first wave), one per launch
   int ds_cursor;        // down-sampling work queue (rows, in chunks of 32)
-  int ds_too_deep;      // set by nm_downsample_kernel: a qualifying row has more than NM_DS_MAX_READS reads
+  int ds_too_deep;      // plan pass: bit 0 a row to be down-sampled has more than NM_DS_MAX_READS reads (the block kernel takes it),
+                        // bit 1 one is beyond that kernel too; the kernels raise it when they meet a row they cannot take
   int max_lane_slack;   // max over lane-tier rows of NM_LANE_TIER_MAX - max(n0,n1)  (-> shortest row)
   int n_le64, n_le104;  // class-binned calls: lane-tier rows whose network class is <= 64 / <= 104
   int n_filtered;       // candidates dropped by the coverage filter (0 => rows == candidates)
@@ -126,6 +127,7 @@ struct nm_summary {
   // every block adds to entry (blockIdx & 31): tens of thousands of atomics on ONE address serialise in L2
   int spread[32][4];
   int n_huge;                 // deep rows beyond the shared-memory deep tier (nm_huge.cu takes them)
+  int ds_deep_cursor;         // work queue of nm_downsample_deep_kernel (rows, in chunks of 256)
   int head_cursor;            // candidates the combine kernel listed for an armed head selection (nm_rank.cuh)
   int head_fail;              // that list could not give the head (too few / too many candidates): select the ordinary way
   int head_cut;               // exponent bin at which that selection reached `want` rows (0: none)

@@ -100,10 +100,7 @@ __global__ void __launch_bounds__(32 * kWarps) nm_downsample_kernel(const nm_ds_
       const int32_t src = a.k.row_pos_index[rr];
       const int cov = a.seg_cov[a.seg[src]];
       need = cov > 0 && (a.k.row_n0[rr] > cov || a.k.row_n1[rr] > cov);
-      if (need && (a.k.row_n0[rr] > NM_DS_MAX_N || a.k.row_n1[rr] > NM_DS_MAX_N)) {
-        *a.too_deep = 1;  // reported by the host as NM_ERR_TOO_DEEP
-        need = false;
-      }
+      if (need && (a.k.row_n0[rr] > NM_DS_MAX_N || a.k.row_n1[rr] > NM_DS_MAX_N)) need = false;  // nm_downsample_deep_kernel's
     }
     unsigned todo = __ballot_sync(0xffffffffu, need);
     while (todo) {
@@ -218,6 +215,177 @@ __global__ void __launch_bounds__(32 * kWarps) nm_downsample_kernel(const nm_ds_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Rows with more than NM_DS_MAX_N reads in a group: one CTA per row.
+// ------------------------------------------------------------------------------------------
+constexpr int kDeepThreads = 256;
+constexpr int kDeepWarps = kDeepThreads / 32;
+
+// ascending bitonic sort of s[0..P) by the CTA (P a power of two >= 2 * kDeepThreads; pads are +inf)
+__device__ __forceinline__ void nm_block_bitonic(float* s, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += kDeepThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const float x = s[lo], y = s[hi];
+        if ((x > y) == up) {
+          s[lo] = y;
+          s[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// number of elements <= v in the ascending array s[0..n)
+__device__ __forceinline__ int nm_upper_bound(const float* s, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kDeepThreads) nm_downsample_deep_kernel(const nm_ds_args a, float* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char nm_smem[];
+  float* sm = reinterpret_cast<float*>(nm_smem);  // the group being sorted | later: per-warp samples
+  __shared__ int s_rows[kDeepThreads];
+  __shared__ int s_n;
+  __shared__ long long s_base;
+  __shared__ int dres[NM_DS_MAX_TIMES];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  float* const srt0 = scratch + (size_t)blockIdx.x * 2 * NM_DS_DEEP_MAX_READS;
+  float* const srt1 = srt0 + NM_DS_DEEP_MAX_READS;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) {
+      s_base = (long long)atomicAdd(a.cursor, kDeepThreads);
+      s_n = 0;
+    }
+    __syncthreads();
+    const long long base = s_base;
+    if (base >= a.k.n_rows) break;
+    {
+      const int64_t rr = base + tid;
+      if (rr < a.k.n_rows) {
+        const int32_t src = a.k.row_pos_index[rr];
+        const int cov = a.seg_cov[a.seg[src]];
+        const int n0 = a.k.row_n0[rr], n1 = a.k.row_n1[rr];
+        if (cov > 0 && (n0 > cov || n1 > cov) && (n0 > NM_DS_MAX_N || n1 > NM_DS_MAX_N)) {
+          if (cov > NM_DS_DEEP_MAX_COV || (n0 > cov && n0 > NM_DS_DEEP_MAX_READS) || (n1 > cov && n1 > NM_DS_DEEP_MAX_READS))
+            atomicOr(a.too_deep, 2);  // reported by the host as NM_ERR_TOO_DEEP
+          else
+            s_rows[atomicAdd(&s_n, 1)] = tid;
+        }
+      }
+    }
+    __syncthreads();
+    const int n_list = s_n;
+    for (int q = 0; q < n_list; ++q) {
+      const int64_t r = base + s_rows[q];
+      const int32_t src = a.k.row_pos_index[r];
+      const int n0 = a.k.row_n0[r], n1 = a.k.row_n1[r];
+      const int cov = a.seg_cov[a.seg[src]];
+      const uint32_t cpos = (uint32_t)a.pos[src], cseg = (uint32_t)a.seg[src];
+      const bool ds0 = n0 > cov, ds1 = n1 > cov;
+      const int m0 = ds0 ? cov : n0, m1 = ds1 ? cov : n1;
+
+      // ---- 1. a down-sampled group is sorted (draws index its ascending values); the other is taken as it is
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int n = g ? n1 : n0;
+        const float* gv = g ? a.k.vals1 + a.k.off1[src] : a.k.vals0 + a.k.off0[src];
+        float* dst = g ? srt1 : srt0;
+        if (g ? ds1 : ds0) {
+          int P = 2 * kDeepThreads;
+          while (P < n) P <<= 1;
+          __syncthreads();
+          for (int t = tid; t < P; t += kDeepThreads) sm[t] = t < n ? gv[t] + 0.0f : INFINITY;
+          __syncthreads();
+          nm_block_bitonic(sm, P);
+          for (int t = tid; t < n; t += kDeepThreads) dst[t] = sm[t];
+        } else {
+          for (int t = tid; t < n; t += kDeepThreads) dst[t] = gv[t] + 0.0f;
+        }
+      }
+      __syncthreads();  // the sorted groups (global, written by this CTA) and the end of the use of sm as sort buffer
+
+      // ---- 2. a warp per resample: gather the draws, sort the two samples, rank every sampled value in both
+      float* S0 = sm + (size_t)wib * 2 * NM_DS_DEEP_MAX_COV;
+      float* S1 = S0 + NM_DS_DEEP_MAX_COV;
+      int P0 = 32, P1 = 32;
+      while (P0 < m0) P0 <<= 1;
+      while (P1 < m1) P1 <<= 1;
+      for (int i = wib; i < a.times; i += kDeepWarps) {
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int n = g ? n1 : n0, m = g ? m1 : m0, P = g ? P1 : P0;
+          const float* sg = g ? srt1 : srt0;
+          float* S = g ? S1 : S0;
+          if (g ? ds1 : ds0) {
+            for (int t = lane; t < P; t += 32) {
+              float v = INFINITY;
+              if (t < m) {
+                uint32_t w[4];
+                nm_philox4x32_10((uint32_t)(t >> 2), (uint32_t)i | ((uint32_t)g << 16), cpos, cseg, a.seed_lo, a.seed_hi, w);
+                const uint32_t word = (t & 3) == 0 ? w[0] : (t & 3) == 1 ? w[1] : (t & 3) == 2 ? w[2] : w[3];
+                v = sg[(int)(((unsigned long long)word * (unsigned long long)n) >> 32)];
+              }
+              S[t] = v;
+            }
+          } else {
+            for (int t = lane; t < P; t += 32) S[t] = t < m ? sg[t] : INFINITY;
+          }
+        }
+        __syncwarp();
+        nm_warp_bitonic(S0, P0, lane);
+        nm_warp_bitonic(S1, P1, lane);
+        int dmax = 0;
+        for (int k = lane; k < m0 + m1; k += 32) {
+          const float v = k < m0 ? S0[k] : S1[k - m0];
+          int d = nm_upper_bound(S0, m0, v) * m1 - nm_upper_bound(S1, m1, v) * m0;
+          d = d < 0 ? -d : d;
+          dmax = d > dmax ? d : dmax;
+        }
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0) dres[i] = dmax;
+        __syncwarp();
+      }
+      __syncthreads();
+
+      // ---- 3. the resample at sorted-p index `index` == the index-th largest numerator
+      if (wib == 0) {
+        int sel = -1;
+        for (int i = lane; i < a.times; i += 32) {
+          const int v = dres[i];
+          int greater = 0, equal = 0;
+          for (int t = 0; t < a.times; ++t) {
+            const int o = dres[t];
+            greater += o > v;
+            equal += o == v;
+          }
+          if (greater <= a.index && a.index < greater + equal) sel = v;
+        }
+        sel = __reduce_max_sync(0xffffffffu, sel);
+        if (lane == 0) {
+          double d, p;
+          nm_ks_tail(sel, m0, m1, &d, &p);
+          a.k.ks_dnum[r] = sel;
+          if (a.k.ks_d) a.k.ks_d[r] = d;
+          a.k.ks_p[r] = p;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 int nm_launch_downsample(const nm_kargs& ka, const int32_t* pos, const int32_t* seg, const int32_t* seg_cov, int times,
@@ -243,5 +411,34 @@ int nm_launch_downsample(const nm_kargs& ka, const int32_t* pos, const int32_t* 
   int64_t grid = (ka.n_rows + 32 * kWarps - 1) / (32 * kWarps);
   if (grid > (int64_t)blocks * sm_count) grid = (int64_t)blocks * sm_count;
   nm_downsample_kernel<<<(unsigned)grid, 32 * kWarps, (size_t)smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+size_t nm_downsample_deep_scratch_bytes(int sm_count) {
+  return sizeof(float) * 2 * (size_t)NM_DS_DEEP_MAX_READS * (size_t)(sm_count > 0 ? sm_count : 1);
+}
+
+int nm_launch_downsample_deep(const nm_kargs& ka, const int32_t* pos, const int32_t* seg, const int32_t* seg_cov, int times,
+                              int index, uint64_t seed, int* cursor, int* too_deep, float* scratch, int sm_count,
+                              cudaStream_t st) {
+  nm_ds_args a;
+  a.k = ka;
+  a.pos = pos;
+  a.seg = seg;
+  a.seg_cov = seg_cov;
+  a.times = times;
+  a.index = index;
+  a.seed_lo = (uint32_t)(seed & 0xffffffffu);
+  a.seed_hi = (uint32_t)(seed >> 32);
+  a.cursor = cursor;
+  a.too_deep = too_deep;
+  // the sort buffer (one group, padded to a power of two) and, afterwards, the warps' sample pairs
+  const size_t smem = sizeof(float) * (size_t)(NM_DS_DEEP_MAX_READS > kDeepWarps * 2 * NM_DS_DEEP_MAX_COV ? NM_DS_DEEP_MAX_READS
+                                                                                                         : kDeepWarps * 2 * NM_DS_DEEP_MAX_COV);
+  cudaError_t e = cudaFuncSetAttribute(nm_downsample_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int64_t grid = (ka.n_rows + kDeepThreads - 1) / kDeepThreads;
+  if (grid > sm_count) grid = sm_count;
+  nm_downsample_deep_kernel<<<(unsigned)grid, kDeepThreads, smem, st>>>(a, scratch);
   return (int)cudaGetLastError();
 }

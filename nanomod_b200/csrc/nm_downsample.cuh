@@ -15,3 +15,12 @@
 // launch; *too_deep becomes 1 if such a row has more than NM_DS_MAX_N reads in a group.
 int nm_launch_downsample(const nm_kargs& ka, const int32_t* pos, const int32_t* seg, const int32_t* seg_cov, int times,
                          int index, uint64_t seed, int* cursor, int* too_deep, int sm_count, cudaStream_t st);
+
+// Rows of that kind with MORE than NM_DS_MAX_N reads in a group (up to NM_DS_DEEP_MAX_READS; thresholds up to
+// NM_DS_DEEP_MAX_COV): one CTA per row -- the groups are sorted in shared memory and parked in `scratch`
+// (nm_downsample_deep_scratch_bytes), a warp per resample gathers its draws, sorts them and ranks them.  Same
+// random stream, same result definition.  *too_deep |= 2 for a row beyond these limits.
+size_t nm_downsample_deep_scratch_bytes(int sm_count);
+int nm_launch_downsample_deep(const nm_kargs& ka, const int32_t* pos, const int32_t* seg, const int32_t* seg_cov, int times,
+                              int index, uint64_t seed, int* cursor, int* too_deep, float* scratch, int sm_count,
+                              cudaStream_t st);

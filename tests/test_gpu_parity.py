@@ -411,11 +411,62 @@ def test_downsampling_branch(det, coverages, times, quantile):
 
 def test_downsampling_limits(det):
     p = nm.synthetic_pileup(50, 300, 20)
-    with pytest.raises(nm.NmError) as e:
-        det.detect(p, nm.DetectOptions(coverages="50"))
-    assert e.value.code == 5  # NM_ERR_TOO_DEEP: more than 256 reads in a down-sampled group
+    assert len(det.detect(p, nm.DetectOptions(coverages="50"))) == 50  # 300 reads: the block kernel's (round 1: refused)
     with pytest.raises(nm.OptionError):
         det.detect(p, nm.DetectOptions(coverages="50", downsampling=5000))
+    # beyond the block kernel: a threshold above 1024 at a position with more than 256 reads -- refused from the plan pass
+    q = nm.synthetic_pileup(20, 1500, 20)
+    with pytest.raises(nm.NmError) as e:
+        det.detect(q, nm.DetectOptions(coverages="1100"))
+    assert e.value.code == 5  # NM_ERR_TOO_DEEP
+    assert "1024" in str(e.value)
+
+
+@pytest.mark.parametrize("coverages,times,quantile", [("20-30", 100, 0.25), ("300", 40, 0.5)])
+def test_downsampling_branch_deep_positions(det, coverages, times, quantile):
+    """Positions to be down-sampled with MORE than 256 reads in a group (nm_downsample_deep_kernel: one CTA per
+    position, same seeded stream): bit-exact KS numerators against the scalar oracle, next to positions the
+    warp kernel takes and positions that are not down-sampled at all."""
+    rng = np.random.default_rng(78)
+    L = 48
+    c0 = rng.integers(6, 70, L).astype(np.int64)
+    c1 = rng.integers(6, 70, L).astype(np.int64)
+    deep = {3: (1500, 40), 4: (35, 2100), 9: (3000, 2600), 10: (257, 10), 20: (600, 600), 30: (4097, 280), 31: (200, 256),
+            40: (513, 512)}
+    for k, (a, b) in deep.items():
+        c0[k], c1[k] = a, b
+    off0 = np.concatenate([[0], np.cumsum(c0)])
+    off1 = np.concatenate([[0], np.cumsum(c1)])
+    shift = np.where(np.arange(L) % 10 == 0, 0.5, 0.0)
+    v0 = np.round(rng.normal(0, 1, off0[-1]), 2).astype(np.float32)
+    v1 = np.round(rng.normal(0, 1, off1[-1]) + np.repeat(shift, c1), 2).astype(np.float32)
+    seg = (np.arange(L) >= L // 2).astype(np.int32)
+    pos = np.concatenate([np.arange(L // 2), np.arange(L - L // 2)]).astype(np.int32)
+    p = nm.Pileup.from_arrays(v0, off0, v1, off1, pos, seg, seg_names=[("chrA", "+"), ("chrA", "-")])
+    opt = nm.DetectOptions(neighborPvalues=2, coverages=coverages, downsampling=times,
+                           downsampling_quantile=quantile, seed=99)
+    t = det.detect(p, opt)
+    d0, d1 = p.to_dicts()
+    mo = o.default_moptions(neighborPvalues=2, coverages=list(opt.coverage_pair()), downsampling=times,
+                            downsampling_quantile=quantile, seed=99)
+    mo["ds2"] = ["g0", "g1"]
+    mo["g0"], mo["g1"] = d0, d1
+    o.mfilter_coverage(mo)
+    o.mtest2(mo, strict=False)
+    assert len(t) == len(mo["sign_test"]) == L
+    n_deep_ds = 0
+    for r, (key, tests) in enumerate(mo["sign_test"]):
+        cov = opt.coverage_pair()[0 if key[1] == "+" else 1]
+        n0, n1 = int(t.n0[r]), int(t.n1[r])
+        m0, m1 = min(n0, cov), min(n1, cov)
+        n_deep_ds += (m0, m1) != (n0, n1) and max(n0, n1) > 256
+        (u, pu), (tt, pt), (d, pks), (z, pz) = tests
+        assert t.ks_dnum[r] == int(round(d * m0 * m1)), (r, key, n0, n1)
+        assert abs(t.ks_d[r] - d) <= 1e-12 and abs(t.ks_p[r] - pks) <= RTOL * pks
+        assert abs(t.u_p[r] - pu) <= RTOL * pu and abs(t.t_p[r] - pt) <= RTOL * pt
+        assert abs(t.stouffer_p[r] - pz) <= RTOL * pz
+    assert n_deep_ds >= 6
+    assert np.array_equal(det.detect(p, opt).ks_dnum, t.ks_dnum)
 
 
 @pytest.mark.parametrize("rank_use", ["pv", "st"])
