@@ -27,7 +27,7 @@ enum {
   NM_ERR_BAD_PARAM = 2,  /* option outside the reference's accepted range (NanoMod.py:66,74) */
   NM_ERR_CUDA = 3,       /* a CUDA runtime call failed                                       */
   NM_ERR_OOM = 4,        /* device or pinned-host allocation failed                          */
-  NM_ERR_TOO_DEEP = 5,   /* a position's coverage exceeds the deep tier's shared-memory cap  */
+  NM_ERR_TOO_DEEP = 5,   /* a position to be down-sampled is beyond NM_DS_DEEP_MAX_READS / _COV  */
   NM_ERR_NO_DEVICE = 6   /* no CUDA device / not an sm_100 device                            */
 };
 
