@@ -346,3 +346,22 @@ def test_native_table_text_equals_python_format(method, nb, tmp_path):
     empty = SignTestTable(options=opt, seg_names=t.seg_names, seg=t.seg[:0], pos=t.pos[:0], base=t.base[:0], n0=t.n0[:0],
                           n1=t.n1[:0], ks_dnum=t.ks_dnum[:0], ks_d=t.ks_d[:0], ks_p=t.ks_p[:0])
     assert empty.format_text() == b""
+
+
+def test_bench_and_entry_scripts_compile_and_parse_their_arguments():
+    """bench.py / __graft_entry__.py / the tools are run by the driver on a GPU box: a syntax error or a bad
+    argument table there would only show at round end."""
+    import py_compile
+    import subprocess
+    import sys
+    for rel in ("bench.py", "__graft_entry__.py", "tools/multi_gpu_check.py", "tools/bench_configs.py",
+                "tools/time_armed_head.py", "tools/time_head_select.py", "tools/summarize_profile.py"):
+        py_compile.compile(os.path.join(ROOT, rel), doraise=True)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, check=True).stdout
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--positions", "--coverage", "--nccl-heads"):
+        assert flag in out
+    sys.path.insert(0, ROOT)
+    import bench
+    cfg = bench.workload_config(1)
+    assert cfg["positions_per_gpu"] == 4_600_000 and cfg["coverage"] == [100, 100] and "workload" in cfg
+    assert "peer" in bench.workload_config(8)["parallelism"]
