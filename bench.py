@@ -7,12 +7,15 @@ filter, per-position KS test, window combination) over one synthetic pileup:
 BASELINE.json configs[1] -- E. coli K-12 scale, 4.6 Mb, 2x100x, float32 Gaussian currents with
 planted shifted sites.
 
-  value      whole-job positions/s with the pileup already resident in HBM.  N = 1:
-             ``Detector.detect_device`` (nm_detect_device).  N > 1 (weak scaling: every rank holds its
-             own 4.6 Mb shard plus a halo): the product's sharded path,
-             ``ShardedDetector.detect_shard`` + ``gather_heads`` -- the table stays sharded, each
-             rank selects the head of its own ranking (nm_rank_head_device) and the heads are
-             all-gathered over NCCL: the only communication, inside the timed region.
+  value      whole-job positions/s with the pileup already resident in HBM.  Steps go through the
+             queued entry (nm_detect_device_async / nm_detect_finish): the host stays one step ahead
+             of the device, every step is validated (finished) inside the timed region.  N = 1:
+             ``Detector.detect_device_async``.  N > 1 (weak scaling: every rank holds its own 4.6 Mb
+             shard plus a halo): the product's sharded path, ``ShardedDetector.detect_shard_async`` /
+             ``finish_shard`` -- the table stays sharded, each rank selects the head of its own ranking
+             behind the step's kernels, and the selection kernels store it into every rank's buffer
+             over NVLink (peer-mapped HBM; ``--nccl-heads``, or a node without peer mapping: one NCCL
+             all-gather per step): the only communication, completed inside the timed region.
   e2e        the same through the host-facing API with pinned HOST buffers: H2D + kernels + D2H
              (+ the head exchange at N > 1) in the timed region
   roofline   the lane kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
