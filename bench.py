@@ -57,7 +57,7 @@ BYTES_PER_POS = 4 * (COV + COV) + 16 + 28  # fp32 values + two int
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 HEAD_WANT = 1024           # rows of each rank's ranking head exchanged per step at N > 1
 HEAD_CAP = 4096            # record capacity of the exchange buffer (48-byte records)
-SM_RESERVE = 2             # SMs the persistent lane kernel leaves to NCCL's copy kernel at N > 1
+SM_RESERVE = 2             # NCCL heads only (--nccl-heads / no peer mapping): SMs the persistent lane kernel leaves to NCCL
 
 
 def workload_config(n_gpus: int, positions: int = GENOME):
