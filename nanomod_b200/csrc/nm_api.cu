@@ -1044,6 +1044,7 @@ extern "C" int nm_detect_device(nm_handle* h, const nm_pileup* pl, const nm_para
                                 const nm_table* tb, int64_t* n_rows_out, void* cuda_stream) {
   if (!h) return nm_fail(nullptr, NM_ERR_BAD_ARG, "handle is NULL");
   h->head.fired = 0;
+  h->head.use_cands = 0;  // set again by this call's own combine launch, if it lists candidates
   const int rc = nm_detect_device_impl(h, pl, params, tb, n_rows_out, cuda_stream);
   h->head.armed = 0;  // one shot (nm_arm_head_select)
   if (rc != NM_OK) h->head.fired = 0;
@@ -1326,6 +1327,7 @@ extern "C" int nm_detect_device_async(nm_handle* h, const nm_pileup* pl, const n
     return NM_OK;
   }
   h->head.fired = 0;
+  h->head.use_cands = 0;
   if ((rc = nm_check_call(h, pl, prm, tb)) != NM_OK) { h->head.armed = 0; return rc; }
   NM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
